@@ -1,0 +1,168 @@
+/*
+ * mixq_b200.h -- C ABI of the B200-native W8A8O16 mixed-precision linear.
+ *
+ * This is the drop-in boundary for the hot path behind
+ * TsinghuaMixQPlugin::enqueue (reference TsinghuaMixQPlugin.cpp:384-765).
+ * Everything above it (the IPluginV2DynamicExt adapter in
+ * mixq_tensorrt_llm_b200/csrc/mixq_plugin.{h,cpp}, the Python MixQLinear mirror,
+ * the tests and bench.py) calls ONLY these entry points.  No torch / TensorRT
+ * types appear in any signature: plain pointers, sizes and a cudaStream_t
+ * passed as void*.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative mixq_status on error,
+ *     never throws, never calls exit() (the reference ignores cuBLAS/CUTLASS
+ *     status and always returns 0: TsinghuaMixQPlugin.cpp:402,752;
+ *     kernel/i8gemm.cu:190-192 -- we report instead);
+ *   - device functions are asynchronous on `stream`, perform no allocation and
+ *     no host synchronisation, and are CUDA-graph-capture safe;
+ *   - there is NO CPU fallback: without a CUDA device these calls fail with
+ *     MIXQ_ERR_CUDA.
+ */
+#ifndef MIXQ_B200_H_
+#define MIXQ_B200_H_
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIXQ_NUM_OUTLIERS 128 /* num_ind: TsinghuaMixQPlugin.cpp:518; fp_features: model_config_utils.py:446 */
+
+typedef enum mixq_status {
+    MIXQ_OK = 0,
+    MIXQ_ERR_BAD_ARG = -1,    /* null pointer, non-positive dim, misaligned pointer/stride */
+    MIXQ_ERR_WORKSPACE = -2,  /* workspace too small */
+    MIXQ_ERR_CUDA = -3,       /* a CUDA runtime/driver call or launch failed (see mixq_last_error) */
+    MIXQ_ERR_UNSUPPORTED = -4 /* shape outside what the kernels support (see mixq_enqueue) */
+} mixq_status;
+
+/* Flags for mixq_enqueue / mixq_quant_extract. Default (0) is the TensorRT plugin's behaviour. */
+enum {
+    /* Zero A[:, ind] before the per-token amax/quantize, as MixQ/src does
+     * (MixQ/src/kernel/mix_cuda/cult.cu:1588); the plugin copy has that store
+     * commented out (kernel/i8gemm.cu:218). */
+    MIXQ_FLAG_MASK_OUTLIERS = 1u << 0,
+    /* Skip the M<=4 weight-only branch (TsinghuaMixQPlugin.cpp:472,641-647) and
+     * run the mixed W8A8O16 path for every M. */
+    MIXQ_FLAG_FORCE_MIXED = 1u << 1
+};
+
+/* The seven plugin inputs + one output, in the order of plugin.py:142-150 /
+ * TsinghuaMixQPlugin.cpp:425-445. All are device pointers. The TensorRT side
+ * types every tensor as kHALF; the true element types are given here. */
+typedef struct mixq_tensors {
+    const void* A;               /* [M, K]  fp16 activations (input 0)                           */
+    const void* W8;              /* [N, K]  int8 weights, outlier columns zeroed (input 1)       */
+    const void* scale_b;         /* [N]     fp16 per-output-channel weight scale (input 2)       */
+    const void* fp_weight;       /* [N,128] fp16 outlier weight columns (input 3)                */
+    const void* ind;             /* [128]   int32 outlier column indices (input 4)               */
+    const void* q_weight;        /* [K, N]  int8 weight-only layout, M<=4 branch only (input 5)  */
+    const void* scaling_factors; /* [N]     fp16 scales for q_weight (input 6)                   */
+    void* Out;                   /* [M, N]  fp16 output                                          */
+} mixq_tensors;
+
+/* Library identity. */
+const char* mixq_version(void);
+/* Human-readable text for the last failing call on this thread ("" if none). */
+const char* mixq_last_error(void);
+/* 1 when a CUDA device of compute capability 10.x is usable, else 0. */
+int mixq_device_ok(void);
+
+/* Bytes of device workspace mixq_enqueue needs for (M, N, K). Layout (each
+ * block 128-byte aligned, as nextWorkspacePtr does, TsinghuaMixQPlugin.cpp:206-215):
+ *   A8 int8 [M,K] | scale_a fp16 [M] | fp_A fp16 [M,128]
+ * Replaces the reference's max(M*K + 2M + 2*K*N, 16*M*N) (TsinghuaMixQPlugin.cpp:342-346). */
+size_t mixq_workspace_size(int64_t M, int64_t N, int64_t K);
+
+/* The hot path: replaces MixQPlugin::enqueueImpl's M>4 branch
+ * (TsinghuaMixQPlugin.cpp:472-532: ExtractOutliersAndSetToZeros -> cublasGemmEx
+ * fp16 -> int8quant -> int8FusedDequantizeCUDA) with two launches:
+ *   1. mixq_quant_extract   (per-token INT8 quantize + outlier gather)
+ *   2. mixq_gemm_dequant    (tcgen05 INT8 GEMM + fused FP16 outlier GEMM + dequant)
+ *
+ *   Out[m,n] = fp16( float(sum_k A8[m,k]*W8[n,k]) * (float(sb[n])*float(sa[m]))
+ *                    + float(fp16(sum_j fp_A[m,j]*fp_weight[n,j])) )
+ *
+ * Requirements: K % 16 == 0, N % 8 == 0, all pointers 16-byte aligned, `ind`
+ * values in [0, K). M may be any positive value (M == 0 is a no-op).
+ * For M <= 4 the reference switches to a weight-only GEMV over q_weight
+ * (TsinghuaMixQPlugin.cpp:641-647); this build runs the mixed path for every M
+ * (see DESIGN.md "M<=4").  */
+int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace,
+                 size_t workspace_bytes, unsigned flags, void* stream);
+
+/* Stage 1 alone. Replaces int8quant (kernel/i8gemm.cu:66-107,139-150) and
+ * ExtractOutliersAndSetToZeros (kernel/i8gemm.cu:198-244) in one pass over A.
+ *   sa[m]   = hdiv(max_k |A[m,k]|, 127)
+ *   A8[m,k] = int8(half2int_rn(hdiv(A[m,k], sa[m])))
+ *   fp_A[m,j] = A[m, ind[j]]   (j < n_ind; fp_A row stride = n_ind)
+ * fp_A/ind may be NULL (n_ind = 0) to quantize only. */
+int mixq_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8,
+                       void* scale_a, void* fp_A, unsigned flags, void* stream);
+
+/* Stage 2 alone. Replaces cublasGemmEx fp16 (TsinghuaMixQPlugin.cpp:122-161) +
+ * int8FusedDequantizeCUDA (kernel/i8gemm.cu:151-194) in one kernel.
+ * fp_A/fp_weight may both be NULL: then the addend is 0 (plain W8A8 dequant GEMM). */
+int mixq_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b,
+                      const void* fp_A, const void* fp_weight, void* Out, int64_t M, int64_t N,
+                      int64_t K, void* stream);
+
+/* End-to-end call with HOST buffers for the per-call tensors: copies A (host,
+ * fp16 [M,K]) to the device, runs mixq_enqueue with the device-resident weights
+ * in `t` (t->A and t->Out are ignored), copies Out back to `Out_host`
+ * (fp16 [M,N]) and synchronises `stream`.  `dev_scratch` must hold
+ * mixq_host_scratch_size(M,N,K) bytes of device memory.  This is the call
+ * bench.py times for its `e2e` figure. */
+size_t mixq_host_scratch_size(int64_t M, int64_t N, int64_t K);
+int mixq_linear_host(const mixq_tensors* t, const void* A_host, void* Out_host, int64_t M,
+                     int64_t N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes,
+                     unsigned flags, void* stream);
+
+/* Kernel launches issued by this library since load (all threads); bench.py
+ * reads it to fill `gpu_launches`. */
+uint64_t mixq_launch_count(void);
+
+/* GEMM tile configuration override for tuning/tests: 0 = auto. Returns the
+ * previous value. Valid ids are listed in DESIGN.md. */
+int mixq_set_gemm_config(int config_id);
+
+/* ---- TensorRT plugin surface through C handles (for ctypes / C callers) ----
+ * Mirrors MixQPluginCreator / MixQPlugin (TsinghuaMixQPlugin.h:34-115). */
+typedef struct mixq_plugin_s mixq_plugin_t;
+
+/* Same symbol and signature as the reference (MixQPlugins.cpp:126-132); loaded by
+ * ctypes.CDLL(...).initOpenAiTritonPlugins(None, b"tensorrt_llm") in plugin.py:34-43. */
+bool initOpenAiTritonPlugins(void* logger, const char* libNamespace);
+
+/* creator.createPlugin(name, {m,n,k}) -- TsinghuaMixQPlugin.cpp:895-933. NULL if the
+ * ("MixQ","1",ns) creator is not registered. */
+mixq_plugin_t* mixq_plugin_create(const char* ns, int m, int n, int k);
+/* creator.deserializePlugin -- TsinghuaMixQPlugin.cpp:935-952 (12 bytes: mm,mn,mk int32 LE). */
+mixq_plugin_t* mixq_plugin_deserialize(const char* ns, const void* data, size_t len);
+mixq_plugin_t* mixq_plugin_clone(const mixq_plugin_t* p);
+void mixq_plugin_destroy(mixq_plugin_t* p);
+const char* mixq_plugin_type(const mixq_plugin_t* p);      /* "MixQ" */
+const char* mixq_plugin_version(const mixq_plugin_t* p);   /* "1"    */
+const char* mixq_plugin_namespace(const mixq_plugin_t* p);
+int mixq_plugin_nb_outputs(const mixq_plugin_t* p);
+size_t mixq_plugin_serialization_size(const mixq_plugin_t* p);
+void mixq_plugin_serialize(const mixq_plugin_t* p, void* buffer);
+/* supportsFormatCombination(pos, ...) with type/format codes of nvinfer1 (kHALF=1, kLINEAR=0). */
+int mixq_plugin_supports_format(const mixq_plugin_t* p, int pos, int dtype_code, int format_code);
+/* configurePlugin + getWorkspaceSize for the given maxima. */
+size_t mixq_plugin_workspace_size(mixq_plugin_t* p, const int64_t* a_max_dims, int a_nb_dims,
+                                  int64_t n);
+/* enqueue(inputDesc, outputDesc, inputs, outputs, workspace, stream):
+ * a_dims/a_nb_dims describe input 0 ([..., K]); w_dim0 = inputDesc[1].dims.d[0] = N. */
+int mixq_plugin_enqueue(mixq_plugin_t* p, const int64_t* a_dims, int a_nb_dims, int64_t w_dim0,
+                        const void* const* inputs, void* const* outputs, void* workspace,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIXQ_B200_H_ */

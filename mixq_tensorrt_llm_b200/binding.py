@@ -1,0 +1,157 @@
+"""ctypes binding of libmixq_b200.so (the C ABI in include/mixq_b200.h).
+
+There is no fallback of any kind: if the shared library is missing this module raises, and
+every compute entry point raises ``MixQError`` when the library reports a failure (for example
+no sm_100 device).  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libmixq_b200.so"
+
+NUM_OUTLIERS = 128
+FLAG_MASK_OUTLIERS = 1
+FLAG_FORCE_MIXED = 2
+
+# every symbol include/mixq_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_enqueue",
+    "mixq_quant_extract", "mixq_gemm_dequant", "mixq_host_scratch_size", "mixq_linear_host",
+    "mixq_launch_count", "mixq_set_gemm_config", "initOpenAiTritonPlugins", "mixq_plugin_create",
+    "mixq_plugin_deserialize", "mixq_plugin_clone", "mixq_plugin_destroy", "mixq_plugin_type",
+    "mixq_plugin_version", "mixq_plugin_namespace", "mixq_plugin_nb_outputs",
+    "mixq_plugin_serialization_size", "mixq_plugin_serialize", "mixq_plugin_supports_format",
+    "mixq_plugin_workspace_size", "mixq_plugin_enqueue",
+]
+
+
+class MixQError(RuntimeError):
+    pass
+
+
+class Tensors(ctypes.Structure):
+    """struct mixq_tensors"""
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("A", "W8", "scale_b", "fp_weight", "ind", "q_weight", "scaling_factors", "Out")]
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libmixq_b200.so; raises if it has not been built (python -m mixq_tensorrt_llm_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise MixQError(f"{LIB_PATH} not found: build it with `python -m mixq_tensorrt_llm_b200.build` "
+                        "(there is no CPU or PyTorch fallback)")
+    L = ctypes.CDLL(str(LIB_PATH), mode=ctypes.RTLD_GLOBAL)
+    vp, i64, sz, u32, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t, ctypes.c_uint, ctypes.c_int
+    L.mixq_version.restype = ctypes.c_char_p
+    L.mixq_last_error.restype = ctypes.c_char_p
+    L.mixq_device_ok.restype = ci
+    L.mixq_workspace_size.restype = sz
+    L.mixq_workspace_size.argtypes = [i64, i64, i64]
+    L.mixq_enqueue.restype = ci
+    L.mixq_enqueue.argtypes = [ctypes.POINTER(Tensors), i64, i64, i64, vp, sz, u32, vp]
+    L.mixq_quant_extract.restype = ci
+    L.mixq_quant_extract.argtypes = [vp, i64, i64, vp, ci, vp, vp, vp, u32, vp]
+    L.mixq_gemm_dequant.restype = ci
+    L.mixq_gemm_dequant.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
+    L.mixq_host_scratch_size.restype = sz
+    L.mixq_host_scratch_size.argtypes = [i64, i64, i64]
+    L.mixq_linear_host.restype = ci
+    L.mixq_linear_host.argtypes = [ctypes.POINTER(Tensors), vp, vp, i64, i64, i64, vp, sz, u32, vp]
+    L.mixq_launch_count.restype = ctypes.c_uint64
+    L.mixq_set_gemm_config.restype = ci
+    L.mixq_set_gemm_config.argtypes = [ci]
+    L.initOpenAiTritonPlugins.restype = ctypes.c_bool
+    L.initOpenAiTritonPlugins.argtypes = [vp, ctypes.c_char_p]
+    L.mixq_plugin_create.restype = vp
+    L.mixq_plugin_create.argtypes = [ctypes.c_char_p, ci, ci, ci]
+    L.mixq_plugin_deserialize.restype = vp
+    L.mixq_plugin_deserialize.argtypes = [ctypes.c_char_p, vp, sz]
+    L.mixq_plugin_clone.restype = vp
+    L.mixq_plugin_clone.argtypes = [vp]
+    L.mixq_plugin_destroy.restype = None
+    L.mixq_plugin_destroy.argtypes = [vp]
+    for f in ("type", "version", "namespace"):
+        getattr(L, "mixq_plugin_" + f).restype = ctypes.c_char_p
+        getattr(L, "mixq_plugin_" + f).argtypes = [vp]
+    L.mixq_plugin_nb_outputs.restype = ci
+    L.mixq_plugin_nb_outputs.argtypes = [vp]
+    L.mixq_plugin_serialization_size.restype = sz
+    L.mixq_plugin_serialization_size.argtypes = [vp]
+    L.mixq_plugin_serialize.restype = None
+    L.mixq_plugin_serialize.argtypes = [vp, vp]
+    L.mixq_plugin_supports_format.restype = ci
+    L.mixq_plugin_supports_format.argtypes = [vp, ci, ci, ci]
+    L.mixq_plugin_workspace_size.restype = sz
+    L.mixq_plugin_workspace_size.argtypes = [vp, ctypes.POINTER(i64), ci, i64]
+    L.mixq_plugin_enqueue.restype = ci
+    L.mixq_plugin_enqueue.argtypes = [vp, ctypes.POINTER(i64), ci, i64, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise MixQError(f"{what} failed with status {rc}: {load().mixq_last_error().decode()}")
+
+
+def require_device() -> None:
+    if not load().mixq_device_ok():
+        raise MixQError("libmixq_b200 needs a CUDA device of compute capability 10.x (B200); none is usable "
+                        "and there is no fallback path")
+
+
+# ------------------------------------------------------------------ torch-facing helpers
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def workspace_size(M: int, N: int, K: int) -> int:
+    return int(load().mixq_workspace_size(M, N, K))
+
+
+def make_tensors(A, W8, scale_b, fp_weight, ind, Out, q_weight=None, scaling_factors=None) -> Tensors:
+    t = Tensors()
+    t.A, t.W8, t.scale_b, t.fp_weight, t.ind = (x.data_ptr() if x is not None else None
+                                               for x in (A, W8, scale_b, fp_weight, ind))
+    t.q_weight = q_weight.data_ptr() if q_weight is not None else None
+    t.scaling_factors = scaling_factors.data_ptr() if scaling_factors is not None else None
+    t.Out = Out.data_ptr() if Out is not None else None
+    return t
+
+
+def enqueue(A, W8, scale_b, fp_weight, ind, Out, workspace, flags: int = 0, stream=None) -> None:
+    """mixq_enqueue on torch CUDA tensors (A [M,K] fp16 contiguous, Out [M,N] fp16)."""
+    M, K = A.shape
+    N = Out.shape[-1]
+    t = make_tensors(A, W8, scale_b, fp_weight, ind, Out)
+    check(load().mixq_enqueue(ctypes.byref(t), M, N, K, _ptr(workspace), workspace.numel() * workspace.element_size(),
+                              flags, _stream(stream)), "mixq_enqueue")
+
+
+def quant_extract(A, ind, A8, scale_a, fp_A, flags: int = 0, stream=None) -> None:
+    M, K = A.shape
+    n_ind = 0 if ind is None else ind.numel()
+    check(load().mixq_quant_extract(_ptr(A), M, K, _ptr(ind), n_ind, _ptr(A8), _ptr(scale_a), _ptr(fp_A), flags,
+                                    _stream(stream)), "mixq_quant_extract")
+
+
+def gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, stream=None) -> None:
+    M, K = A8.shape
+    N = W8.shape[0]
+    check(load().mixq_gemm_dequant(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A), _ptr(fp_weight),
+                                   _ptr(Out), M, N, K, _stream(stream)), "mixq_gemm_dequant")

@@ -1,0 +1,406 @@
+// gemm_i8_tcgen05.cu -- stage 2 of the W8A8O16 path: ONE kernel that
+//   (a) contracts A8[M,K] (int8) with W8[N,K]^T (int8) on the tcgen05 INT8 tensor cores
+//       (tcgen05.mma.kind::i8, 128 x BLOCK_N x 32 per instruction, int32 accumulators in TMEM),
+//   (b) contracts the 128 outlier columns fp_A[M,128] x fp_weight[N,128]^T with
+//       tcgen05.mma.kind::f16 into a second (fp32) TMEM accumulator, and
+//   (c) dequantises in the epilogue:
+//          Out[m,n] = fp16( fma( float(acc_i32), float(sb[n]) * float(sa[m]), float(fp16(acc_f32)) ) )
+//
+// It replaces two reference launches and the fp16 round trip between them:
+//   gemmfp16 / cublasGemmEx            (TsinghuaMixQPlugin.cpp:122-161, called at :521)
+//   int8FusedDequantizeCUDA / CUTLASS  (kernel/i8gemm.cu:151-194; mainloop
+//       kernel/symmetric/gemm/kernel/gemm_dequant.h:224-292, epilogue
+//       kernel/symmetric/epilogue/thread/linear_combination_dequant.h:152-157)
+// The inner fp16() in (c) reproduces the reference's rounding of the outlier product when
+// cuBLAS stores it to `Out` before the CUTLASS epilogue reads it back as the addend.
+//
+// Structure (persistent, warp specialised, 256 threads, 1 CTA / SM):
+//   warp 0   TMA producer: fills a ring of kStages smem slots, each one K-block of
+//            A (128 rows x 128 B) and of W (BLOCK_N rows x 128 B), 128B-swizzled.  The outlier
+//            slab rides the same ring as two extra K-blocks of 64 fp16 columns (same footprint).
+//   warp 1   MMA issuer: one elected thread issues 4 tcgen05.mma per slot and commits the slot's
+//            "empty" barrier; after the last K-block it commits the accumulator's "full" barrier.
+//   warp 2   TMEM allocator (alloc before, dealloc after).
+//   warps 4-7 epilogue: tcgen05.ld both accumulators (32 lanes x 32 columns per warp and step),
+//            dequantise in registers, 16-byte global stores.  With kAccStages = 2 the epilogue of
+//            tile i overlaps the main loop of tile i+1.
+// Barriers: full[kStages] (TMA -> MMA, tx bytes), empty[kStages] (MMA -> TMA, tcgen05.commit),
+//           tmem_full[kAccStages] (MMA -> epilogue), tmem_empty[kAccStages] (epilogue -> MMA).
+#include <cstdio>
+#include <mutex>
+
+#include "mixq_internal.h"
+#include "ptx.cuh"
+
+namespace mixq {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockKBytes = 128;  // one 128B swizzle atom per row per K-block
+constexpr int kUmmaKBytes = 32;    // K=32 int8 / K=16 fp16 per tcgen05.mma
+constexpr int kGemmThreads = 256;
+constexpr int kEpilogueWarp0 = 4;
+constexpr int kNumEpilogueThreads = 128;
+constexpr int kOutlierKBlocks = (MIXQ_NUM_OUTLIERS * 2) / kBlockKBytes;  // 2
+
+template <int BLOCK_N, int ACC_STAGES, int STAGES>
+struct GemmTraits {
+    static constexpr int kBlockN = BLOCK_N;
+    static constexpr int kAccStages = ACC_STAGES;
+    static constexpr int kStages = STAGES;
+    static constexpr int kABytes = kBlockM * kBlockKBytes;
+    static constexpr int kBBytes = BLOCK_N * kBlockKBytes;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kAccCols = 2 * BLOCK_N;  // int32 accumulator | fp32 outlier accumulator
+    static constexpr int kTmemColsRaw = kAccCols * ACC_STAGES;
+    static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : kTmemColsRaw <= 64 ? 64 : kTmemColsRaw <= 128 ? 128
+                                     : kTmemColsRaw <= 256 ? 256 : 512;
+    static_assert(kTmemColsRaw <= 512, "TMEM has 512 columns");
+    static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
+    // dynamic smem: ring | sb staging (2 x BLOCK_N floats) | barriers | tmem ptr  (+1024 alignment slack)
+    static constexpr int kNumBarriers = 2 * STAGES + 2 * ACC_STAGES;
+    static constexpr size_t kSmemBytes =
+        1024 + static_cast<size_t>(STAGES) * kStageBytes + 2 * BLOCK_N * sizeof(float) + kNumBarriers * 8 + 16;
+};
+
+struct TileCoord {
+    int m_blk, n_blk;
+};
+// Grouped rasterisation: tiles are walked in bands of `group_m` row-blocks, M fastest inside a
+// band, so the CTAs of one wave share a few A row-blocks and a few W row-blocks in L2.
+__device__ __forceinline__ TileCoord tile_coord(int tile, int m_tiles, int n_tiles, int group_m) {
+    const int per_group = group_m * n_tiles;
+    const int g = tile / per_group;
+    const int first_m = g * group_m;
+    const int gsz = min(m_tiles - first_m, group_m);
+    const int r = tile - g * per_group;
+    return {first_m + r % gsz, r / gsz};
+}
+
+template <class T>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_w8,
+                         const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fw,
+                         const __half* __restrict__ scale_a, const __half* __restrict__ scale_b,
+                         __half* __restrict__ Out, int M, int N, int K, int has_outlier, int m_tiles, int n_tiles,
+                         int group_m) {
+    constexpr int BLOCK_N = T::kBlockN;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;
+    float* sb_s = reinterpret_cast<float*>(ring + static_cast<size_t>(T::kStages) * T::kStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sb_s + 2 * BLOCK_N);
+    uint64_t* empty_bar = full_bar + T::kStages;
+    uint64_t* tmem_full_bar = empty_bar + T::kStages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + T::kAccStages;
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty_bar + T::kAccStages);
+
+    const int warp_idx = threadIdx.x >> 5;  // warp-uniform
+    const int lane = threadIdx.x & 31;
+
+    if (warp_idx == 0 && ptx::elect_one()) {
+        ptx::prefetch_tensormap(&tm_a8);
+        ptx::prefetch_tensormap(&tm_w8);
+        if (has_outlier) {
+            ptx::prefetch_tensormap(&tm_fa);
+            ptx::prefetch_tensormap(&tm_fw);
+        }
+    }
+    if (warp_idx == 1 && ptx::elect_one()) {
+        for (int i = 0; i < T::kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < T::kAccStages; ++i) {
+            ptx::mbar_init(&tmem_full_bar[i], 1);
+            ptx::mbar_init(&tmem_empty_bar[i], kNumEpilogueThreads / 32);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp_idx == 2) {
+        ptx::tmem_alloc(tmem_ptr_s, T::kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    // Everything above overlaps the tail of the previous kernel (PDL); A8/sa/fp_A are produced by it.
+    ptx::pdl_wait_prior_grid();
+
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = (K + kBlockKBytes - 1) / kBlockKBytes;
+    const int n_f = has_outlier ? kOutlierKBlocks : 0;
+    const int num_items = n_f + num_kb;
+
+    if (warp_idx == 0) {
+        if (ptx::elect_one()) {
+            // ===================== TMA producer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, group_m);
+                const int m0 = tc.m_blk * kBlockM;
+                const int n0 = tc.n_blk * BLOCK_N;
+                for (int it = 0; it < num_items; ++it) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], T::kStageBytes);
+                    uint8_t* sA = ring + static_cast<size_t>(stage) * T::kStageBytes;
+                    uint8_t* sB = sA + T::kABytes;
+                    if (it < n_f) {
+                        ptx::tma_load_2d(sA, &tm_fa, &full_bar[stage], it * (kBlockKBytes / 2), m0, ptx::kEvictNormal);
+                        ptx::tma_load_2d(sB, &tm_fw, &full_bar[stage], it * (kBlockKBytes / 2), n0, ptx::kEvictNormal);
+                    } else {
+                        const int k0 = (it - n_f) * kBlockKBytes;
+                        ptx::tma_load_2d(sA, &tm_a8, &full_bar[stage], k0, m0, ptx::kEvictNormal);
+                        ptx::tma_load_2d(sB, &tm_w8, &full_bar[stage], k0, n0, ptx::kEvictNormal);
+                    }
+                    if (++stage == T::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp_idx == 1) {
+        if (ptx::elect_one()) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t idesc_i8 = ptx::make_idesc_i8(kBlockM, BLOCK_N);
+            constexpr uint32_t idesc_f16 = ptx::make_idesc_f16(kBlockM, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc_stage = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
+                ptx::tc_fence_after_sync();
+                const uint32_t tmem_i = tmem_base + acc_stage * T::kAccCols;
+                const uint32_t tmem_f = tmem_i + BLOCK_N;
+                for (int it = 0; it < num_items; ++it) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after_sync();
+                    const uint32_t sA = ptx::smem_u32(ring + static_cast<size_t>(stage) * T::kStageBytes);
+                    const uint64_t da = ptx::make_smem_desc_sw128(sA);
+                    const uint64_t db = ptx::make_smem_desc_sw128(sA + T::kABytes);
+                    if (it < n_f) {
+#pragma unroll
+                        for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k)
+                            ptx::umma_f16(tmem_f, da + k * (kUmmaKBytes >> 4), db + k * (kUmmaKBytes >> 4), idesc_f16,
+                                          (it > 0 || k > 0) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k)
+                            ptx::umma_i8(tmem_i, da + k * (kUmmaKBytes >> 4), db + k * (kUmmaKBytes >> 4), idesc_i8,
+                                         (it > n_f || k > 0) ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
+                    if (++stage == T::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                ptx::umma_commit(&tmem_full_bar[acc_stage]);  // accumulators complete
+                if (++acc_stage == T::kAccStages) {
+                    acc_stage = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp_idx >= kEpilogueWarp0) {
+        // ===================== epilogue =====================
+        const int quarter = warp_idx - kEpilogueWarp0;  // == warp_idx % 4: the TMEM lane quarter this warp may read
+        const int et = threadIdx.x - kEpilogueWarp0 * 32;
+        const int row = quarter * 32 + lane;
+        int acc_stage = 0;
+        uint32_t acc_phase = 0;
+        int local_tile = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+            const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, group_m);
+            const int m0 = tc.m_blk * kBlockM;
+            const int n0 = tc.n_blk * BLOCK_N;
+            float* sbt = sb_s + (local_tile & 1) * BLOCK_N;
+            for (int j = et; j < BLOCK_N; j += kNumEpilogueThreads)
+                sbt[j] = (n0 + j < N) ? __half2float(scale_b[n0 + j]) : 0.0f;
+            const int gm = m0 + row;
+            const bool row_ok = gm < M;
+            const float sa_f = row_ok ? __half2float(scale_a[gm]) : 0.0f;
+            ptx::named_bar_sync(1, kNumEpilogueThreads);
+
+            ptx::mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
+            ptx::tc_fence_after_sync();
+            const uint32_t t_i = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_stage * T::kAccCols;
+            __half* out_row = Out + static_cast<size_t>(gm) * N + n0;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t vi[32], vf[32];
+                ptx::tmem_ld_32x32(t_i + c * 32, vi);
+                if (has_outlier) {
+                    ptx::tmem_ld_32x32(t_i + BLOCK_N + c * 32, vf);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) vf[j] = 0u;
+                }
+                ptx::tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = __fmul_rn(sbt[c * 32 + j], sa_f);
+                    const float p1 = __fmul_rn(sbt[c * 32 + j + 1], sa_f);
+                    // outlier product: fp32 accumulator -> fp16 (the reference's store to Out) -> fp32 addend
+                    const __half2 o = __floats2half2_rn(__uint_as_float(vf[j]), __uint_as_float(vf[j + 1]));
+                    const float2 of = __half22float2(o);
+                    const float r0 = __fmaf_rn(__int2float_rn(static_cast<int>(vi[j])), p0, of.x);
+                    const float r1 = __fmaf_rn(__int2float_rn(static_cast<int>(vi[j + 1])), p1, of.y);
+                    const __half2 r = __floats2half2_rn(r0, r1);
+                    packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&r);
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (n0 + c * 32 + g * 8 + 8 <= N)
+                            ptx::st_global_v4(out_row + c * 32 + g * 8, packed[g * 4], packed[g * 4 + 1],
+                                              packed[g * 4 + 2], packed[g * 4 + 3]);
+                    }
+                }
+            }
+            // hand the accumulator stage back to the MMA warp
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
+            if (++acc_stage == T::kAccStages) {
+                acc_stage = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    // teardown
+    ptx::pdl_launch_dependents();
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp_idx == 2) ptx::tmem_dealloc(tmem_base, T::kTmemCols);
+}
+
+// ---------------------------------------------------------------- host side
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 2D row-major [rows, cols] tensor of `elem_bytes` elements, box = 128 bytes x box_rows, 128B swizzle.
+int make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols,
+              uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return set_error(MIXQ_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * static_cast<uint64_t>(elem_bytes)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockKBytes / elem_bytes), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        static thread_local char buf[160];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed: CUresult %d (rows=%llu cols=%llu elem=%d)", (int)r,
+                 (unsigned long long)rows, (unsigned long long)cols, elem_bytes);
+        return set_error(MIXQ_ERR_CUDA, buf);
+    }
+    return MIXQ_OK;
+}
+
+template <class T>
+int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
+               const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl) {
+    const DeviceInfo& dev = device_info();
+    CUtensorMap tm_a8, tm_w8, tm_fa, tm_fw;
+    int rc;
+    if ((rc = make_tmap(&tm_a8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, A8, M, K, kBlockM))) return rc;
+    if ((rc = make_tmap(&tm_w8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W8, N, K, T::kBlockN))) return rc;
+    const int has_outlier = (fp_A && fp_weight) ? 1 : 0;
+    if (has_outlier) {
+        if ((rc = make_tmap(&tm_fa, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_A, M, MIXQ_NUM_OUTLIERS, kBlockM))) return rc;
+        if ((rc = make_tmap(&tm_fw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_weight, N, MIXQ_NUM_OUTLIERS, T::kBlockN)))
+            return rc;
+    } else {
+        tm_fa = tm_a8;
+        tm_fw = tm_w8;
+    }
+    auto kern = mixq_gemm_dequant_kernel<T>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::kSmemBytes));
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_dequant)");
+
+    const int m_tiles = static_cast<int>((M + kBlockM - 1) / kBlockM);
+    const int n_tiles = static_cast<int>((N + T::kBlockN - 1) / T::kBlockN);
+    const int64_t num_tiles = static_cast<int64_t>(m_tiles) * n_tiles;
+    if (num_tiles > (1ll << 30)) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: too many tiles");
+    const int grid = static_cast<int>(num_tiles < dev.num_sms ? num_tiles : dev.num_sms);
+    const int group_m = 8;
+
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = T::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, static_cast<const __half*>(scale_a),
+                           static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M),
+                           static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m);
+    if (e != cudaSuccess) return set_cuda_error(e, "launch gemm_dequant");
+    count_launch();
+    return MIXQ_OK;
+}
+
+}  // namespace
+
+int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
+                        const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
+                        bool pdl) {
+    if (M == 0 || N == 0) return MIXQ_OK;
+    if (!A8 || !W8 || !scale_a || !scale_b || !Out) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: null pointer");
+    if ((fp_A == nullptr) != (fp_weight == nullptr))
+        return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: fp_A and fp_weight must both be given or both be null");
+    if (M < 0 || N < 0 || K <= 0 || M > INT32_MAX || N > INT32_MAX || K > INT32_MAX)
+        return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: bad dimensions");
+    if ((K & 15) != 0) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: K must be a multiple of 16 (TMA row pitch)");
+    if ((N & 7) != 0) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: N must be a multiple of 8 (16-byte stores)");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(A8) | reinterpret_cast<uintptr_t>(W8) |
+                         reinterpret_cast<uintptr_t>(Out) | reinterpret_cast<uintptr_t>(fp_A) |
+                         reinterpret_cast<uintptr_t>(fp_weight);
+    if (al & 15) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: tensors must be 16-byte aligned");
+    if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
+
+    int cfg = current_gemm_config();
+    if (cfg == kCfgAuto) cfg = kCfgN128x2;
+    switch (cfg) {
+        case kCfgN128x2:
+            return launch_cfg<GemmTraits<128, 2, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+        case kCfgN256x1:
+            return launch_cfg<GemmTraits<256, 1, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+        case kCfgN64x2:
+            return launch_cfg<GemmTraits<64, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+        default:
+            return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: unknown config id");
+    }
+}
+
+}  // namespace mixq

@@ -1,0 +1,158 @@
+// mixq_api.cu -- the extern "C" entry points of include/mixq_b200.h (everything except the
+// plugin-handle functions, which live in mixq_plugin.cpp).  Host logic only: argument checks,
+// workspace carving (reference TsinghuaMixQPlugin.cpp:406-421), the two launches.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "mixq_internal.h"
+
+namespace mixq {
+
+namespace {
+thread_local char g_err[256] = "";
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_gemm_cfg{0};
+
+constexpr size_t kAlign = 128;  // kCudaMemAlign, TsinghuaMixQPlugin.cpp:204
+inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+struct Carve {
+    size_t off_a8, off_sa, off_fpa, total;
+};
+// int8_out | scale_a | fp_activation, in the reference's order (TsinghuaMixQPlugin.cpp:410-421)
+inline Carve carve(int64_t M, int64_t K) {
+    Carve c;
+    c.off_a8 = 0;
+    c.off_sa = align_up(static_cast<size_t>(M) * static_cast<size_t>(K));
+    c.off_fpa = c.off_sa + align_up(static_cast<size_t>(M) * 2);
+    c.total = c.off_fpa + align_up(static_cast<size_t>(M) * MIXQ_NUM_OUTLIERS * 2);
+    return c;
+}
+}  // namespace
+
+int set_error(int status, const char* msg) {
+    std::snprintf(g_err, sizeof(g_err), "%s", msg ? msg : "");
+    return status;
+}
+int set_cuda_error(cudaError_t e, const char* what) {
+    std::snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return MIXQ_ERR_CUDA;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int current_gemm_config() { return g_gemm_cfg.load(std::memory_order_relaxed); }
+
+const DeviceInfo& device_info() {
+    static DeviceInfo info;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+            cudaGetLastError();
+            return;
+        }
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return;
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return;
+        info.device = dev;
+        info.cc_major = p.major;
+        info.cc_minor = p.minor;
+        info.num_sms = p.multiProcessorCount;
+        info.max_smem_optin = p.sharedMemPerBlockOptin;
+        info.smem_per_sm = p.sharedMemPerMultiprocessor;
+        info.ok = (p.major == 10);  // the cubin is sm_100a only
+    });
+    return info;
+}
+
+}  // namespace mixq
+
+using namespace mixq;
+
+extern "C" {
+
+const char* mixq_version(void) { return "mixq-b200 0.1.0 (sm_100a; tcgen05 W8A8O16)"; }
+const char* mixq_last_error(void) { return g_err; }
+int mixq_device_ok(void) { return device_info().ok ? 1 : 0; }
+uint64_t mixq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int mixq_set_gemm_config(int config_id) {
+    if (config_id < 0 || config_id >= kCfgCount) return -1;
+    return g_gemm_cfg.exchange(config_id);
+}
+
+size_t mixq_workspace_size(int64_t M, int64_t N, int64_t K) {
+    (void)N;
+    if (M <= 0 || K <= 0) return 0;
+    return carve(M, K).total + kAlign;  // + slack to align the base like nextWorkspacePtr does
+}
+
+int mixq_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8, void* scale_a,
+                       void* fp_A, unsigned flags, void* stream) {
+    if (M < 0) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: M < 0");
+    return launch_quant_extract(A, M, K, ind, n_ind, A8, scale_a, fp_A, flags, static_cast<cudaStream_t>(stream),
+                                /*pdl=*/false);
+}
+
+int mixq_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
+                      const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, void* stream) {
+    return launch_gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K,
+                               static_cast<cudaStream_t>(stream), /*pdl=*/false);
+}
+
+int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes,
+                 unsigned flags, void* stream) {
+    if (!t) return set_error(MIXQ_ERR_BAD_ARG, "enqueue: null tensor table");
+    if (M < 0 || N <= 0 || K <= 0) return set_error(MIXQ_ERR_BAD_ARG, "enqueue: bad dimensions");
+    if (M == 0) return MIXQ_OK;
+    if (!t->A || !t->W8 || !t->scale_b || !t->fp_weight || !t->ind || !t->Out)
+        return set_error(MIXQ_ERR_BAD_ARG, "enqueue: null tensor (A, W8, scale_b, fp_weight, ind and Out are required)");
+    if (!workspace) return set_error(MIXQ_ERR_WORKSPACE, "enqueue: null workspace");
+    const Carve c = carve(M, K);
+    // align the base the way nextWorkspacePtr(ptr, 0) does (TsinghuaMixQPlugin.cpp:206-215)
+    uintptr_t base = reinterpret_cast<uintptr_t>(workspace);
+    const uintptr_t aligned = (base + kAlign - 1) / kAlign * kAlign;
+    if (workspace_bytes < (aligned - base) + c.total) return set_error(MIXQ_ERR_WORKSPACE, "enqueue: workspace too small");
+    uint8_t* ws = reinterpret_cast<uint8_t*>(aligned);
+    void* A8 = ws + c.off_a8;
+    void* sa = ws + c.off_sa;
+    void* fpA = ws + c.off_fpa;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = launch_quant_extract(t->A, M, K, t->ind, MIXQ_NUM_OUTLIERS, A8, sa, fpA, flags, s, /*pdl=*/true);
+    if (rc) return rc;
+    return launch_gemm_dequant(A8, t->W8, sa, t->scale_b, fpA, t->fp_weight, t->Out, M, N, K, s, /*pdl=*/true);
+}
+
+size_t mixq_host_scratch_size(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return align_up(static_cast<size_t>(M) * K * 2) + align_up(static_cast<size_t>(M) * N * 2) +
+           mixq_workspace_size(M, N, K) + kAlign;
+}
+
+int mixq_linear_host(const mixq_tensors* t, const void* A_host, void* Out_host, int64_t M, int64_t N, int64_t K,
+                     void* dev_scratch, size_t dev_scratch_bytes, unsigned flags, void* stream) {
+    if (!t || !A_host || !Out_host || !dev_scratch) return set_error(MIXQ_ERR_BAD_ARG, "linear_host: null pointer");
+    if (M <= 0 || N <= 0 || K <= 0) return set_error(MIXQ_ERR_BAD_ARG, "linear_host: bad dimensions");
+    if (dev_scratch_bytes < mixq_host_scratch_size(M, N, K)) return set_error(MIXQ_ERR_WORKSPACE, "linear_host: scratch too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uintptr_t base = (reinterpret_cast<uintptr_t>(dev_scratch) + kAlign - 1) / kAlign * kAlign;
+    uint8_t* dA = reinterpret_cast<uint8_t*>(base);
+    uint8_t* dOut = dA + align_up(static_cast<size_t>(M) * K * 2);
+    uint8_t* ws = dOut + align_up(static_cast<size_t>(M) * N * 2);
+    cudaError_t e = cudaMemcpyAsync(dA, A_host, static_cast<size_t>(M) * K * 2, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return set_cuda_error(e, "H2D activations");
+    mixq_tensors d = *t;
+    d.A = dA;
+    d.Out = dOut;
+    int rc = mixq_enqueue(&d, M, N, K, ws, mixq_workspace_size(M, N, K), flags, stream);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(Out_host, dOut, static_cast<size_t>(M) * N * 2, cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return set_cuda_error(e, "D2H output");
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return set_cuda_error(e, "stream synchronize");
+    return MIXQ_OK;
+}
+
+}  // extern "C"

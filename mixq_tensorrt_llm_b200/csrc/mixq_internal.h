@@ -1,0 +1,41 @@
+// mixq_internal.h -- declarations shared by the translation units of libmixq_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/mixq_b200.h"
+
+namespace mixq {
+
+struct DeviceInfo {
+    bool ok = false;         // a CUDA device with compute capability 10.x is current
+    int device = -1;
+    int cc_major = 0, cc_minor = 0;
+    int num_sms = 0;
+    size_t max_smem_optin = 0;  // per-block opt-in limit (227 KB on B200)
+    size_t smem_per_sm = 0;
+};
+
+// Queried once per process for the current device.
+const DeviceInfo& device_info();
+
+// Error bookkeeping (thread-local text behind mixq_last_error()).
+int set_error(int status, const char* msg);
+int set_cuda_error(cudaError_t e, const char* what);
+void count_launch();
+
+// stage 1 (quant_extract.cu)
+int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8, void* scale_a,
+                         void* fp_A, unsigned flags, cudaStream_t stream, bool pdl);
+
+// stage 2 (gemm_i8_tcgen05.cu)
+int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
+                        const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
+                        bool pdl);
+
+// GEMM tile configuration ids (mixq_set_gemm_config); 0 = pick automatically.
+enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfgCount };
+int current_gemm_config();
+
+}  // namespace mixq

@@ -1,0 +1,216 @@
+// quant_extract.cu -- stage 1 of the W8A8O16 path: one pass over the activations that
+//   * gathers the 128 outlier columns        fp_A[m, j] = A[m, ind[j]]
+//   * finds the per-token scale              sa[m] = hdiv(max_k |A[m,k]|, 127)
+//   * writes the INT8 codes                  A8[m,k] = int8(half2int_rn(hdiv(A[m,k], sa[m])))
+//
+// It replaces two reference launches:
+//   ExtractOutliersAndSetToZeros / FindOutliersAndSetToZeros_kernel  (kernel/i8gemm.cu:198-244)
+//   int8quant / FindRowScaleKernel<256>                               (kernel/i8gemm.cu:66-107,139-150)
+// which read A three times with 2-byte accesses (the gather with one 32-byte sector per
+// element).  Here each row is streamed once from HBM into shared memory with 16-byte
+// cp.async (double buffered across rows), everything else works out of shared memory, and the
+// INT8 codes leave in 8-byte coalesced stores: HBM traffic is the algorithmic minimum
+// 2*M*K (read) + M*K + 256*M + 2*M (write).
+//
+// Bit-exactness with the reference kernel:
+//   * the max is order-free; it is taken on the |x| bit patterns as unsigned integers, which
+//     orders finite fp16 values exactly like __hmax and makes Inf/NaN the largest codes, so a
+//     single reduction both yields the max and tells us whether the row is "abnormal";
+//   * sa uses the real __hdiv intrinsic;
+//   * device __hdiv(x, s) is fp16_rn(float(x) * rcp.approx.ftz.f32(float(s))) plus a fix-up that
+//     only touches results below 2^-17 (cuda_fp16.hpp:2723-2746), all of which round to the
+//     integer 0 either way.  The fast path therefore hoists the one rcp per row, multiplies in
+//     fp32, rounds to fp16 (the reference's intermediate rounding), and rounds to integer with
+//     the 1.5*2^23 magic-number add (round-to-nearest-even, identical to cvt.rni for |v| < 2^22).
+//   * rows that are abnormal (Inf/NaN present, or sa == 0 so that x/sa is Inf/NaN) take a slow
+//     path built from the very intrinsics the reference uses, so that even the saturating
+//     conversions agree.
+#include "mixq_internal.h"
+#include "ptx.cuh"
+
+namespace mixq {
+
+namespace {
+
+constexpr int kQuantThreads = 256;
+
+__device__ __forceinline__ uint32_t quant4_fast(uint32_t h01, uint32_t h23, float rcp) {
+    // 4 halves -> 4 int8 (packed little-endian)
+    const __half2 a = *reinterpret_cast<const __half2*>(&h01);
+    const __half2 b = *reinterpret_cast<const __half2*>(&h23);
+    float2 fa = __half22float2(a);
+    float2 fb = __half22float2(b);
+    // fp32 product, rounded to fp16 exactly like __float2half(rcp * fa) in __hdiv
+    const __half2 qa = __floats2half2_rn(__fmul_rn(fa.x, rcp), __fmul_rn(fa.y, rcp));
+    const __half2 qb = __floats2half2_rn(__fmul_rn(fb.x, rcp), __fmul_rn(fb.y, rcp));
+    fa = __half22float2(qa);
+    fb = __half22float2(qb);
+    const float magic = 12582912.0f;  // 1.5 * 2^23: low mantissa bits hold rint_even(v) in two's complement
+    const uint32_t i0 = __float_as_uint(__fadd_rn(fa.x, magic));
+    const uint32_t i1 = __float_as_uint(__fadd_rn(fa.y, magic));
+    const uint32_t i2 = __float_as_uint(__fadd_rn(fb.x, magic));
+    const uint32_t i3 = __float_as_uint(__fadd_rn(fb.y, magic));
+    const uint32_t lo = __byte_perm(i0, i1, 0x0040);  // bytes: i0.b0, i1.b0
+    const uint32_t hi = __byte_perm(i2, i3, 0x0040);
+    return __byte_perm(lo, hi, 0x5410);
+}
+
+__device__ __forceinline__ uint32_t quant4_exact(uint32_t h01, uint32_t h23, __half scale) {
+    // the reference's own sequence (kernel/i8gemm.cu:103-104), saturating cvt included
+    const __half2 a = *reinterpret_cast<const __half2*>(&h01);
+    const __half2 b = *reinterpret_cast<const __half2*>(&h23);
+    const uint32_t q0 = static_cast<uint8_t>(static_cast<int8_t>(__half2int_rn(__hdiv(__low2half(a), scale))));
+    const uint32_t q1 = static_cast<uint8_t>(static_cast<int8_t>(__half2int_rn(__hdiv(__high2half(a), scale))));
+    const uint32_t q2 = static_cast<uint8_t>(static_cast<int8_t>(__half2int_rn(__hdiv(__low2half(b), scale))));
+    const uint32_t q3 = static_cast<uint8_t>(static_cast<int8_t>(__half2int_rn(__hdiv(__high2half(b), scale))));
+    return q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+}
+
+// grid: persistent CTAs striding over rows; block: 256 threads; dynamic smem: 2 * K * 2 bytes.
+__global__ void __launch_bounds__(kQuantThreads)
+mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const int* __restrict__ ind, int n_ind,
+                          int8_t* __restrict__ A8, __half* __restrict__ scale_a, __half* __restrict__ fp_A,
+                          int mask_outliers) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ uint32_t s_warp_max[kQuantThreads / 32];
+    const int tid = threadIdx.x;
+    const int vec_per_row = K >> 3;  // 16-byte vectors (K % 8 == 0 is checked on the host)
+    uint4* const buf0 = reinterpret_cast<uint4*>(smem_raw);
+
+    // The activations are produced by the previous kernel in the stream.
+    ptx::pdl_wait_prior_grid();
+
+    int64_t row = blockIdx.x;
+    if (row < M) {
+        const uint4* src = reinterpret_cast<const uint4*>(A + row * K);
+        for (int i = tid; i < vec_per_row; i += kQuantThreads) ptx::cp_async_16(ptx::smem_u32(buf0 + i), src + i);
+    }
+    ptx::cp_async_commit();
+
+    int cur = 0;
+    for (; row < M; row += gridDim.x, cur ^= 1) {
+        const int64_t next = row + gridDim.x;
+        if (next < M) {
+            const uint4* src = reinterpret_cast<const uint4*>(A + next * K);
+            for (int i = tid; i < vec_per_row; i += kQuantThreads)
+                ptx::cp_async_16(ptx::smem_u32(buf0 + (cur ^ 1) * vec_per_row + i), src + i);
+        }
+        ptx::cp_async_commit();
+        ptx::cp_async_wait<1>();  // the current row has landed (the prefetch may still be in flight)
+        __syncthreads();
+
+        uint4* rowv = buf0 + cur * vec_per_row;
+        __half* rowh = reinterpret_cast<__half*>(rowv);
+
+        // outlier gather (and, in MixQ/src mode, zeroing: cult.cu:1588)
+        if (tid < n_ind) {
+            const int c = ind[tid];
+            fp_A[row * n_ind + tid] = rowh[c];
+        }
+        if (mask_outliers) {
+            __syncthreads();
+            if (tid < n_ind) rowh[ind[tid]] = __ushort_as_half(0);
+            __syncthreads();
+        }
+
+        // per-token max of |x| on the bit patterns
+        uint32_t m = 0;
+        for (int i = tid; i < vec_per_row; i += kQuantThreads) {
+            const uint4 v = rowv[i];
+            m = __vmaxu2(m, v.x & 0x7FFF7FFFu);
+            m = __vmaxu2(m, v.y & 0x7FFF7FFFu);
+            m = __vmaxu2(m, v.z & 0x7FFF7FFFu);
+            m = __vmaxu2(m, v.w & 0x7FFF7FFFu);
+        }
+        m = max(m & 0xFFFFu, m >> 16);
+        m = __reduce_max_sync(0xFFFFFFFFu, m);
+        if ((tid & 31) == 0) s_warp_max[tid >> 5] = m;
+        __syncthreads();
+        uint32_t mx_bits = 0;
+#pragma unroll
+        for (int w = 0; w < kQuantThreads / 32; ++w) mx_bits = max(mx_bits, s_warp_max[w]);
+
+        // NaN elements do not take part in the reference's __hmax chain; if the row holds any
+        // Inf/NaN we recompute the max the slow, faithful way.
+        __half mx = __ushort_as_half(static_cast<unsigned short>(mx_bits));
+        const bool nonfinite = mx_bits >= 0x7C00u;
+        if (nonfinite) {
+            __half t = __ushort_as_half(0);
+            for (int i = 0; i < K; ++i) t = __hmax(__habs(rowh[i]), t);  // redundant per thread; rare path
+            mx = t;
+        }
+        const __half scale = __hdiv(mx, __float2half(127.0f));
+        if (tid == 0) scale_a[row] = scale;
+
+        uint2* dst = reinterpret_cast<uint2*>(A8 + row * K);
+        if (!nonfinite && __half_as_ushort(scale) != 0) {
+            float rcp;
+            const float fs = __half2float(scale);
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(fs));
+            for (int i = tid; i < vec_per_row; i += kQuantThreads) {
+                const uint4 v = rowv[i];
+                dst[i] = make_uint2(quant4_fast(v.x, v.y, rcp), quant4_fast(v.z, v.w, rcp));
+            }
+        } else {
+            for (int i = tid; i < vec_per_row; i += kQuantThreads) {
+                const uint4 v = rowv[i];
+                dst[i] = make_uint2(quant4_exact(v.x, v.y, scale), quant4_exact(v.z, v.w, scale));
+            }
+        }
+        __syncthreads();  // everyone is done with buf[cur] before it is refilled two rows ahead
+    }
+    ptx::cp_async_wait<0>();
+    // Let the dependent GEMM start its prologue.
+    ptx::pdl_launch_dependents();
+}
+
+}  // namespace
+
+int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8, void* scale_a,
+                         void* fp_A, unsigned flags, cudaStream_t stream, bool pdl) {
+    if (M == 0) return MIXQ_OK;
+    if (K <= 0 || (K & 7) != 0 || K > (1 << 20)) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: K must be a positive multiple of 8");
+    if (n_ind < 0 || n_ind > kQuantThreads) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: n_ind must be in [0,256]");
+    if (n_ind > 0 && (!ind || !fp_A)) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: ind/fp_A null");
+    if (!A || !A8 || !scale_a) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: null pointer");
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(A8) & 7))
+        return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: A must be 16-byte and A8 8-byte aligned");
+
+    const DeviceInfo& dev = device_info();
+    if (!dev.ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
+    const size_t smem = static_cast<size_t>(K) * 2 * 2;
+    if (smem > dev.max_smem_optin) return set_error(MIXQ_ERR_UNSUPPORTED, "quant_extract: K too large for shared memory staging");
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(mixq_quant_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(dev.max_smem_optin));
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(quant_extract)");
+        configured = dev.max_smem_optin;
+    }
+    // resident CTAs per SM: limited by threads (2048/256 = 8) and by shared memory
+    int per_sm = static_cast<int>(dev.smem_per_sm / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    int64_t grid = static_cast<int64_t>(dev.num_sms) * per_sm;
+    if (grid > M) grid = M;
+
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kQuantThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const int mask = (flags & MIXQ_FLAG_MASK_OUTLIERS) ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mixq_quant_extract_kernel, static_cast<const __half*>(A), M,
+                                       static_cast<int>(K), static_cast<const int*>(ind), n_ind,
+                                       static_cast<int8_t*>(A8), static_cast<__half*>(scale_a),
+                                       static_cast<__half*>(fp_A), mask);
+    if (e != cudaSuccess) return set_cuda_error(e, "launch quant_extract");
+    count_launch();
+    return MIXQ_OK;
+}
+
+}  // namespace mixq

@@ -1,0 +1,175 @@
+"""Python side of the drop-in boundary: ``mixgemm`` and ``MixQLinear``.
+
+Mirrors the reference's plugin.py (reference plugin.py:34-47 library load +
+initOpenAiTritonPlugins, :52-79 ``mixgemm``, :86-162 ``MixQLinear``) with torch CUDA tensors in
+place of TensorRT network tensors: same constructor arguments, same parameter names, shapes and
+fp16-typed containers (so a reference ``int8_mix`` checkpoint maps 1:1), same seven plugin
+inputs in the same order.  The call goes Python -> C handle API -> MixQPlugin::enqueue ->
+mixq_enqueue -> two CUDA kernels.  No fallback: without the built library or without a B200
+this module raises.
+
+Differences from the reference, on purpose:
+  * tensor parallelism: the reference all-reduces after *every* MixQLinear that has a tp_group
+    (plugin.py:155-156), which is wrong for the column-parallel linears it wraps, and forbids
+    row-parallel (quantization/quantize.py:342).  Here ``parallel_mode="column"`` needs no
+    collective (optionally all-gathers when gather_output) and ``parallel_mode="row"`` does the
+    single all-reduce of the partial sums.
+  * the M<=4 weight-only branch is not taken; ``qweight`` is accepted and
+    ignored.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional
+
+import torch
+
+from . import binding
+
+TRT_LLM_PLUGIN_NAMESPACE = "tensorrt_llm"
+LAYER_NAME = "MixQLayer"
+NUM_OUTLIERS = binding.NUM_OUTLIERS
+
+_registered = False
+
+
+def _load_plugin_lib() -> None:
+    """plugin.py:34-47 -- dlopen the library and register the creator under 'tensorrt_llm'."""
+    global _registered
+    if _registered:
+        return
+    lib = binding.load()
+    assert lib.initOpenAiTritonPlugins(None, TRT_LLM_PLUGIN_NAMESPACE.encode("utf-8"))
+    _registered = True
+
+
+class _PluginHandle:
+    """Owns one MixQPlugin instance created through the registered creator ('MixQ','1',ns)."""
+
+    def __init__(self, m: int, n: int, k: int):
+        _load_plugin_lib()
+        self._lib = binding.load()
+        self._h = self._lib.mixq_plugin_create(TRT_LLM_PLUGIN_NAMESPACE.encode(), int(m), int(n), int(k))
+        if not self._h:
+            raise binding.MixQError("plugin creator ('MixQ','1','tensorrt_llm') is not registered")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.mixq_plugin_destroy(h)
+
+    def enqueue(self, a_dims, n: int, inputs, out, workspace, stream) -> None:
+        dims = (ctypes.c_int64 * len(a_dims))(*a_dims)
+        in_ptrs = (ctypes.c_void_p * 7)(*[t.data_ptr() for t in inputs])
+        out_ptrs = (ctypes.c_void_p * 1)(out.data_ptr())
+        rc = self._lib.mixq_plugin_enqueue(self._h, dims, len(a_dims), int(n), in_ptrs, out_ptrs,
+                                           ctypes.c_void_p(workspace.data_ptr()), ctypes.c_void_p(stream.cuda_stream))
+        binding.check(rc, "MixQPlugin::enqueue")
+
+
+_workspaces: dict = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Grow-only per-device scratch, playing the role of the workspace TensorRT hands to enqueue."""
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def mixgemm(m: int, n: int, k: int, inputs: List[torch.Tensor], plugin: Optional[_PluginHandle] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """plugin.py:52-79.  ``inputs`` are the seven plugin inputs in the reference's order:
+    [A, weight(int8 bytes as fp16 [N,K/2]), weights_scaling_factor [N], fp_weight [N,128],
+     fp_ind (int32 bytes as fp16 [256]), qweight, scaling_factors]."""
+    binding.require_device()
+    A = inputs[0]
+    if not (A.is_cuda and A.dtype == torch.float16):
+        raise binding.MixQError("mixgemm: activation must be a CUDA fp16 tensor")
+    if not A.is_contiguous():
+        A = A.contiguous()
+    if plugin is None:
+        plugin = _PluginHandle(m, n, k)
+    a_dims = list(A.shape)
+    M = 1
+    for d in a_dims[:-1]:
+        M *= d
+    K = a_dims[-1]
+    N = inputs[1].shape[0]
+    if out is None:
+        out = torch.empty(*a_dims[:-1], N, dtype=torch.float16, device=A.device)
+    ws = _workspace(A.device, binding.workspace_size(max(M, 1), N, K))
+    plugin.enqueue(a_dims, N, [A] + list(inputs[1:7]), out, ws, torch.cuda.current_stream(A.device))
+    return out
+
+
+class MixQLinear(torch.nn.Module):
+    """reference plugin.py:86-162, torch flavour.
+
+    Parameters hold exactly the reference's checkpoint tensors (all typed float16):
+      weight [N/tp, K/2]      int8 codes, two per fp16 slot  (model_config_utils.py:460-466)
+      fp_weight [N/tp, 128]   outlier weight columns          (:452)
+      fp_ind [256]            128 int32 indices as raw bytes  (:455-457)
+      qweight [K, N/tp/2]     weight-only layout for M<=4     (:437-441; unused here)
+      weights_scaling_factor [N/tp]                            (:429-430)
+    """
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = False, dtype=None, tp_group=None,
+                 tp_size: int = 1, gather_output: bool = True, parallel_mode: str = "column", device=None):
+        super().__init__()
+        if parallel_mode not in ("column", "row"):
+            raise ValueError("parallel_mode must be 'column' or 'row'")
+        self.parallel_mode = parallel_mode
+        self.tp_size = tp_size
+        self.tp_group = tp_group
+        self.gather_output = gather_output
+        if parallel_mode == "column":
+            self.in_features = in_features
+            self.out_features = out_features // tp_size
+        else:
+            self.in_features = in_features // tp_size
+            self.out_features = out_features
+        h = dict(dtype=torch.float16, device=device)
+        N, K = self.out_features, self.in_features
+        self.register_buffer("weight", torch.zeros(N, K // 2, **h))
+        self.register_buffer("fp_weight", torch.zeros(N, NUM_OUTLIERS, **h))
+        self.register_buffer("fp_ind", torch.zeros(NUM_OUTLIERS * 2, **h))
+        self.register_buffer("qweight", torch.zeros(0, **h))  # kept for layout parity; M<=4 branch not built
+        self.register_buffer("weights_scaling_factor", torch.zeros(N, **h))
+        if bias:
+            self.register_buffer("bias", torch.zeros(N, dtype=dtype or torch.float16, device=device))
+        else:
+            self.bias = None
+        self._plugin = None
+
+    @torch.no_grad()
+    def load_packed(self, W8: torch.Tensor, scale_b: torch.Tensor, fp_weight: torch.Tensor, ind: torch.Tensor,
+                    bias: Optional[torch.Tensor] = None) -> "MixQLinear":
+        """Fill the buffers from typed tensors (int8 [N,K], fp16 [N], fp16 [N,128], int32 [128])."""
+        self.weight.copy_(W8.contiguous().view(torch.float16))
+        self.weights_scaling_factor.copy_(scale_b.reshape(-1))
+        self.fp_weight.copy_(fp_weight)
+        self.fp_ind.copy_(ind.to(torch.int32).contiguous().view(torch.float16))
+        if bias is not None and self.bias is not None:
+            self.bias.copy_(bias)
+        return self
+
+    def forward(self, A: torch.Tensor) -> torch.Tensor:
+        if self._plugin is None:
+            self._plugin = _PluginHandle(A.shape[0], self.out_features, self.in_features)
+        x = mixgemm(A.shape[0], self.out_features, self.in_features,
+                    [A, self.weight, self.weights_scaling_factor, self.fp_weight, self.fp_ind, self.qweight,
+                     self.weights_scaling_factor], plugin=self._plugin)
+        if self.tp_size > 1 and self.tp_group is not None:
+            import torch.distributed as dist
+            if self.parallel_mode == "row":
+                dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.tp_group)  # the one exchange step of the path
+            elif self.gather_output:
+                parts = [torch.empty_like(x) for _ in range(self.tp_size)]
+                dist.all_gather(parts, x, group=self.tp_group)
+                x = torch.cat(parts, dim=-1)
+        if self.bias is not None:
+            x = x + self.bias.to(x.dtype)  # outside the plugin, as plugin.py:158-160
+        return x

@@ -1,0 +1,219 @@
+/*
+ * mixq_oracle.c -- CPU restatement of the reference's W8A8O16 hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under mixq_tensorrt_llm_b200/ may link,
+ * import or call this file; it is the checker used by tests/, by
+ * __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference leg.
+ *
+ * Each function restates one step of MixQPlugin::enqueueImpl's M>4 branch
+ * (reference TsinghuaMixQPlugin.cpp:472-532) in the order that function runs it:
+ *
+ *   mixq_oracle_gather        <- kernel/i8gemm.cu:198-224  (FindOutliersAndSetToZeros_kernel)
+ *   mixq_oracle_outlier_gemm  <- TsinghuaMixQPlugin.cpp:122-161 (cublasGemmEx fp16, fp32 accumulate)
+ *   mixq_oracle_quant         <- kernel/i8gemm.cu:66-107   (FindRowScaleKernel<256>)
+ *   mixq_oracle_igemm         <- kernel/symmetric/gemm/kernel/gemm_dequant.h:224-292 (int8 x int8 -> int32)
+ *   mixq_oracle_epilogue      <- kernel/symmetric/epilogue/thread/linear_combination_dequant.h:152-157
+ *
+ * Device arithmetic that has no host equivalent is emulated bit-for-bit:
+ *   __hdiv(a,b) on the device is fp16_rn( float(a) * rcp.approx.ftz.f32(float(b)) ) with a
+ *   refinement only for results in the fp16 denormal range
+ *   (/usr/local/cuda/include/cuda_fp16.hpp:2723-2746).  rcp.approx is a hardware table
+ *   look-up; since b is always an fp16 value there are only 65536 possible inputs, so the
+ *   table is captured once on a B200 (tests/golden/make_gpu_golden.py ->
+ *   tests/golden/rcp_approx_f16.bin) and passed in here.  Without the table the oracle
+ *   falls back to the correctly rounded 1/b (differs from the device by <=1 ulp of the
+ *   reciprocal, which changes the int8 code of ~1e-5 of the elements).
+ *
+ * Parity status: the reference ships no test or golden vector for this path
+ * (SURVEY.md section 4).  The oracle is pinned instead against the reference's own kernels
+ * compiled from /root/reference/kernel/i8gemm.cu (oracle/_ref) and run on a B200; their
+ * outputs are committed under tests/golden/ (see tests/golden/README.md).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef _Float16 f16;
+
+static inline f16 bits_to_f16(uint16_t b) {
+    f16 h;
+    memcpy(&h, &b, 2);
+    return h;
+}
+static inline uint16_t f16_to_bits(f16 h) {
+    uint16_t b;
+    memcpy(&b, &h, 2);
+    return b;
+}
+static inline float bits_to_f32(uint32_t b) {
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+
+/* rcp.approx.ftz.f32 of an fp16-valued input; `bits` is the fp16 bit pattern. */
+static inline float rcp_approx(uint16_t bits, const uint32_t* table) {
+    if (table) return bits_to_f32(table[bits]);
+    return 1.0f / (float)bits_to_f16(bits);
+}
+
+/* Device __hdiv (cuda_fp16.hpp:2723-2746). */
+static inline f16 dev_hdiv(f16 a, f16 b, const uint32_t* table) {
+    const float fa = (float)a;
+    const float fb = (float)b;
+    const float rcp = rcp_approx(f16_to_bits(b), table);
+    float fv = rcp * fa;
+    f16 v = (f16)fv;
+    const f16 den = bits_to_f16(0x008F);
+    f16 av = bits_to_f16((uint16_t)(f16_to_bits(v) & 0x7FFF));
+    /* __hlt is false for NaN operands */
+    if (av < den && (f16)0.0f < av) {
+        const float err = fmaf(-fb, fv, fa);
+        fv = fmaf(rcp, err, fv);
+        v = (f16)fv;
+    }
+    return v;
+}
+
+/* __hmax: returns the non-NaN operand when exactly one is NaN (PTX max.f16). */
+static inline f16 dev_hmax(f16 a, f16 b) {
+    if (a != a) return b;
+    if (b != b) return a;
+    return a > b ? a : b;
+}
+
+/* cvt.rni.s32.f16 (what __half2int_rn lowers to): NaN -> 0, saturating. */
+static inline int32_t dev_half2int_rn(f16 h) {
+    if (h != h) return 0;
+    const float f = (float)h;
+    if (f >= 2147483648.0f) return INT32_MAX;
+    if (f <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)nearbyintf(f); /* default rounding mode = nearest-even */
+}
+
+/* kernel/i8gemm.cu:198-224: fp_A[i, j] = A[i, ind[j]]; the zeroing store is commented
+ * out in the plugin's copy (line 218) and live in MixQ/src (cult.cu:1588) -- see `mask`
+ * in mixq_oracle_quant. */
+void mixq_oracle_gather(const uint16_t* A, int64_t M, int64_t K, const int32_t* ind, int n_ind,
+                        uint16_t* fp_A) {
+    for (int64_t m = 0; m < M; ++m)
+        for (int j = 0; j < n_ind; ++j) fp_A[m * n_ind + j] = A[m * K + ind[j]];
+}
+
+/* kernel/i8gemm.cu:66-107 FindRowScaleKernel<256>:
+ *   max   = reduce(__hmax, __habs(row))                       (:76-88, order-free)
+ *   scale = __hdiv(max, 127.0)                                (:96)
+ *   q[k]  = (int8_t)__half2int_rn(__hdiv(row[k], scale))      (:103-104)
+ * mask != 0 restates MixQ/src (cult.cu:1588): the n_ind outlier columns are treated as
+ * zero for both the max and the quantised value. */
+void mixq_oracle_quant(const uint16_t* A, int64_t M, int64_t K, const uint32_t* rcp_table,
+                       const int32_t* ind, int n_ind, int mask, int8_t* q, uint16_t* scale_a) {
+    uint8_t* is_out = NULL;
+    if (mask && n_ind > 0) {
+        is_out = (uint8_t*)calloc((size_t)K, 1);
+        for (int j = 0; j < n_ind; ++j) is_out[ind[j]] = 1;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < M; ++m) {
+        const uint16_t* row = A + m * K;
+        f16 mx = (f16)0.0f;
+        for (int64_t k = 0; k < K; ++k) {
+            uint16_t b = (is_out && is_out[k]) ? 0 : (uint16_t)(row[k] & 0x7FFF); /* __habs */
+            mx = dev_hmax(bits_to_f16(b), mx);
+        }
+        const f16 scale = dev_hdiv(mx, (f16)127.0f, rcp_table);
+        scale_a[m] = f16_to_bits(scale);
+        for (int64_t k = 0; k < K; ++k) {
+            const f16 x = (is_out && is_out[k]) ? (f16)0.0f : bits_to_f16(row[k]);
+            q[m * K + k] = (int8_t)dev_half2int_rn(dev_hdiv(x, scale, rcp_table));
+        }
+    }
+    free(is_out);
+}
+
+/* TsinghuaMixQPlugin.cpp:122-161: Out0 = fp_A [M,kf] x fp_weight[N,kf]^T, fp16 in/out,
+ * CUBLAS_COMPUTE_32F.  cuBLAS' accumulation order is unspecified; the products are exact
+ * in fp32, so the oracle accumulates in double and rounds once to fp32 and once to fp16
+ * (the reference rounds the fp32 accumulator to fp16 on store). */
+void mixq_oracle_outlier_gemm(const uint16_t* fp_A, const uint16_t* fp_W, int64_t M, int64_t N,
+                              int kf, uint16_t* out0) {
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < M; ++m) {
+        float a[1024];
+        for (int j = 0; j < kf; ++j) a[j] = (float)bits_to_f16(fp_A[m * kf + j]);
+        for (int64_t n = 0; n < N; ++n) {
+            const uint16_t* w = fp_W + n * kf;
+            double acc = 0.0;
+            for (int j = 0; j < kf; ++j) acc += (double)a[j] * (double)(float)bits_to_f16(w[j]);
+            out0[m * N + n] = f16_to_bits((f16)(float)acc);
+        }
+    }
+}
+
+/* The O(MNK) term: acc[m,n] = sum_k q[m,k] * w[n,k] in exact int32
+ * (kernel/symmetric/gemm/kernel/gemm_dequant.h:224-292; OpMultiplyAddSaturate cannot
+ * saturate for K*127*128 < 2^31). */
+__attribute__((target_clones("arch=skylake-avx512", "avx2", "default"))) static int32_t dot_i8(
+    const int8_t* __restrict a, const int8_t* __restrict b, int64_t K) {
+    int32_t s = 0;
+    for (int64_t k = 0; k < K; ++k) s += (int32_t)a[k] * (int32_t)b[k];
+    return s;
+}
+
+void mixq_oracle_igemm(const int8_t* q, const int8_t* w, int64_t M, int64_t N, int64_t K,
+                       int32_t* acc) {
+#pragma omp parallel for schedule(static) collapse(2)
+    for (int64_t mb = 0; mb < M; mb += 8)
+        for (int64_t n = 0; n < N; ++n) {
+            const int64_t me = mb + 8 < M ? mb + 8 : M;
+            for (int64_t m = mb; m < me; ++m) acc[m * N + n] = dot_i8(q + m * K, w + n * K, K);
+        }
+}
+
+/* linear_combination_dequant.h:152-157 with C = Out0:
+ *   D = __float2half( float(acc) * (float(sb[n]) * float(sa[m])) + float(C) )
+ * compiled by nvcc to I2FP.F32.S32, FMUL (scale product), FFMA, F2FP.F16.F32,
+ * i.e. a single-rounded fused multiply-add followed by one RN-even fp16 rounding. */
+void mixq_oracle_epilogue(const int32_t* acc, const uint16_t* scale_a, const uint16_t* scale_b,
+                          const uint16_t* out0, int64_t M, int64_t N, uint16_t* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < M; ++m) {
+        const float sa = (float)bits_to_f16(scale_a[m]);
+        for (int64_t n = 0; n < N; ++n) {
+            const float p = (float)bits_to_f16(scale_b[n]) * sa;
+            const float c = out0 ? (float)bits_to_f16(out0[m * N + n]) : 0.0f;
+            out[m * N + n] = f16_to_bits((f16)fmaf((float)acc[m * N + n], p, c));
+        }
+    }
+}
+
+/* MixQPlugin::enqueueImpl M>4 branch, TsinghuaMixQPlugin.cpp:518-532, in call order.
+ * scratch buffers are caller-provided so the timing legs do not measure malloc:
+ *   fp_A [M,128] u16 | out0 [M,N] u16 | q [M,K] i8 | sa [M] u16 | acc [M,N] i32 */
+void mixq_oracle_forward(const uint16_t* A, const int8_t* W8, const uint16_t* scale_b,
+                         const uint16_t* fp_weight, const int32_t* ind, int n_ind, int64_t M,
+                         int64_t N, int64_t K, const uint32_t* rcp_table, int mask,
+                         uint16_t* fp_A, uint16_t* out0, int8_t* q, uint16_t* sa, int32_t* acc,
+                         uint16_t* out) {
+    mixq_oracle_gather(A, M, K, ind, n_ind, fp_A);                       /* :519 */
+    mixq_oracle_outlier_gemm(fp_A, fp_weight, M, N, n_ind, out0);        /* :521 */
+    mixq_oracle_quant(A, M, K, rcp_table, ind, n_ind, mask, q, sa);      /* :522 */
+    mixq_oracle_igemm(q, W8, M, N, K, acc);                              /* :529 mainloop */
+    mixq_oracle_epilogue(acc, sa, scale_b, out0, M, N, out);             /* :529 epilogue */
+}
+
+int mixq_oracle_num_threads(void) {
+    int n = 1;
+#ifdef _OPENMP
+#pragma omp parallel
+    {
+#pragma omp master
+        n = omp_get_num_threads();
+    }
+#endif
+    return n;
+}

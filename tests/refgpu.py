@@ -1,0 +1,91 @@
+"""ctypes front end of oracle/_ref/libref_driver.so -- the reference's own CUDA kernels
+(compiled from /root/reference/kernel/i8gemm.cu) replayed in enqueueImpl's order.
+TEST / BENCH INFRASTRUCTURE ONLY; the product never loads it."""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+REF_DIR = Path(__file__).resolve().parent.parent / "oracle" / "_ref"
+_lib = None
+
+
+def available() -> bool:
+    return (REF_DIR / "libref_driver.so").exists() and (REF_DIR / "libref_i8gemm.so").exists()
+
+
+def load():
+    global _lib
+    if _lib is None:
+        ctypes.CDLL(str(REF_DIR / "libref_i8gemm.so"), mode=ctypes.RTLD_GLOBAL)
+        L = ctypes.CDLL(str(REF_DIR / "libref_driver.so"))
+        vp, ci, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+        L.ref_init.restype = ci
+        L.ref_workspace_size.restype = ctypes.c_size_t
+        L.ref_workspace_size.argtypes = [i64, i64, i64]
+        L.ref_int8quant.argtypes = [vp, ci, ci, vp, vp, vp]
+        L.ref_extract.argtypes = [vp, ci, ci, vp, ci, vp, vp]
+        L.ref_fused_dequant.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp]
+        L.ref_enqueue.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, vp, vp]
+        L.ref_rcp_table.argtypes = [vp, vp]
+        L.ref_hdiv.argtypes = [vp, vp, vp, vp, ci, vp]
+        for f in ("ref_int8quant", "ref_extract", "ref_fused_dequant", "ref_enqueue", "ref_rcp_table", "ref_hdiv"):
+            getattr(L, f).restype = ci
+        assert L.ref_init() == 0
+        _lib = L
+    return _lib
+
+
+def _s():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def int8quant(A):
+    import torch
+    M, K = A.shape
+    q = torch.empty(M, K, dtype=torch.int8, device=A.device)
+    sa = torch.empty(M, dtype=torch.float16, device=A.device)
+    assert load().ref_int8quant(_p(A), M, K, _p(q), _p(sa), _s()) == 0
+    return q, sa
+
+
+def extract(A, ind):
+    import torch
+    M, K = A.shape
+    fpA = torch.empty(M, ind.numel(), dtype=torch.float16, device=A.device)
+    assert load().ref_extract(_p(A), M, K, _p(ind), ind.numel(), _p(fpA), _s()) == 0
+    return fpA
+
+
+def enqueue(A, W8, sb, fp_weight, ind, out=None, ws=None):
+    import torch
+    M, K = A.shape
+    N = W8.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float16, device=A.device)
+    if ws is None:
+        ws = torch.empty(load().ref_workspace_size(M, N, K), dtype=torch.uint8, device=A.device)
+    rc = load().ref_enqueue(_p(A), _p(W8), _p(sb), _p(fp_weight), _p(ind), _p(out), M, N, K, _p(ws), _s())
+    assert rc == 0, rc
+    return out
+
+
+def rcp_table():
+    import torch
+    t = torch.empty(65536, dtype=torch.int32, device="cuda")
+    assert load().ref_rcp_table(_p(t), _s()) == 0
+    torch.cuda.synchronize()
+    return t.cpu().numpy().view("uint32")
+
+
+def hdiv(a, b):
+    import torch
+    q = torch.empty_like(a)
+    qi = torch.empty(a.numel(), dtype=torch.int32, device=a.device)
+    assert load().ref_hdiv(_p(a), _p(b), _p(q), _p(qi), a.numel(), _s()) == 0
+    return q, qi

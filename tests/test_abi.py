@@ -1,0 +1,156 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, and the plugin surface (creator lookup, identity strings, format negotiation,
+serialisation, workspace sizing, argument validation) behaves like the reference's
+(TsinghuaMixQPlugin.cpp).  No kernel is launched here."""
+import ctypes
+import re
+import struct
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_header_symbols_are_exported(lib):
+    from mixq_tensorrt_llm_b200 import binding
+    hdr = (ROOT / "include" / "mixq_b200.h").read_text()
+    declared = set(re.findall(r"\b(mixq_[a-z0-9_]+|initOpenAiTritonPlugins)\s*\(", hdr))
+    declared -= {"mixq_status"}
+    assert declared == set(binding.EXPORTS), declared ^ set(binding.EXPORTS)
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(binding.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in nm.splitlines() if " T " in l}
+    missing = declared - exported
+    assert not missing, missing
+    assert "getPluginRegistry" in exported      # shim build: our own registry stands in for libnvinfer's
+    assert b"mixq-b200" in lib.mixq_version()
+
+
+def test_header_compiles_as_c():
+    src = '#include "mixq_b200.h"\nint main(void){ mixq_tensors t; (void)t; return MIXQ_NUM_OUTLIERS == 128 ? 0 : 1; }\n'
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", str(ROOT / "include"),
+                        "-x", "c", "-"], input=src, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_plugin_identity_and_registry(lib):
+    ns = b"tensorrt_llm"
+    assert lib.mixq_plugin_create(b"never_registered_ns", 1, 2, 3) is None
+    assert lib.initOpenAiTritonPlugins(None, ns) is True
+    assert lib.initOpenAiTritonPlugins(None, ns) is True          # idempotent (MixQPlugins.cpp:55-76)
+    h = lib.mixq_plugin_create(ns, 512, 12288, 4096)
+    assert h
+    try:
+        assert lib.mixq_plugin_type(h) == b"MixQ"                  # TsinghuaMixQPlugin.cpp:181
+        assert lib.mixq_plugin_version(h) == b"1"                  # :180
+        assert lib.mixq_plugin_namespace(h) == ns
+        assert lib.mixq_plugin_nb_outputs(h) == 1
+    finally:
+        lib.mixq_plugin_destroy(h)
+
+
+def test_plugin_format_combination(lib):
+    lib.initOpenAiTritonPlugins(None, b"tensorrt_llm")
+    h = lib.mixq_plugin_create(b"tensorrt_llm", 1, 1, 1)
+    kHALF, kFLOAT, kINT8, kLINEAR, kCHW32 = 1, 0, 2, 0, 5
+    try:
+        for pos in range(8):                                       # 7 inputs + 1 output, all half/linear (:263-320)
+            assert lib.mixq_plugin_supports_format(h, pos, kHALF, kLINEAR) == 1
+            assert lib.mixq_plugin_supports_format(h, pos, kFLOAT, kLINEAR) == 0
+            assert lib.mixq_plugin_supports_format(h, pos, kINT8, kLINEAR) == 0
+            assert lib.mixq_plugin_supports_format(h, pos, kHALF, kCHW32) == 0
+        assert lib.mixq_plugin_supports_format(h, 8, kHALF, kLINEAR) == 0
+    finally:
+        lib.mixq_plugin_destroy(h)
+
+
+def test_plugin_serialization_roundtrip(lib):
+    lib.initOpenAiTritonPlugins(None, b"tensorrt_llm")
+    h = lib.mixq_plugin_create(b"tensorrt_llm", 512, 12288, 4096)
+    try:
+        n = lib.mixq_plugin_serialization_size(h)
+        assert n == 12                                             # three int32 (:808-820)
+        buf = ctypes.create_string_buffer(n)
+        lib.mixq_plugin_serialize(h, buf)
+        assert struct.unpack("<iii", buf.raw) == (512, 12288, 4096)
+        h2 = lib.mixq_plugin_deserialize(b"tensorrt_llm", buf, n)  # (:227-234, :935-952)
+        assert h2
+        buf2 = ctypes.create_string_buffer(n)
+        lib.mixq_plugin_serialize(h2, buf2)
+        assert buf2.raw == buf.raw
+        h3 = lib.mixq_plugin_clone(h2)
+        buf3 = ctypes.create_string_buffer(n)
+        lib.mixq_plugin_serialize(h3, buf3)
+        assert buf3.raw == buf.raw and lib.mixq_plugin_namespace(h3) == b"tensorrt_llm"
+        lib.mixq_plugin_destroy(h3)
+        lib.mixq_plugin_destroy(h2)
+        assert lib.mixq_plugin_deserialize(b"tensorrt_llm", buf, 8) is None   # truncated engine blob
+    finally:
+        lib.mixq_plugin_destroy(h)
+
+
+def test_workspace_size(lib):
+    M, N, K = 512, 12288, 4096
+    need = lib.mixq_workspace_size(M, N, K)
+    raw = M * K + 2 * M + 256 * M                                  # A8 | scale_a | fp_A  (:406-421)
+    assert raw <= need <= raw + 4 * 128
+    # far below the reference's max(M*K + 2M + 2KN, 16MN) (:342-346), and no int overflow for big M
+    assert need < max(M * K + 2 * M + 2 * K * N, 16 * M * N)
+    big = lib.mixq_workspace_size(65536, 12288, 11008)
+    assert big > 2**29 and big < 2**31
+    assert lib.mixq_workspace_size(0, N, K) == 0
+    lib.initOpenAiTritonPlugins(None, b"tensorrt_llm")
+    h = lib.mixq_plugin_create(b"tensorrt_llm", M, N, K)
+    try:
+        dims = (ctypes.c_int64 * 3)(32, 16, K)                     # [batch, seq, K] -> M = 512
+        assert lib.mixq_plugin_workspace_size(h, dims, 3, N) == need
+    finally:
+        lib.mixq_plugin_destroy(h)
+
+
+def test_argument_validation_without_gpu(lib):
+    """Bad arguments are rejected with a status and a message before any CUDA call; nothing throws."""
+    from mixq_tensorrt_llm_b200 import binding
+    t = binding.Tensors()
+    assert lib.mixq_enqueue(None, 1, 8, 16, None, 0, 0, None) == -1
+    assert lib.mixq_enqueue(ctypes.byref(t), 8, 8, 16, None, 0, 0, None) == -1          # null tensors
+    assert b"null" in lib.mixq_last_error()
+    assert lib.mixq_enqueue(ctypes.byref(t), 0, 8, 16, None, 0, 0, None) == 0           # M == 0 is a no-op
+    assert lib.mixq_enqueue(ctypes.byref(t), -1, 8, 16, None, 0, 0, None) == -1
+    assert lib.mixq_gemm_dequant(1, 1, 1, 1, None, None, 1, 8, 8, 24, None) == -4        # K % 16
+    assert lib.mixq_gemm_dequant(16, 16, 16, 16, None, None, 16, 8, 12, 32, None) == -4  # N % 8
+    assert lib.mixq_gemm_dequant(16, 16, 16, 16, 16, None, 16, 8, 8, 32, None) == -1     # fp_A without fp_weight
+    assert lib.mixq_quant_extract(16, 4, 20, None, 0, 16, 16, None, 0, None) == -1       # K % 8
+    assert lib.mixq_set_gemm_config(99) == -1
+
+
+def test_no_cpu_fallback(lib):
+    """Without a B200 the compute entry points fail loudly (status + message), they do not compute."""
+    import torch
+    from mixq_tensorrt_llm_b200 import binding
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.mixq_device_ok() == 0
+    with pytest.raises(binding.MixQError):
+        binding.require_device()
+    buf = (ctypes.c_uint8 * 4096)()
+    p = ctypes.addressof(buf)
+    p = (p + 127) // 128 * 128
+    rc = lib.mixq_quant_extract(p, 1, 64, None, 0, p + 1024, p + 2048, None, 0, None)
+    assert rc == -3 and b"device" in lib.mixq_last_error()
+    rc = lib.mixq_gemm_dequant(p, p, p, p, None, None, p, 8, 8, 64, None)
+    assert rc == -3
+
+
+def test_product_does_not_touch_oracle():
+    """The shipped package must not import, link or execute anything under oracle/."""
+    pkg = ROOT / "mixq_tensorrt_llm_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cpp")) + list(pkg.rglob("*.h")) + \
+            list(pkg.rglob("*.cuh")):
+        txt = f.read_text()
+        assert "oracle" not in txt.lower() or f.name == "__never__", f
+    so = pkg / "libmixq_b200.so"
+    if so.exists():
+        ldd = subprocess.run(["ldd", str(so)], capture_output=True, text=True).stdout
+        assert "oracle" not in ldd and "ref_" not in ldd

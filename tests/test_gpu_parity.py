@@ -1,0 +1,306 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI
+(libmixq_b200.so via ctypes); the checkers are the CPU oracle (oracle/) and, when present, the
+reference's own CUDA kernels compiled from /root/reference/kernel/i8gemm.cu (oracle/_ref).
+
+Tolerances:
+  * INT8 codes, per-token scales, outlier gather: bit-exact vs the reference kernels and vs the
+    oracle (which emulates device __hdiv with the captured rcp.approx table);
+  * int32 accumulators: exact -- with the outlier slab disabled the fp16 output must equal the
+    oracle bit for bit;
+  * full mixed output: <= 2 fp16 ulp element-wise and rel-Frobenius <= 1e-3 vs the reference
+    kernels / oracle (the only freedom is the accumulation order of the 128-term fp16 outlier
+    dot product inside cuBLAS / the tensor core).
+"""
+import ctypes
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import refgpu
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def B(lib):
+    from mixq_tensorrt_llm_b200 import binding
+    binding.require_device()
+    return binding
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+def _ulp_diff(a, b):
+    """distance in fp16 ulps (of b) between two fp16 arrays"""
+    a32, b32 = a.astype(np.float32), b.astype(np.float32)
+    ulp = np.spacing(np.abs(b).astype(np.float16)).astype(np.float32)
+    with np.errstate(invalid="ignore"):
+        return np.abs(a32 - b32) / ulp
+
+
+def _edge_activations(O, M, K, act_scale=None, seed=0):
+    if act_scale is None:
+        act_scale = O.synth_act_scale(K, seed)
+    A = O.synth_activations(M, act_scale, seed=seed + 100)
+    if M >= 10:
+        A[1] = 0
+        A[2, :] = np.float16(6e-8)
+        A[3, K // 2] = np.float16(65504.0)
+        A[4, 3] = np.float16(np.inf)
+        A[5, 7] = np.float16(np.nan)
+        A[6] = (np.arange(K) % 255 - 127).astype(np.float16) * np.float16(0.5)
+        A[7, :] = np.float16(-1.0)
+    return A
+
+
+# ----------------------------------------------------------------------------- stage 1
+@pytest.mark.parametrize("M,K", [(1, 256), (5, 256), (48, 512), (33, 4096), (512, 4096), (64, 11008), (3, 28672),
+                                 (1500, 1024)])
+@pytest.mark.parametrize("mask", [False, True])
+def test_quant_extract_bit_exact(B, oracle, M, K, mask):
+    A = _edge_activations(oracle, M, K, seed=M + K)
+    rng = np.random.default_rng(K)
+    ind = rng.choice(K, size=128, replace=False).astype(np.int32)
+    tA, tind = _t(A), _t(ind)
+    A8 = torch.full((M, K), 99, dtype=torch.int8, device=DEV)
+    sa = torch.zeros(M, dtype=torch.float16, device=DEV)
+    fpA = torch.zeros(M, 128, dtype=torch.float16, device=DEV)
+    B.quant_extract(tA, tind, A8, sa, fpA, flags=B.FLAG_MASK_OUTLIERS if mask else 0)
+    torch.cuda.synchronize()
+    assert torch.equal(tA.view(torch.int16), _t(A).view(torch.int16))          # input untouched
+    # gather: exact copy
+    assert np.array_equal(fpA.cpu().numpy().view(np.uint16), A[:, ind].view(np.uint16))
+    # oracle (device-__hdiv emulation needs the captured rcp table for bit-exactness)
+    oq, osa = oracle.quant(A, ind=ind, mask=mask)
+    gq, gsa = A8.cpu().numpy(), sa.cpu().numpy()
+    assert np.array_equal(gsa.view(np.uint16), osa.view(np.uint16))
+    if oracle.rcp_table() is not None:
+        assert np.array_equal(gq, oq)
+    else:
+        assert (gq != oq).mean() < 1e-4 and np.abs(gq.astype(int) - oq.astype(int)).max() <= 1
+    # the reference's own kernels (plugin semantics = no mask)
+    if refgpu.available() and not mask:
+        rq, rsa = refgpu.int8quant(tA)
+        rfp = refgpu.extract(tA, tind)
+        torch.cuda.synchronize()
+        assert torch.equal(rsa.view(torch.int16), sa.view(torch.int16))
+        assert torch.equal(rq, A8)
+        assert torch.equal(rfp.view(torch.int16), fpA.view(torch.int16))
+
+
+def test_quant_only_no_outliers(B, oracle):
+    A = _edge_activations(oracle, 40, 768, seed=3)
+    tA = _t(A)
+    A8 = torch.empty(40, 768, dtype=torch.int8, device=DEV)
+    sa = torch.empty(40, dtype=torch.float16, device=DEV)
+    B.quant_extract(tA, None, A8, sa, None)
+    torch.cuda.synchronize()
+    oq, osa = oracle.quant(A)
+    assert np.array_equal(sa.cpu().numpy().view(np.uint16), osa.view(np.uint16))
+    assert (A8.cpu().numpy() != oq).mean() < (1e-4 if oracle.rcp_table() is None else 1e-12)
+
+
+# ----------------------------------------------------------------------------- stage 2
+GEMM_SHAPES = [(128, 128, 128), (128, 128, 256), (256, 256, 512), (1, 8, 16), (100, 136, 144), (5, 4096, 4096),
+               (130, 264, 4096), (512, 1024, 4096), (300, 512, 11008), (257, 1280, 8192)]
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
+    """No outlier slab: int32 accumulation is exact, the epilogue is one fma + one rounding, so
+    the fp16 output must equal the oracle bit for bit."""
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    q = rng.integers(-127, 128, (M, K), dtype=np.int8)
+    w = rng.integers(-128, 128, (N, K), dtype=np.int8)
+    sa = (rng.random(M) * 0.05 + 1e-3).astype(np.float16)
+    sb = (rng.random(N) * 0.002 + 1e-4).astype(np.float16)
+    out = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
+    prev = lib.mixq_set_gemm_config(cfg)
+    try:
+        B.gemm_dequant(_t(q), _t(w), _t(sa), _t(sb), None, None, out)
+        torch.cuda.synchronize()
+    finally:
+        lib.mixq_set_gemm_config(prev)
+    ref = oracle.epilogue(oracle.igemm(q, w), sa, sb, None)
+    got = out.cpu().numpy()
+    bad = np.argwhere(got.view(np.uint16) != ref.view(np.uint16))
+    assert bad.size == 0, f"{len(bad)} mismatches, first at {bad[:5].tolist()}: got {got[tuple(bad[0])]} want {ref[tuple(bad[0])]}"
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (100, 136, 144), (64, 512, 4096), (512, 1024, 4096)])
+def test_gemm_dequant_with_outlier_slab(B, lib, oracle, cfg, M, N, K):
+    rng = np.random.default_rng(M + N + K)
+    q = rng.integers(-127, 128, (M, K), dtype=np.int8)
+    w = rng.integers(-128, 128, (N, K), dtype=np.int8)
+    sa = (rng.random(M) * 0.05 + 1e-3).astype(np.float16)
+    sb = (rng.random(N) * 0.002 + 1e-4).astype(np.float16)
+    fpA = (rng.standard_normal((M, 128)) * 4).astype(np.float16)
+    fpW = (rng.standard_normal((N, 128)) * 0.05).astype(np.float16)
+    out = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
+    prev = lib.mixq_set_gemm_config(cfg)
+    try:
+        B.gemm_dequant(_t(q), _t(w), _t(sa), _t(sb), _t(fpA), _t(fpW), out)
+        torch.cuda.synchronize()
+    finally:
+        lib.mixq_set_gemm_config(prev)
+    ref = oracle.epilogue(oracle.igemm(q, w), sa, sb, oracle.outlier_gemm(fpA, fpW))
+    got = out.cpu().numpy()
+    assert np.isfinite(got.astype(np.float32)).all()
+    assert _ulp_diff(got, ref).max() <= 2.0
+    rel = np.linalg.norm(got.astype(np.float64) - ref.astype(np.float64)) / np.linalg.norm(ref.astype(np.float64))
+    assert rel <= 1e-3
+    # pure outlier product (int part zeroed): isolates the kind::f16 accumulator
+    out2 = torch.empty_like(out)
+    B.gemm_dequant(_t(np.zeros_like(q)), _t(w), _t(sa), _t(sb), _t(fpA), _t(fpW), out2)
+    torch.cuda.synchronize()
+    ref2 = oracle.outlier_gemm(fpA, fpW)
+    assert _ulp_diff(out2.cpu().numpy(), ref2).max() <= 1.0
+
+
+# ----------------------------------------------------------------------------- whole path
+def _packed(oracle, name, N, K, seed=1234):
+    a = np.load(GOLD / "act_scales_l0.npz")
+    scale = a[name] if name in a.files and a[name].shape[0] == K else None
+    return oracle.synth_linear(N, K, scale, seed=seed)
+
+
+ENQ_CASES = [  # (act-scale fixture, M, N, K)   N kept moderate so the CPU oracle stays fast
+    ("Llama-2-7b/self_attn.q_proj", 1, 512, 4096),       # config 0: bs = 1 (mixed path forced for M <= 4)
+    ("Llama-2-7b/self_attn.q_proj", 32, 1024, 4096),
+    ("Llama-2-7b/self_attn.q_proj", 512, 768, 4096),
+    ("Llama-2-7b/mlp.down_proj", 77, 512, 11008),
+    ("qwen2-7b-instruct/self_attn.q_proj", 200, 512, 3584),
+    ("Llama-2-70b/mlp.down_proj", 33, 256, 28672),
+    ("synthetic", 130, 264, 400),
+]
+
+
+@pytest.mark.parametrize("name,M,N,K", ENQ_CASES)
+def test_enqueue_matches_oracle_and_reference_plugin(B, oracle, name, M, N, K):
+    lin = _packed(oracle, name, N, K)
+    A = oracle.synth_activations(M, lin["act_scale"], seed=M)
+    tA, tW, tsb, tfw, tind = _t(A), _t(lin["W8"]), _t(lin["scale_b"]), _t(lin["fp_weight"]), _t(lin["ind"])
+    out = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
+    ws = torch.empty(B.workspace_size(M, N, K), dtype=torch.uint8, device=DEV)
+    B.enqueue(tA, tW, tsb, tfw, tind, out, ws)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    r = oracle.forward(A, lin["W8"], lin["scale_b"], lin["fp_weight"], lin["ind"], return_parts=True)
+    # workspace carries the stage-1 results in the reference's order: A8 | scale_a | fp_A
+    a8 = ws[: M * K].view(torch.int8).view(M, K).cpu().numpy()
+    if oracle.rcp_table() is not None:
+        assert np.array_equal(a8, r["q"])
+    assert _ulp_diff(got, r["out"]).max() <= 2.0
+    rel = np.linalg.norm(got.astype(np.float64) - r["out"].astype(np.float64)) / np.linalg.norm(r["out"].astype(np.float64))
+    assert rel <= 1e-3, rel
+    if refgpu.available() and M > 4 and K >= 256:
+        ref = refgpu.enqueue(tA, tW, tsb, tfw, tind)
+        torch.cuda.synchronize()
+        ref = ref.cpu().numpy()
+        assert _ulp_diff(got, ref).max() <= 2.0
+        rel = np.linalg.norm(got.astype(np.float64) - ref.astype(np.float64)) / np.linalg.norm(ref.astype(np.float64))
+        assert rel <= 1e-3, rel
+
+
+def test_enqueue_workspace_and_errors(B, lib, oracle):
+    lin = _packed(oracle, "synthetic", 64, 256)
+    A = oracle.synth_activations(16, lin["act_scale"])
+    tA, tW, tsb, tfw, tind = _t(A), _t(lin["W8"]), _t(lin["scale_b"]), _t(lin["fp_weight"]), _t(lin["ind"])
+    out = torch.empty(16, 64, dtype=torch.float16, device=DEV)
+    small = torch.empty(64, dtype=torch.uint8, device=DEV)
+    with pytest.raises(B.MixQError, match="workspace"):
+        B.enqueue(tA, tW, tsb, tfw, tind, out, small)
+    # unaligned workspace base is realigned like nextWorkspacePtr (TsinghuaMixQPlugin.cpp:206-215)
+    ws = torch.empty(B.workspace_size(16, 64, 256) + 64, dtype=torch.uint8, device=DEV)
+    B.enqueue(tA, tW, tsb, tfw, tind, out, ws[3:])
+    torch.cuda.synchronize()
+    ref = oracle.forward(A, lin["W8"], lin["scale_b"], lin["fp_weight"], lin["ind"])
+    assert _ulp_diff(out.cpu().numpy(), ref).max() <= 2.0
+
+
+def test_enqueue_is_graph_capturable_and_async(B, oracle):
+    """enqueue must not sync or allocate: capture it in a CUDA graph and replay (SURVEY 8b threading/stream row)."""
+    lin = _packed(oracle, "synthetic", 256, 512)
+    A = oracle.synth_activations(96, lin["act_scale"])
+    tA, tW, tsb, tfw, tind = _t(A), _t(lin["W8"]), _t(lin["scale_b"]), _t(lin["fp_weight"]), _t(lin["ind"])
+    out = torch.zeros(96, 256, dtype=torch.float16, device=DEV)
+    ws = torch.empty(B.workspace_size(96, 256, 512), dtype=torch.uint8, device=DEV)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        B.enqueue(tA, tW, tsb, tfw, tind, out, ws, stream=s)   # warm-up (first-use attribute sets)
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        out.zero_()
+        with torch.cuda.graph(g, stream=s):
+            B.enqueue(tA, tW, tsb, tfw, tind, out, ws, stream=s)
+        g.replay()
+        g.replay()
+    torch.cuda.synchronize()
+    ref = oracle.forward(A, lin["W8"], lin["scale_b"], lin["fp_weight"], lin["ind"])
+    assert _ulp_diff(out.cpu().numpy(), ref).max() <= 2.0
+
+
+def test_python_plugin_mirror(B, oracle):
+    """MixQLinear / mixgemm (reference plugin.py) end to end, 3-D activations, bias outside the plugin."""
+    from mixq_tensorrt_llm_b200.plugin import MixQLinear
+    lin = _packed(oracle, "Llama-2-7b/self_attn.q_proj", 384, 4096)
+    mod = MixQLinear(4096, 384, bias=True, device=DEV)
+    bias = (np.arange(384) % 7 - 3).astype(np.float16)
+    mod.load_packed(_t(lin["W8"]), _t(lin["scale_b"]), _t(lin["fp_weight"]), _t(lin["ind"]), _t(bias))
+    assert mod.weight.shape == (384, 2048) and mod.fp_ind.shape == (256,) and mod.weight.dtype == torch.float16
+    A = oracle.synth_activations(6 * 5, lin["act_scale"]).reshape(6, 5, 4096)
+    y = mod(_t(A))
+    torch.cuda.synchronize()
+    assert y.shape == (6, 5, 384)
+    ref = oracle.forward(A.reshape(30, 4096), lin["W8"], lin["scale_b"], lin["fp_weight"], lin["ind"])
+    ref = (ref.astype(np.float32) + bias.astype(np.float32)).astype(np.float16)
+    assert _ulp_diff(y.cpu().numpy().reshape(30, 384), ref).max() <= 2.0
+
+
+# ----------------------------------------------------------------------------- full-size properties
+def test_full_size_properties(B, oracle):
+    """Llama-2-7B qkv shape (N=12288, K=4096) at M=4096: size-independent properties + sampled rows vs oracle."""
+    M, N, K = 4096, 12288, 4096
+    lin = _packed(oracle, "Llama-2-7b/self_attn.q_proj", N, K)
+    A = oracle.synth_activations(M, lin["act_scale"], seed=5)
+    tA, tW, tsb, tfw, tind = _t(A), _t(lin["W8"]), _t(lin["scale_b"]), _t(lin["fp_weight"]), _t(lin["ind"])
+    ws = torch.empty(B.workspace_size(M, N, K), dtype=torch.uint8, device=DEV)
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    B.enqueue(tA, tW, tsb, tfw, tind, out, ws)
+    torch.cuda.synchronize()
+    # (1) sampled rows against the oracle
+    rows = np.random.default_rng(0).choice(M, 24, replace=False)
+    ref = oracle.forward(A[rows], lin["W8"], lin["scale_b"], lin["fp_weight"], lin["ind"])
+    got = out[_t(rows)].cpu().numpy()
+    assert _ulp_diff(got, ref).max() <= 2.0
+    # (2) token permutation equivariance, bit-exact (per-token quantisation, no cross-row coupling)
+    perm = torch.randperm(M, device=DEV)
+    out_p = torch.empty_like(out)
+    B.enqueue(tA[perm].contiguous(), tW, tsb, tfw, tind, out_p, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(out_p.view(torch.int16), out[perm].view(torch.int16))
+    # (3) output-channel slicing: a column-parallel shard reproduces its slice bit for bit
+    n0, n1 = 4096, 4096 + 1280
+    out_s = torch.empty(M, n1 - n0, dtype=torch.float16, device=DEV)
+    B.enqueue(tA, tW[n0:n1].contiguous(), tsb[n0:n1].contiguous(), tfw[n0:n1].contiguous(), tind, out_s, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(out_s.view(torch.int16), out[:, n0:n1].contiguous().view(torch.int16))
+    # (4) scaling the activations by a power of two scales the per-token scale, not the codes
+    out_2 = torch.empty_like(out)
+    B.enqueue((tA * 2).contiguous(), tW, tsb, tfw, tind, out_2, ws)
+    torch.cuda.synchronize()
+    # (exact up to fp16-subnormal rounding of the outlier product, which is not scale invariant)
+    assert (out_2.view(torch.int16) != (out * 2).view(torch.int16)).float().mean().item() < 1e-6
+    # (5) deterministic: same call, same bits
+    out_r = torch.empty_like(out)
+    B.enqueue(tA, tW, tsb, tfw, tind, out_r, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(out_r.view(torch.int16), out.view(torch.int16))
