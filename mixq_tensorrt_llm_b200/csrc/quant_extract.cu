@@ -179,13 +179,11 @@ int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, i
     const DeviceInfo& dev = device_info();
     if (!dev.ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
     const size_t smem = static_cast<size_t>(K) * 2 * 2;
-    if (smem > dev.max_smem_optin) return set_error(MIXQ_ERR_UNSUPPORTED, "quant_extract: K too large for shared memory staging");
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem + 1024 > dev.max_smem_optin) return set_error(MIXQ_ERR_UNSUPPORTED, "quant_extract: K too large for shared memory staging");
+    if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(mixq_quant_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(dev.max_smem_optin));
+                                             static_cast<int>(smem));
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(quant_extract)");
-        configured = dev.max_smem_optin;
     }
     // resident CTAs per SM: limited by threads (2048/256 = 8) and by shared memory
     int per_sm = static_cast<int>(dev.smem_per_sm / (smem + 1024));

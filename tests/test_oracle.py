@@ -172,7 +172,11 @@ def test_oracle_matches_reference_kernels_fixture(oracle):
     assert np.array_equal(q, z["ref_q"])
     assert np.array_equal(oracle.gather(A, ind).view(np.uint16), z["ref_fpA"].view(np.uint16))
     out = oracle.forward(A, z["W8"], z["scale_b"], z["fp_weight"], ind)
-    d = np.abs(out.astype(np.float32) - z["ref_out"].astype(np.float32))
-    ulp = np.spacing(np.abs(z["ref_out"]).astype(np.float16)).astype(np.float32)
+    ref = z["ref_out"]
+    nan_o, nan_r = np.isnan(out.astype(np.float32)), np.isnan(ref.astype(np.float32))
+    assert np.array_equal(nan_o, nan_r) and nan_r.any()          # the Inf token poisons its row in both
+    ok = ~nan_r
+    d = np.abs(out.astype(np.float32) - ref.astype(np.float32))[ok]
+    ulp = np.spacing(np.abs(ref).astype(np.float16)).astype(np.float32)[ok]
     assert (d <= ulp).all()
-    assert (out.view(np.uint16) != z["ref_out"].view(np.uint16)).mean() < 0.02
+    assert (out.view(np.uint16) != ref.view(np.uint16))[ok].mean() < 0.02
