@@ -44,24 +44,35 @@ constexpr int kEpilogueWarp0 = 4;
 constexpr int kNumEpilogueThreads = 128;
 constexpr int kOutlierKBlocks = (MIXQ_NUM_OUTLIERS * 2) / kBlockKBytes;  // 2
 
-template <int BLOCK_N, int ACC_STAGES, int STAGES>
+// CTA  = 1: one CTA per 128 x BLOCK_N tile (tcgen05 cta_group::1, UMMA M = 128)
+// CTA  = 2: a CTA pair (cluster of 2 on one TPC) per 256 x BLOCK_N tile (cta_group::2, UMMA M = 256):
+//           each CTA stages its own 128 rows of A and HALF of the W rows, the leader issues the MMAs
+//           for both, each CTA's TMEM holds its 128 accumulator rows.  Halves the shared-memory
+//           and L2 operand traffic per MAC.
+template <int CTA, int BLOCK_N, int ACC_STAGES, int STAGES>
 struct GemmTraits {
-    static constexpr int kBlockN = BLOCK_N;
+    static constexpr int kCta = CTA;
+    static constexpr int kBlockN = BLOCK_N;            // UMMA N = output columns per tile
+    static constexpr int kLoadN = BLOCK_N / CTA;       // W rows each CTA stages per K-block
+    static constexpr int kTileM = kBlockM * CTA;       // output rows per tile
     static constexpr int kAccStages = ACC_STAGES;
     static constexpr int kStages = STAGES;
     static constexpr int kABytes = kBlockM * kBlockKBytes;
-    static constexpr int kBBytes = BLOCK_N * kBlockKBytes;
+    static constexpr int kBBytes = kLoadN * kBlockKBytes;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kAccCols = 2 * BLOCK_N;  // int32 accumulator | fp32 outlier accumulator
     static constexpr int kTmemColsRaw = kAccCols * ACC_STAGES;
     static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : kTmemColsRaw <= 64 ? 64 : kTmemColsRaw <= 128 ? 128
                                      : kTmemColsRaw <= 256 ? 256 : 512;
+    static_assert(CTA == 1 || CTA == 2, "CTA group size");
     static_assert(kTmemColsRaw <= 512, "TMEM has 512 columns");
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
+    static_assert(kLoadN % 8 == 0 && kBBytes % 1024 == 0, "W tile must be whole 8-row swizzle groups");
     // dynamic smem: ring | sb staging (2 x BLOCK_N floats) | barriers | tmem ptr  (+1024 alignment slack)
     static constexpr int kNumBarriers = 2 * STAGES + 2 * ACC_STAGES;
     static constexpr size_t kSmemBytes =
         1024 + static_cast<size_t>(STAGES) * kStageBytes + 2 * BLOCK_N * sizeof(float) + kNumBarriers * 8 + 16;
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 struct TileCoord {
@@ -86,6 +97,7 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
                          __half* __restrict__ Out, int M, int N, int K, int has_outlier, int m_tiles, int n_tiles,
                          int group_m) {
     constexpr int BLOCK_N = T::kBlockN;
+    constexpr int CTA = T::kCta;
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -99,6 +111,11 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
 
     const int warp_idx = threadIdx.x >> 5;  // warp-uniform
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CTA == 2) ? ptx::cluster_ctarank() : 0u;
+    const bool is_leader = cta_rank == 0;
+    // tiles are distributed over CTA groups (a single CTA, or a pair working on one 256-row tile)
+    const int group_id = blockIdx.x / CTA;
+    const int num_groups = gridDim.x / CTA;
 
     if (warp_idx == 0 && ptx::elect_one()) {
         ptx::prefetch_tensormap(&tm_a8);
@@ -110,21 +127,26 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
     }
     if (warp_idx == 1 && ptx::elect_one()) {
         for (int i = 0; i < T::kStages; ++i) {
-            ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], 1);
+            ptx::mbar_init(&full_bar[i], 1);   // leader's arrive.expect_tx; TMA bytes of the whole group
+            ptx::mbar_init(&empty_bar[i], 1);  // one tcgen05.commit (multicast to both CTAs of a pair)
         }
         for (int i = 0; i < T::kAccStages; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
-            ptx::mbar_init(&tmem_empty_bar[i], kNumEpilogueThreads / 32);
+            ptx::mbar_init(&tmem_empty_bar[i], CTA * kNumEpilogueThreads / 32);  // every epilogue warp of the group
         }
         ptx::fence_barrier_init();
     }
     if (warp_idx == 2) {
-        ptx::tmem_alloc(tmem_ptr_s, T::kTmemCols);
-        ptx::tmem_relinquish();
+        if constexpr (CTA == 2) {
+            ptx::tmem_alloc_2cta(tmem_ptr_s, T::kTmemCols);
+            ptx::tmem_relinquish_2cta();
+        } else {
+            ptx::tmem_alloc(tmem_ptr_s, T::kTmemCols);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before_sync();
-    __syncthreads();
+    if constexpr (CTA == 2) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr_s;
 
@@ -138,25 +160,27 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
 
     if (warp_idx == 0) {
         if (ptx::elect_one()) {
-            // ===================== TMA producer =====================
+            // ===================== TMA producer (every CTA) =====================
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = group_id; tile < num_tiles; tile += num_groups) {
                 const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, group_m);
-                const int m0 = tc.m_blk * kBlockM;
-                const int n0 = tc.n_blk * BLOCK_N;
+                const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
+                const int n0 = tc.n_blk * BLOCK_N + static_cast<int>(cta_rank) * T::kLoadN;
                 for (int it = 0; it < num_items; ++it) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], T::kStageBytes);
+                    if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], T::kStageBytes * CTA);
                     uint8_t* sA = ring + static_cast<size_t>(stage) * T::kStageBytes;
                     uint8_t* sB = sA + T::kABytes;
-                    if (it < n_f) {
-                        ptx::tma_load_2d(sA, &tm_fa, &full_bar[stage], it * (kBlockKBytes / 2), m0, ptx::kEvictNormal);
-                        ptx::tma_load_2d(sB, &tm_fw, &full_bar[stage], it * (kBlockKBytes / 2), n0, ptx::kEvictNormal);
+                    const CUtensorMap* ma = it < n_f ? &tm_fa : &tm_a8;
+                    const CUtensorMap* mb = it < n_f ? &tm_fw : &tm_w8;
+                    const int k0 = it < n_f ? it * (kBlockKBytes / 2) : (it - n_f) * kBlockKBytes;
+                    if constexpr (CTA == 2) {
+                        ptx::tma_load_2d_2cta(sA, ma, &full_bar[stage], k0, m0, ptx::kEvictNormal);
+                        ptx::tma_load_2d_2cta(sB, mb, &full_bar[stage], k0, n0, ptx::kEvictNormal);
                     } else {
-                        const int k0 = (it - n_f) * kBlockKBytes;
-                        ptx::tma_load_2d(sA, &tm_a8, &full_bar[stage], k0, m0, ptx::kEvictNormal);
-                        ptx::tma_load_2d(sB, &tm_w8, &full_bar[stage], k0, n0, ptx::kEvictNormal);
+                        ptx::tma_load_2d(sA, ma, &full_bar[stage], k0, m0, ptx::kEvictNormal);
+                        ptx::tma_load_2d(sB, mb, &full_bar[stage], k0, n0, ptx::kEvictNormal);
                     }
                     if (++stage == T::kStages) {
                         stage = 0;
@@ -167,15 +191,15 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
         }
         __syncwarp();
     } else if (warp_idx == 1) {
-        if (ptx::elect_one()) {
-            // ===================== MMA issuer =====================
-            constexpr uint32_t idesc_i8 = ptx::make_idesc_i8(kBlockM, BLOCK_N);
-            constexpr uint32_t idesc_f16 = ptx::make_idesc_f16(kBlockM, BLOCK_N);
+        if (is_leader && ptx::elect_one()) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            constexpr uint32_t idesc_i8 = ptx::make_idesc_i8(T::kTileM, BLOCK_N);
+            constexpr uint32_t idesc_f16 = ptx::make_idesc_f16(T::kTileM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int acc_stage = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = group_id; tile < num_tiles; tile += num_groups) {
                 ptx::mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
                 ptx::tc_fence_after_sync();
                 const uint32_t tmem_i = tmem_base + acc_stage * T::kAccCols;
@@ -186,24 +210,29 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
                     const uint32_t sA = ptx::smem_u32(ring + static_cast<size_t>(stage) * T::kStageBytes);
                     const uint64_t da = ptx::make_smem_desc_sw128(sA);
                     const uint64_t db = ptx::make_smem_desc_sw128(sA + T::kABytes);
-                    if (it < n_f) {
 #pragma unroll
-                        for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k)
-                            ptx::umma_f16(tmem_f, da + k * (kUmmaKBytes >> 4), db + k * (kUmmaKBytes >> 4), idesc_f16,
-                                          (it > 0 || k > 0) ? 1u : 0u);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k)
-                            ptx::umma_i8(tmem_i, da + k * (kUmmaKBytes >> 4), db + k * (kUmmaKBytes >> 4), idesc_i8,
-                                         (it > n_f || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k) {
+                        const uint64_t dak = da + k * (kUmmaKBytes >> 4), dbk = db + k * (kUmmaKBytes >> 4);
+                        if (it < n_f) {
+                            const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+                            if constexpr (CTA == 2) ptx::umma_f16_2cta(tmem_f, dak, dbk, idesc_f16, acc);
+                            else ptx::umma_f16(tmem_f, dak, dbk, idesc_f16, acc);
+                        } else {
+                            const uint32_t acc = (it > n_f || k > 0) ? 1u : 0u;
+                            if constexpr (CTA == 2) ptx::umma_i8_2cta(tmem_i, dak, dbk, idesc_i8, acc);
+                            else ptx::umma_i8(tmem_i, dak, dbk, idesc_i8, acc);
+                        }
                     }
-                    ptx::umma_commit(&empty_bar[stage]);  // slot reusable once these MMAs have read it
+                    // slot reusable (in both CTAs) once these MMAs have read it
+                    if constexpr (CTA == 2) ptx::umma_commit_2cta(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
                     if (++stage == T::kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                ptx::umma_commit(&tmem_full_bar[acc_stage]);  // accumulators complete
+                // accumulators complete (signalled to the epilogue warps of both CTAs)
+                if constexpr (CTA == 2) ptx::umma_commit_2cta(&tmem_full_bar[acc_stage]);
+                else ptx::umma_commit(&tmem_full_bar[acc_stage]);
                 if (++acc_stage == T::kAccStages) {
                     acc_stage = 0;
                     acc_phase ^= 1;
@@ -212,16 +241,16 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
         }
         __syncwarp();
     } else if (warp_idx >= kEpilogueWarp0) {
-        // ===================== epilogue =====================
+        // ===================== epilogue (every CTA: its own 128 accumulator rows) =====================
         const int quarter = warp_idx - kEpilogueWarp0;  // == warp_idx % 4: the TMEM lane quarter this warp may read
         const int et = threadIdx.x - kEpilogueWarp0 * 32;
         const int row = quarter * 32 + lane;
         int acc_stage = 0;
         uint32_t acc_phase = 0;
         int local_tile = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+        for (int tile = group_id; tile < num_tiles; tile += num_groups, ++local_tile) {
             const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, group_m);
-            const int m0 = tc.m_blk * kBlockM;
+            const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
             const int n0 = tc.n_blk * BLOCK_N;
             float* sbt = sb_s + (local_tile & 1) * BLOCK_N;
             for (int j = et; j < BLOCK_N; j += kNumEpilogueThreads)
@@ -268,10 +297,13 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
                     }
                 }
             }
-            // hand the accumulator stage back to the MMA warp
+            // hand the accumulator stage back to the MMA warp (which lives in the leader CTA)
             ptx::tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
+            if (lane == 0) {
+                if constexpr (CTA == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc_stage], 0);
+                else ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
+            }
             if (++acc_stage == T::kAccStages) {
                 acc_stage = 0;
                 acc_phase ^= 1;
@@ -282,8 +314,11 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
     // teardown
     ptx::pdl_launch_dependents();
     ptx::tc_fence_before_sync();
-    __syncthreads();
-    if (warp_idx == 2) ptx::tmem_dealloc(tmem_base, T::kTmemCols);
+    if constexpr (CTA == 2) ptx::cluster_sync(); else __syncthreads();
+    if (warp_idx == 2) {
+        if constexpr (CTA == 2) ptx::tmem_dealloc_2cta(tmem_base, T::kTmemCols);
+        else ptx::tmem_dealloc(tmem_base, T::kTmemCols);
+    }
 }
 
 // ---------------------------------------------------------------- host side
@@ -331,11 +366,11 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     CUtensorMap tm_a8, tm_w8, tm_fa, tm_fw;
     int rc;
     if ((rc = make_tmap(&tm_a8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, A8, M, K, kBlockM))) return rc;
-    if ((rc = make_tmap(&tm_w8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W8, N, K, T::kBlockN))) return rc;
+    if ((rc = make_tmap(&tm_w8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W8, N, K, T::kLoadN))) return rc;
     const int has_outlier = (fp_A && fp_weight) ? 1 : 0;
     if (has_outlier) {
         if ((rc = make_tmap(&tm_fa, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_A, M, MIXQ_NUM_OUTLIERS, kBlockM))) return rc;
-        if ((rc = make_tmap(&tm_fw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_weight, N, MIXQ_NUM_OUTLIERS, T::kBlockN)))
+        if ((rc = make_tmap(&tm_fw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_weight, N, MIXQ_NUM_OUTLIERS, T::kLoadN)))
             return rc;
     } else {
         tm_fa = tm_a8;
@@ -345,23 +380,35 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::kSmemBytes));
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_dequant)");
 
-    const int m_tiles = static_cast<int>((M + kBlockM - 1) / kBlockM);
+    const int m_tiles = static_cast<int>((M + T::kTileM - 1) / T::kTileM);
     const int n_tiles = static_cast<int>((N + T::kBlockN - 1) / T::kBlockN);
     const int64_t num_tiles = static_cast<int64_t>(m_tiles) * n_tiles;
     if (num_tiles > (1ll << 30)) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: too many tiles");
-    const int grid = static_cast<int>(num_tiles < dev.num_sms ? num_tiles : dev.num_sms);
-    const int group_m = 8;
+    const int64_t max_groups = dev.num_sms / T::kCta;
+    const int grid = static_cast<int>(num_tiles < max_groups ? num_tiles : max_groups) * T::kCta;
+    const int group_m = 8 / T::kCta;
 
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = T::kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (T::kCta == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, static_cast<const __half*>(scale_a),
                            static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M),
                            static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m);
@@ -393,11 +440,15 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
     if (cfg == kCfgAuto) cfg = kCfgN128x2;
     switch (cfg) {
         case kCfgN128x2:
-            return launch_cfg<GemmTraits<128, 2, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+            return launch_cfg<GemmTraits<1, 128, 2, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
         case kCfgN256x1:
-            return launch_cfg<GemmTraits<256, 1, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+            return launch_cfg<GemmTraits<1, 256, 1, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
         case kCfgN64x2:
-            return launch_cfg<GemmTraits<64, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+            return launch_cfg<GemmTraits<1, 64, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+        case kCfg2CtaN256x1:
+            return launch_cfg<GemmTraits<2, 256, 1, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+        case kCfg2CtaN128x2:
+            return launch_cfg<GemmTraits<2, 128, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
         default:
             return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: unknown config id");
     }

@@ -18,6 +18,7 @@ from oracle import oracle as O  # noqa: E402
 
 DEV = "cuda"
 res = {}
+CFGS = (1, 2, 4, 5)
 
 
 def t(x):
@@ -50,8 +51,8 @@ def run_gemm(cfg, q, w, sa, sb, fpA=None, fpW=None):
 
 def layout_probes():
     rng = np.random.default_rng(0)
-    for cfg in (1, 2, 3):
-        for (M, N, K) in [(128, 128, 128), (128, 256, 256), (256, 128, 512), (100, 136, 144)]:
+    for cfg in CFGS:
+        for (M, N, K) in [(128, 128, 128), (128, 256, 256), (256, 128, 512), (100, 136, 144), (384, 512, 1040)]:
             key = f"cfg{cfg}_{M}x{N}x{K}"
             try:
                 q = rng.integers(-127, 128, (M, K), dtype=np.int8)
@@ -112,7 +113,7 @@ def timings():
             r = {}
             r["quant_us"] = timeit(lambda: B.quant_extract(A, ind, A8, sa, fpA))
             r["quant_GBps"] = (3 * M * K + 258 * M) / r["quant_us"] / 1e3
-            for cfg in (1, 2, 3):
+            for cfg in CFGS:
                 lib.mixq_set_gemm_config(cfg)
                 us = timeit(lambda: B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out))
                 r[f"gemm_cfg{cfg}_us"] = us

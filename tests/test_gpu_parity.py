@@ -111,7 +111,7 @@ GEMM_SHAPES = [(128, 128, 128), (128, 128, 256), (256, 256, 512), (1, 8, 16), (1
                (130, 264, 4096), (512, 1024, 4096), (300, 512, 11008), (257, 1280, 8192)]
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     """No outlier slab: int32 accumulation is exact, the epilogue is one fma + one rounding, so
@@ -134,8 +134,8 @@ def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     assert bad.size == 0, f"{len(bad)} mismatches, first at {bad[:5].tolist()}: got {got[tuple(bad[0])]} want {ref[tuple(bad[0])]}"
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (100, 136, 144), (64, 512, 4096), (512, 1024, 4096)])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (100, 136, 144), (300, 520, 1040), (64, 512, 4096), (512, 1024, 4096)])
 def test_gemm_dequant_with_outlier_slab(B, lib, oracle, cfg, M, N, K):
     rng = np.random.default_rng(M + N + K)
     q = rng.integers(-127, 128, (M, K), dtype=np.int8)
