@@ -28,6 +28,7 @@
 //           tmem_full[kAccStages] (MMA -> epilogue), tmem_empty[kAccStages] (epilogue -> MMA).
 #include <cstdio>
 #include <mutex>
+#include <type_traits>
 
 #include "mixq_internal.h"
 #include "ptx.cuh"
@@ -193,43 +194,52 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
     } else if (warp_idx == 1) {
         if (is_leader && ptx::elect_one()) {
             // ===================== MMA issuer (leader CTA only) =====================
+            // The loop body runs once per 128-byte K-block and must stay well below the time the tensor
+            // core needs for it (4 MMAs = 256 cycles at N = 128), so everything loop-invariant is
+            // hoisted: descriptors are a per-stage constant plus 2 (= 32 B >> 4) per MMA, the outlier
+            // and int8 K-blocks run in separate loops, and the barrier of the NEXT stage is probed
+            // before the MMAs of this one are issued so its latency overlaps the issue.
             constexpr uint32_t idesc_i8 = ptx::make_idesc_i8(T::kTileM, BLOCK_N);
             constexpr uint32_t idesc_f16 = ptx::make_idesc_f16(T::kTileM, BLOCK_N);
+            constexpr uint32_t kDescStep = kUmmaKBytes >> 4;
+            const uint64_t desc_a0 = ptx::make_smem_desc_sw128(ptx::smem_u32(ring));
+            const uint64_t desc_b0 = ptx::make_smem_desc_sw128(ptx::smem_u32(ring) + T::kABytes);
             int stage = 0;
             uint32_t phase = 0;
             int acc_stage = 0;
             uint32_t acc_phase = 0;
+            bool ready = false;
+            auto issue_block = [&](auto kind_tag, uint32_t tmem_d, bool first) {
+                if (!ready) ptx::mbar_wait(&full_bar[stage], phase);
+                const int nstage = (stage + 1 == T::kStages) ? 0 : stage + 1;
+                const uint32_t nphase = (stage + 1 == T::kStages) ? phase ^ 1 : phase;
+                ready = ptx::mbar_try_wait(&full_bar[nstage], nphase);  // early probe of the next slot
+                ptx::tc_fence_after_sync();
+                const uint64_t da = desc_a0 + static_cast<uint64_t>(stage) * (T::kStageBytes >> 4);
+                const uint64_t db = desc_b0 + static_cast<uint64_t>(stage) * (T::kStageBytes >> 4);
+#pragma unroll
+                for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k) {
+                    const uint32_t acc = (first && k == 0) ? 0u : 1u;
+                    if constexpr (decltype(kind_tag)::value == 0) {
+                        if constexpr (CTA == 2) ptx::umma_f16_2cta(tmem_d, da + k * kDescStep, db + k * kDescStep, idesc_f16, acc);
+                        else ptx::umma_f16(tmem_d, da + k * kDescStep, db + k * kDescStep, idesc_f16, acc);
+                    } else {
+                        if constexpr (CTA == 2) ptx::umma_i8_2cta(tmem_d, da + k * kDescStep, db + k * kDescStep, idesc_i8, acc);
+                        else ptx::umma_i8(tmem_d, da + k * kDescStep, db + k * kDescStep, idesc_i8, acc);
+                    }
+                }
+                // slot reusable (in both CTAs of a pair) once these MMAs have read it
+                if constexpr (CTA == 2) ptx::umma_commit_2cta(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
+                stage = nstage;
+                phase = nphase;
+            };
             for (int tile = group_id; tile < num_tiles; tile += num_groups) {
                 ptx::mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
                 ptx::tc_fence_after_sync();
                 const uint32_t tmem_i = tmem_base + acc_stage * T::kAccCols;
                 const uint32_t tmem_f = tmem_i + BLOCK_N;
-                for (int it = 0; it < num_items; ++it) {
-                    ptx::mbar_wait(&full_bar[stage], phase);
-                    ptx::tc_fence_after_sync();
-                    const uint32_t sA = ptx::smem_u32(ring + static_cast<size_t>(stage) * T::kStageBytes);
-                    const uint64_t da = ptx::make_smem_desc_sw128(sA);
-                    const uint64_t db = ptx::make_smem_desc_sw128(sA + T::kABytes);
-#pragma unroll
-                    for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k) {
-                        const uint64_t dak = da + k * (kUmmaKBytes >> 4), dbk = db + k * (kUmmaKBytes >> 4);
-                        if (it < n_f) {
-                            const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-                            if constexpr (CTA == 2) ptx::umma_f16_2cta(tmem_f, dak, dbk, idesc_f16, acc);
-                            else ptx::umma_f16(tmem_f, dak, dbk, idesc_f16, acc);
-                        } else {
-                            const uint32_t acc = (it > n_f || k > 0) ? 1u : 0u;
-                            if constexpr (CTA == 2) ptx::umma_i8_2cta(tmem_i, dak, dbk, idesc_i8, acc);
-                            else ptx::umma_i8(tmem_i, dak, dbk, idesc_i8, acc);
-                        }
-                    }
-                    // slot reusable (in both CTAs) once these MMAs have read it
-                    if constexpr (CTA == 2) ptx::umma_commit_2cta(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
-                    if (++stage == T::kStages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
+                for (int it = 0; it < n_f; ++it) issue_block(std::integral_constant<int, 0>{}, tmem_f, it == 0);
+                for (int kb = 0; kb < num_kb; ++kb) issue_block(std::integral_constant<int, 1>{}, tmem_i, kb == 0);
                 // accumulators complete (signalled to the epilogue warps of both CTAs)
                 if constexpr (CTA == 2) ptx::umma_commit_2cta(&tmem_full_bar[acc_stage]);
                 else ptx::umma_commit(&tmem_full_bar[acc_stage]);
@@ -321,6 +331,317 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
     }
 }
 
+// =================================================================================================
+// Wide-tile variant ("stash" kernel): 256 output columns per tile with DOUBLE-BUFFERED int32
+// accumulators (2 x 256 TMEM columns = all of TMEM), so the epilogue of tile t overlaps the main
+// loop of tile t+1 while the operand traffic per MAC is the lowest the hardware allows
+// (with CTA = 2: 64 B/clk/SM from L2 and from shared memory).
+// There is no TMEM left for the fp32 outlier accumulator, so it borrows the *other* accumulator
+// buffer while that one is idle:
+//     MMA thread, tile t in buffer b:   I-MMAs [0, split) -> wait E(t-1) done -> F-MMAs into buffer b^1
+//                                       -> commit f_full -> I-MMAs [split, end) -> commit tmem_full(b)
+//     epilogue warps, tile t:           wait f_full -> drain F (fp32 -> fp16, the reference's rounding)
+//                                       into a thread-private shared-memory stash -> arrive f_drained(b^1)
+//                                       -> wait tmem_full(b) -> out = fma(float(I), sa*sb, stash) -> release b
+// f_drained(b^1) gates the main loop of tile t+1 (which accumulates into b^1); both happen half a
+// main loop earlier than needed, so in steady state the tensor core never waits.
+template <int CTA, int STAGES>
+struct StashTraits {
+    static constexpr int kCta = CTA;
+    static constexpr int kBlockN = 256;
+    static constexpr int kLoadN = kBlockN / CTA;
+    static constexpr int kTileM = kBlockM * CTA;
+    static constexpr int kStages = STAGES;
+    static constexpr int kABytes = kBlockM * kBlockKBytes;
+    static constexpr int kBBytes = kLoadN * kBlockKBytes;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = 512;
+    static constexpr int kStashBytes = kBlockM * kBlockN * 2;  // fp16 outlier product of this CTA's 128 rows
+    static constexpr int kNumBarriers = 2 * STAGES + 8;
+    static constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(STAGES) * kStageBytes + kStashBytes +
+                                         2 * kBlockN * sizeof(float) + kNumBarriers * 8 + 16;
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+template <class T>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_w8,
+                               const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fw,
+                               const __half* __restrict__ scale_a, const __half* __restrict__ scale_b,
+                               __half* __restrict__ Out, int M, int N, int K, int has_outlier, int m_tiles,
+                               int n_tiles, int group_m) {
+    constexpr int BLOCK_N = T::kBlockN;
+    constexpr int CTA = T::kCta;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;
+    uint4* stash = reinterpret_cast<uint4*>(ring + static_cast<size_t>(T::kStages) * T::kStageBytes);
+    float* sb_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stash) + T::kStashBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sb_s + 2 * BLOCK_N);
+    uint64_t* empty_bar = full_bar + T::kStages;
+    uint64_t* tmem_full_bar = empty_bar + T::kStages;  // [2] int32 accumulators of buffer b complete
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2] epilogue has read buffer b's int32 accumulators
+    uint64_t* f_full_bar = tmem_empty_bar + 2;         // [2] outlier accumulators in buffer b complete
+    uint64_t* f_drained_bar = f_full_bar + 2;          // [2] outlier accumulators of buffer b moved to the stash
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(f_drained_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CTA == 2) ? ptx::cluster_ctarank() : 0u;
+    const bool is_leader = cta_rank == 0;
+    const int group_id = blockIdx.x / CTA;
+    const int num_groups = gridDim.x / CTA;
+
+    if (warp_idx == 0 && ptx::elect_one()) {
+        ptx::prefetch_tensormap(&tm_a8);
+        ptx::prefetch_tensormap(&tm_w8);
+        if (has_outlier) {
+            ptx::prefetch_tensormap(&tm_fa);
+            ptx::prefetch_tensormap(&tm_fw);
+        }
+    }
+    if (warp_idx == 1 && ptx::elect_one()) {
+        for (int i = 0; i < T::kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tmem_full_bar[i], 1);
+            ptx::mbar_init(&f_full_bar[i], 1);
+            ptx::mbar_init(&tmem_empty_bar[i], CTA * kNumEpilogueThreads / 32);
+            ptx::mbar_init(&f_drained_bar[i], CTA * kNumEpilogueThreads / 32);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp_idx == 2) {
+        if constexpr (CTA == 2) {
+            ptx::tmem_alloc_2cta(tmem_ptr_s, T::kTmemCols);
+            ptx::tmem_relinquish_2cta();
+        } else {
+            ptx::tmem_alloc(tmem_ptr_s, T::kTmemCols);
+            ptx::tmem_relinquish();
+        }
+    }
+    ptx::tc_fence_before_sync();
+    if constexpr (CTA == 2) ptx::cluster_sync(); else __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    ptx::pdl_wait_prior_grid();
+
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = (K + kBlockKBytes - 1) / kBlockKBytes;
+    const int n_f = has_outlier ? kOutlierKBlocks : 0;
+    const int kb_split = num_kb / 2;  // the outlier K-blocks are slotted in after this many int8 K-blocks
+
+    if (warp_idx == 0) {
+        if (ptx::elect_one()) {
+            // ===================== TMA producer (every CTA) =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            auto load_block = [&](const CUtensorMap* ma, const CUtensorMap* mb, int k0, int m0, int n0) {
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], T::kStageBytes * CTA);
+                uint8_t* sA = ring + static_cast<size_t>(stage) * T::kStageBytes;
+                uint8_t* sB = sA + T::kABytes;
+                if constexpr (CTA == 2) {
+                    ptx::tma_load_2d_2cta(sA, ma, &full_bar[stage], k0, m0, ptx::kEvictNormal);
+                    ptx::tma_load_2d_2cta(sB, mb, &full_bar[stage], k0, n0, ptx::kEvictNormal);
+                } else {
+                    ptx::tma_load_2d(sA, ma, &full_bar[stage], k0, m0, ptx::kEvictNormal);
+                    ptx::tma_load_2d(sB, mb, &full_bar[stage], k0, n0, ptx::kEvictNormal);
+                }
+                if (++stage == T::kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            };
+            for (int tile = group_id; tile < num_tiles; tile += num_groups) {
+                const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, group_m);
+                const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
+                const int n0 = tc.n_blk * BLOCK_N + static_cast<int>(cta_rank) * T::kLoadN;
+                for (int kb = 0; kb < kb_split; ++kb) load_block(&tm_a8, &tm_w8, kb * kBlockKBytes, m0, n0);
+                for (int it = 0; it < n_f; ++it) load_block(&tm_fa, &tm_fw, it * (kBlockKBytes / 2), m0, n0);
+                for (int kb = kb_split; kb < num_kb; ++kb) load_block(&tm_a8, &tm_w8, kb * kBlockKBytes, m0, n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp_idx == 1) {
+        if (is_leader && ptx::elect_one()) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            constexpr uint32_t idesc_i8 = ptx::make_idesc_i8(T::kTileM, BLOCK_N);
+            constexpr uint32_t idesc_f16 = ptx::make_idesc_f16(T::kTileM, BLOCK_N);
+            constexpr uint32_t kDescStep = kUmmaKBytes >> 4;
+            const uint64_t desc_a0 = ptx::make_smem_desc_sw128(ptx::smem_u32(ring));
+            const uint64_t desc_b0 = ptx::make_smem_desc_sw128(ptx::smem_u32(ring) + T::kABytes);
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ready = false;
+            auto issue_block = [&](auto kind_tag, uint32_t tmem_d, bool first) {
+                if (!ready) ptx::mbar_wait(&full_bar[stage], phase);
+                const int nstage = (stage + 1 == T::kStages) ? 0 : stage + 1;
+                const uint32_t nphase = (stage + 1 == T::kStages) ? phase ^ 1 : phase;
+                ready = ptx::mbar_try_wait(&full_bar[nstage], nphase);
+                ptx::tc_fence_after_sync();
+                const uint64_t da = desc_a0 + static_cast<uint64_t>(stage) * (T::kStageBytes >> 4);
+                const uint64_t db = desc_b0 + static_cast<uint64_t>(stage) * (T::kStageBytes >> 4);
+#pragma unroll
+                for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k) {
+                    const uint32_t acc = (first && k == 0) ? 0u : 1u;
+                    if constexpr (decltype(kind_tag)::value == 0) {
+                        if constexpr (CTA == 2) ptx::umma_f16_2cta(tmem_d, da + k * kDescStep, db + k * kDescStep, idesc_f16, acc);
+                        else ptx::umma_f16(tmem_d, da + k * kDescStep, db + k * kDescStep, idesc_f16, acc);
+                    } else {
+                        if constexpr (CTA == 2) ptx::umma_i8_2cta(tmem_d, da + k * kDescStep, db + k * kDescStep, idesc_i8, acc);
+                        else ptx::umma_i8(tmem_d, da + k * kDescStep, db + k * kDescStep, idesc_i8, acc);
+                    }
+                }
+                if constexpr (CTA == 2) ptx::umma_commit_2cta(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
+                stage = nstage;
+                phase = nphase;
+            };
+            auto commit = [&](uint64_t* bar) {
+                if constexpr (CTA == 2) ptx::umma_commit_2cta(bar); else ptx::umma_commit(bar);
+            };
+            int local_tile = 0;
+            for (int tile = group_id; tile < num_tiles; tile += num_groups, ++local_tile) {
+                const int b = local_tile & 1;
+                const uint32_t use = static_cast<uint32_t>(local_tile >> 1);  // how often buffer b was used before
+                const uint32_t tmem_i = tmem_base + b * BLOCK_N;
+                const uint32_t tmem_f = tmem_base + (b ^ 1) * BLOCK_N;
+                // buffer b last held the outlier accumulator of tile t-1 (drained) and, before that, the
+                // int32 accumulator of tile t-2 (released before that drain by the same epilogue warps)
+                if (has_outlier) {
+                    if (local_tile >= 1) ptx::mbar_wait(&f_drained_bar[b], ((local_tile - 1) >> 1) & 1);
+                } else {
+                    ptx::mbar_wait(&tmem_empty_bar[b], (use & 1) ^ 1);
+                }
+                ptx::tc_fence_after_sync();
+                for (int kb = 0; kb < kb_split; ++kb) issue_block(std::integral_constant<int, 1>{}, tmem_i, kb == 0);
+                if (has_outlier) {
+                    // the other buffer is free once the epilogue of tile t-1 has read its int32 accumulators
+                    if (local_tile >= 1) ptx::mbar_wait(&tmem_empty_bar[b ^ 1], ((local_tile - 1) >> 1) & 1);
+                    ptx::tc_fence_after_sync();
+                    for (int it = 0; it < n_f; ++it) issue_block(std::integral_constant<int, 0>{}, tmem_f, it == 0);
+                    commit(&f_full_bar[b ^ 1]);
+                }
+                for (int kb = kb_split; kb < num_kb; ++kb) issue_block(std::integral_constant<int, 1>{}, tmem_i, kb == 0);
+                commit(&tmem_full_bar[b]);
+            }
+        }
+        __syncwarp();
+    } else if (warp_idx >= kEpilogueWarp0) {
+        // ===================== epilogue (every CTA: its own 128 accumulator rows) =====================
+        const int quarter = warp_idx - kEpilogueWarp0;
+        const int et = threadIdx.x - kEpilogueWarp0 * 32;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+        uint4* my_stash = stash + et;  // thread-private, conflict-free: vector v lives at stash[v * 128 + et]
+        auto arrive = [&](uint64_t* bar) {
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CTA == 2) ptx::mbar_arrive_cluster(bar, 0); else ptx::mbar_arrive(bar);
+            }
+        };
+        int local_tile = 0;
+        for (int tile = group_id; tile < num_tiles; tile += num_groups, ++local_tile) {
+            const int b = local_tile & 1;
+            const uint32_t use = static_cast<uint32_t>(local_tile >> 1);
+            const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, group_m);
+            const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
+            const int n0 = tc.n_blk * BLOCK_N;
+            float* sbt = sb_s + b * BLOCK_N;
+            for (int j = et; j < BLOCK_N; j += kNumEpilogueThreads)
+                sbt[j] = (n0 + j < N) ? __half2float(scale_b[n0 + j]) : 0.0f;
+            const int gm = m0 + row;
+            const bool row_ok = gm < M;
+            const float sa_f = row_ok ? __half2float(scale_a[gm]) : 0.0f;
+            ptx::named_bar_sync(1, kNumEpilogueThreads);
+
+            if (has_outlier) {
+                // ---- drain the outlier accumulator (parked in the other buffer) into the stash as fp16
+                ptx::mbar_wait(&f_full_bar[b ^ 1], use & 1);
+                ptx::tc_fence_after_sync();
+                const uint32_t t_f = tmem_base + lane_base + (b ^ 1) * BLOCK_N;
+                uint32_t va[32], vb[32];
+                ptx::tmem_ld_32x32(t_f, va);
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; c += 2) {
+                    ptx::tmem_ld_wait();
+                    ptx::tmem_ld_32x32(t_f + (c + 1) * 32, vb);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        uint32_t h[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const __half2 o = __floats2half2_rn(__uint_as_float(va[v * 8 + q * 2]), __uint_as_float(va[v * 8 + q * 2 + 1]));
+                            h[q] = *reinterpret_cast<const uint32_t*>(&o);
+                        }
+                        my_stash[(c * 4 + v) * kNumEpilogueThreads] = make_uint4(h[0], h[1], h[2], h[3]);
+                    }
+                    ptx::tmem_ld_wait();
+                    if (c + 2 < BLOCK_N / 32) ptx::tmem_ld_32x32(t_f + (c + 2) * 32, va);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        uint32_t h[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const __half2 o = __floats2half2_rn(__uint_as_float(vb[v * 8 + q * 2]), __uint_as_float(vb[v * 8 + q * 2 + 1]));
+                            h[q] = *reinterpret_cast<const uint32_t*>(&o);
+                        }
+                        my_stash[((c + 1) * 4 + v) * kNumEpilogueThreads] = make_uint4(h[0], h[1], h[2], h[3]);
+                    }
+                }
+                arrive(&f_drained_bar[b ^ 1]);
+            }
+
+            // ---- dequantise the int32 accumulators of buffer b
+            ptx::mbar_wait(&tmem_full_bar[b], use & 1);
+            ptx::tc_fence_after_sync();
+            const uint32_t t_i = tmem_base + lane_base + b * BLOCK_N;
+            __half* out_row = Out + static_cast<size_t>(gm) * N + n0;
+            uint32_t vi[2][32];
+            ptx::tmem_ld_32x32(t_i, vi[0]);
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                ptx::tmem_ld_wait();
+                if (c + 1 < BLOCK_N / 32) ptx::tmem_ld_32x32(t_i + (c + 1) * 32, vi[(c + 1) & 1]);
+                const uint32_t* v = vi[c & 1];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 f = make_uint4(0u, 0u, 0u, 0u);
+                    if (has_outlier) f = my_stash[(c * 4 + g) * kNumEpilogueThreads];
+                    const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
+                    uint32_t packed[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = g * 8 + q * 2;
+                        const float p0 = __fmul_rn(sbt[c * 32 + j], sa_f);
+                        const float p1 = __fmul_rn(sbt[c * 32 + j + 1], sa_f);
+                        const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&fw[q]));
+                        const float r0 = __fmaf_rn(__int2float_rn(static_cast<int>(v[j])), p0, of.x);
+                        const float r1 = __fmaf_rn(__int2float_rn(static_cast<int>(v[j + 1])), p1, of.y);
+                        const __half2 r = __floats2half2_rn(r0, r1);
+                        packed[q] = *reinterpret_cast<const uint32_t*>(&r);
+                    }
+                    if (row_ok && n0 + c * 32 + g * 8 + 8 <= N)
+                        ptx::st_global_v4(out_row + c * 32 + g * 8, packed[0], packed[1], packed[2], packed[3]);
+                }
+            }
+            arrive(&tmem_empty_bar[b]);
+        }
+    }
+
+    ptx::pdl_launch_dependents();
+    ptx::tc_fence_before_sync();
+    if constexpr (CTA == 2) ptx::cluster_sync(); else __syncthreads();
+    if (warp_idx == 2) {
+        if constexpr (CTA == 2) ptx::tmem_dealloc_2cta(tmem_base, T::kTmemCols);
+        else ptx::tmem_dealloc(tmem_base, T::kTmemCols);
+    }
+}
+
 // ---------------------------------------------------------------- host side
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -360,6 +681,15 @@ int make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const vo
 }
 
 template <class T>
+struct KernelOf {
+    static auto get() { return mixq_gemm_dequant_kernel<T>; }
+};
+template <int CTA, int STAGES>
+struct KernelOf<StashTraits<CTA, STAGES>> {
+    static auto get() { return mixq_gemm_dequant_stash_kernel<StashTraits<CTA, STAGES>>; }
+};
+
+template <class T>
 int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl) {
     const DeviceInfo& dev = device_info();
@@ -376,7 +706,7 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
         tm_fa = tm_a8;
         tm_fw = tm_w8;
     }
-    auto kern = mixq_gemm_dequant_kernel<T>;
+    auto kern = KernelOf<T>::get();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::kSmemBytes));
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_dequant)");
 
@@ -449,6 +779,10 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
             return launch_cfg<GemmTraits<2, 256, 1, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
         case kCfg2CtaN128x2:
             return launch_cfg<GemmTraits<2, 128, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+        case kCfg2CtaN256Stash:
+            return launch_cfg<StashTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+        case kCfgN256Stash:
+            return launch_cfg<StashTraits<1, 3>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
         default:
             return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: unknown config id");
     }

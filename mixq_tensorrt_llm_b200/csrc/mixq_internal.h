@@ -35,7 +35,7 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
                         bool pdl);
 
 // GEMM tile configuration ids (mixq_set_gemm_config); 0 = pick automatically.
-enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfgCount };
+enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfgCount };
 int current_gemm_config();
 
 }  // namespace mixq

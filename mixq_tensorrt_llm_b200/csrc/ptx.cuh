@@ -260,12 +260,14 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, 
         : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// mbarrier.arrive on the copy of `bar` that lives in CTA `cta` of the cluster.
+// mbarrier.arrive on the copy of `bar` that lives in CTA `cta` of the cluster.  Relaxed: the only data
+// the waiter depends on is TMEM, ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync (a
+// release at cluster scope costs a MEMBAR.ALL.GPU + ERRBAR per arrive).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
     asm volatile(
         "{\n\t.reg .b32 remote;\n\t"
         "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n\t}\n" ::"r"(smem_u32(bar)),
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [remote];\n\t}\n" ::"r"(smem_u32(bar)),
         "r"(cta)
         : "memory");
 }

@@ -18,7 +18,7 @@ from oracle import oracle as O  # noqa: E402
 
 DEV = "cuda"
 res = {}
-CFGS = (1, 2, 4, 5)
+CFGS = (1, 2, 4, 5, 6, 7)
 
 
 def t(x):
