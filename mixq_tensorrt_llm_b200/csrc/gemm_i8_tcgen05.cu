@@ -767,7 +767,14 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
     if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
 
     int cfg = current_gemm_config();
-    if (cfg == kCfgAuto) cfg = kCfgN128x2;
+    if (cfg == kCfgAuto) {
+        // Measured on B200 (profiles/): a single row-block of tokens cannot use a CTA pair's 256 rows;
+        // a few row-blocks (decode batches) want many small double-buffered tiles to fill 148 SMs;
+        // prefill-sized M is tensor-bound and wants the widest tile (lowest operand traffic per MAC).
+        if (M <= 128) cfg = kCfgN128x2;
+        else if (M < 2048) cfg = kCfg2CtaN128x2;
+        else cfg = kCfg2CtaN256Stash;
+    }
     switch (cfg) {
         case kCfgN128x2:
             return launch_cfg<GemmTraits<1, 128, 2, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);

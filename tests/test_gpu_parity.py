@@ -320,8 +320,11 @@ def test_full_size_properties(B, oracle):
     out_2 = torch.empty_like(out)
     B.enqueue((tA * 2).contiguous(), tW, tsb, tfw, tind, out_2, ws)
     torch.cuda.synchronize()
-    # (exact up to fp16-subnormal rounding of the outlier product, which is not scale invariant)
-    assert (out_2.view(torch.int16) != (out * 2).view(torch.int16)).float().mean().item() < 1e-6
+    # (exact wherever the fp16 result is a normal number: subnormal rounding is not scale invariant; the
+    #  same holds for the rare outlier products that are themselves fp16-subnormal)
+    normal = out.abs() >= 2.0 ** -14
+    neq = (out_2.view(torch.int16) != (out * 2).view(torch.int16)) & normal
+    assert neq.float().mean().item() < 1e-6
     # (5) deterministic: same call, same bits
     out_r = torch.empty_like(out)
     B.enqueue(tA, tW, tsb, tfw, tind, out_r, ws)
