@@ -44,6 +44,8 @@ constexpr int kGemmThreads = 256;
 constexpr int kEpilogueWarp0 = 4;
 constexpr int kNumEpilogueThreads = 128;
 constexpr int kOutlierKBlocks = (MIXQ_NUM_OUTLIERS * 2) / kBlockKBytes;  // 2
+constexpr int kStashEpiThreads = 256;                                      // wide-tile kernel: 8 epilogue warps
+constexpr int kStashThreads = kEpilogueWarp0 * 32 + kStashEpiThreads;      // 384
 
 // CTA  = 1: one CTA per 128 x BLOCK_N tile (tcgen05 cta_group::1, UMMA M = 128)
 // CTA  = 2: a CTA pair (cluster of 2 on one TPC) per 256 x BLOCK_N tile (cta_group::2, UMMA M = 256):
@@ -364,7 +366,7 @@ struct StashTraits {
 };
 
 template <class T>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kStashThreads, 1)
 mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_w8,
                                const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fw,
                                const __half* __restrict__ scale_a, const __half* __restrict__ scale_b,
@@ -408,8 +410,8 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
             ptx::mbar_init(&f_full_bar[i], 1);
-            ptx::mbar_init(&tmem_empty_bar[i], CTA * kNumEpilogueThreads / 32);
-            ptx::mbar_init(&f_drained_bar[i], CTA * kNumEpilogueThreads / 32);
+            ptx::mbar_init(&tmem_empty_bar[i], CTA * kStashEpiThreads / 32);
+            ptx::mbar_init(&f_drained_bar[i], CTA * kStashEpiThreads / 32);
         }
         ptx::fence_barrier_init();
     }
@@ -532,11 +534,16 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
         __syncwarp();
     } else if (warp_idx >= kEpilogueWarp0) {
         // ===================== epilogue (every CTA: its own 128 accumulator rows) =====================
-        const int quarter = warp_idx - kEpilogueWarp0;
-        const int et = threadIdx.x - kEpilogueWarp0 * 32;
+        // 8 warps = two per TMEM lane quarter (a warp may only touch lanes 32*(warp_idx % 4)...): the pair
+        // splits the 256 columns, which doubles the latency hiding of the LDTM / LDS / convert chains.
+        const int quarter = warp_idx & 3;
+        const int half = (warp_idx - kEpilogueWarp0) >> 2;  // 0: columns [0,128)   1: columns [128,256)
+        const int et = threadIdx.x - kEpilogueWarp0 * 32;   // 0..255
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-        uint4* my_stash = stash + et;  // thread-private, conflict-free: vector v lives at stash[v * 128 + et]
+        constexpr int kCols = BLOCK_N / 2;                  // columns per epilogue thread
+        const int col0 = half * kCols;
+        uint4* my_stash = stash + et;  // thread-private, conflict-free: vector v lives at stash[v * 256 + et]
         auto arrive = [&](uint64_t* bar) {
             ptx::tc_fence_before_sync();
             __syncwarp();
@@ -552,22 +559,21 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
             const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
             const int n0 = tc.n_blk * BLOCK_N;
             float* sbt = sb_s + b * BLOCK_N;
-            for (int j = et; j < BLOCK_N; j += kNumEpilogueThreads)
-                sbt[j] = (n0 + j < N) ? __half2float(scale_b[n0 + j]) : 0.0f;
+            sbt[et] = (n0 + et < N) ? __half2float(scale_b[n0 + et]) : 0.0f;
             const int gm = m0 + row;
             const bool row_ok = gm < M;
             const float sa_f = row_ok ? __half2float(scale_a[gm]) : 0.0f;
-            ptx::named_bar_sync(1, kNumEpilogueThreads);
+            ptx::named_bar_sync(1, kStashEpiThreads);
 
             if (has_outlier) {
                 // ---- drain the outlier accumulator (parked in the other buffer) into the stash as fp16
                 ptx::mbar_wait(&f_full_bar[b ^ 1], use & 1);
                 ptx::tc_fence_after_sync();
-                const uint32_t t_f = tmem_base + lane_base + (b ^ 1) * BLOCK_N;
+                const uint32_t t_f = tmem_base + lane_base + (b ^ 1) * BLOCK_N + col0;
                 uint32_t va[32], vb[32];
                 ptx::tmem_ld_32x32(t_f, va);
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; c += 2) {
+#pragma unroll
+                for (int c = 0; c < kCols / 32; c += 2) {
                     ptx::tmem_ld_wait();
                     ptx::tmem_ld_32x32(t_f + (c + 1) * 32, vb);
 #pragma unroll
@@ -578,10 +584,10 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
                             const __half2 o = __floats2half2_rn(__uint_as_float(va[v * 8 + q * 2]), __uint_as_float(va[v * 8 + q * 2 + 1]));
                             h[q] = *reinterpret_cast<const uint32_t*>(&o);
                         }
-                        my_stash[(c * 4 + v) * kNumEpilogueThreads] = make_uint4(h[0], h[1], h[2], h[3]);
+                        my_stash[(c * 4 + v) * kStashEpiThreads] = make_uint4(h[0], h[1], h[2], h[3]);
                     }
                     ptx::tmem_ld_wait();
-                    if (c + 2 < BLOCK_N / 32) ptx::tmem_ld_32x32(t_f + (c + 2) * 32, va);
+                    if (c + 2 < kCols / 32) ptx::tmem_ld_32x32(t_f + (c + 2) * 32, va);
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
                         uint32_t h[4];
@@ -590,7 +596,7 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
                             const __half2 o = __floats2half2_rn(__uint_as_float(vb[v * 8 + q * 2]), __uint_as_float(vb[v * 8 + q * 2 + 1]));
                             h[q] = *reinterpret_cast<const uint32_t*>(&o);
                         }
-                        my_stash[((c + 1) * 4 + v) * kNumEpilogueThreads] = make_uint4(h[0], h[1], h[2], h[3]);
+                        my_stash[((c + 1) * 4 + v) * kStashEpiThreads] = make_uint4(h[0], h[1], h[2], h[3]);
                     }
                 }
                 arrive(&f_drained_bar[b ^ 1]);
@@ -599,33 +605,36 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
             // ---- dequantise the int32 accumulators of buffer b
             ptx::mbar_wait(&tmem_full_bar[b], use & 1);
             ptx::tc_fence_after_sync();
-            const uint32_t t_i = tmem_base + lane_base + b * BLOCK_N;
-            __half* out_row = Out + static_cast<size_t>(gm) * N + n0;
+            const uint32_t t_i = tmem_base + lane_base + b * BLOCK_N + col0;
+            __half* out_row = Out + static_cast<size_t>(gm) * N + n0 + col0;
+            const float4* sb4 = reinterpret_cast<const float4*>(sbt + col0);
             uint32_t vi[2][32];
             ptx::tmem_ld_32x32(t_i, vi[0]);
 #pragma unroll
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
+            for (int c = 0; c < kCols / 32; ++c) {
                 ptx::tmem_ld_wait();
-                if (c + 1 < BLOCK_N / 32) ptx::tmem_ld_32x32(t_i + (c + 1) * 32, vi[(c + 1) & 1]);
+                if (c + 1 < kCols / 32) ptx::tmem_ld_32x32(t_i + (c + 1) * 32, vi[(c + 1) & 1]);
                 const uint32_t* v = vi[c & 1];
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint4 f = make_uint4(0u, 0u, 0u, 0u);
-                    if (has_outlier) f = my_stash[(c * 4 + g) * kNumEpilogueThreads];
+                    if (has_outlier) f = my_stash[(c * 4 + g) * kStashEpiThreads];
                     const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
+                    const float4 s0 = sb4[c * 8 + g * 2], s1 = sb4[c * 8 + g * 2 + 1];
+                    const float sbv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                     uint32_t packed[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int j = g * 8 + q * 2;
-                        const float p0 = __fmul_rn(sbt[c * 32 + j], sa_f);
-                        const float p1 = __fmul_rn(sbt[c * 32 + j + 1], sa_f);
+                        const float p0 = __fmul_rn(sbv[q * 2], sa_f);
+                        const float p1 = __fmul_rn(sbv[q * 2 + 1], sa_f);
                         const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&fw[q]));
                         const float r0 = __fmaf_rn(__int2float_rn(static_cast<int>(v[j])), p0, of.x);
                         const float r1 = __fmaf_rn(__int2float_rn(static_cast<int>(v[j + 1])), p1, of.y);
                         const __half2 r = __floats2half2_rn(r0, r1);
                         packed[q] = *reinterpret_cast<const uint32_t*>(&r);
                     }
-                    if (row_ok && n0 + c * 32 + g * 8 + 8 <= N)
+                    if (row_ok && n0 + col0 + c * 32 + g * 8 + 8 <= N)
                         ptx::st_global_v4(out_row + c * 32 + g * 8, packed[0], packed[1], packed[2], packed[3]);
                 }
             }
@@ -682,10 +691,12 @@ int make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const vo
 
 template <class T>
 struct KernelOf {
+    static constexpr int kThreads = kGemmThreads;
     static auto get() { return mixq_gemm_dequant_kernel<T>; }
 };
 template <int CTA, int STAGES>
 struct KernelOf<StashTraits<CTA, STAGES>> {
+    static constexpr int kThreads = kStashThreads;
     static auto get() { return mixq_gemm_dequant_stash_kernel<StashTraits<CTA, STAGES>>; }
 };
 
@@ -720,7 +731,7 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
 
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kGemmThreads);
+    cfg.blockDim = dim3(KernelOf<T>::kThreads);
     cfg.dynamicSmemBytes = T::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];

@@ -34,25 +34,21 @@ namespace {
 
 constexpr int kQuantThreads = 256;
 
+// 4 halves -> 4 int8 (packed little-endian), the reference's arithmetic on the fast path:
+//   q16 = fp16_rn(float(x) * rcp)           (what device __hdiv computes, cuda_fp16.hpp:2723-2746)
+//   i   = rint_even(q16)                     (cvt.rni.s32.f16)
+// rint is done in fp16 with the 1.5 * 2^10 magic add: for |q16| < 512 the sum lands in [1024, 2048)
+// where the fp16 ulp is 1, so the add itself rounds to nearest-even and the low byte of each
+// half is the two's-complement int8 code (|q16| <= ~190 on this path, see the file comment).
 __device__ __forceinline__ uint32_t quant4_fast(uint32_t h01, uint32_t h23, float rcp) {
-    // 4 halves -> 4 int8 (packed little-endian)
-    const __half2 a = *reinterpret_cast<const __half2*>(&h01);
-    const __half2 b = *reinterpret_cast<const __half2*>(&h23);
-    float2 fa = __half22float2(a);
-    float2 fb = __half22float2(b);
-    // fp32 product, rounded to fp16 exactly like __float2half(rcp * fa) in __hdiv
+    const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+    const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&h23));
     const __half2 qa = __floats2half2_rn(__fmul_rn(fa.x, rcp), __fmul_rn(fa.y, rcp));
     const __half2 qb = __floats2half2_rn(__fmul_rn(fb.x, rcp), __fmul_rn(fb.y, rcp));
-    fa = __half22float2(qa);
-    fb = __half22float2(qb);
-    const float magic = 12582912.0f;  // 1.5 * 2^23: low mantissa bits hold rint_even(v) in two's complement
-    const uint32_t i0 = __float_as_uint(__fadd_rn(fa.x, magic));
-    const uint32_t i1 = __float_as_uint(__fadd_rn(fa.y, magic));
-    const uint32_t i2 = __float_as_uint(__fadd_rn(fb.x, magic));
-    const uint32_t i3 = __float_as_uint(__fadd_rn(fb.y, magic));
-    const uint32_t lo = __byte_perm(i0, i1, 0x0040);  // bytes: i0.b0, i1.b0
-    const uint32_t hi = __byte_perm(i2, i3, 0x0040);
-    return __byte_perm(lo, hi, 0x5410);
+    const __half2 magic = __half2half2(__ushort_as_half(0x6600));  // 1536.0
+    const __half2 ra = __hadd2(qa, magic);
+    const __half2 rb = __hadd2(qb, magic);
+    return __byte_perm(*reinterpret_cast<const uint32_t*>(&ra), *reinterpret_cast<const uint32_t*>(&rb), 0x6420);
 }
 
 __device__ __forceinline__ uint32_t quant4_exact(uint32_t h01, uint32_t h23, __half scale) {
@@ -66,7 +62,15 @@ __device__ __forceinline__ uint32_t quant4_exact(uint32_t h01, uint32_t h23, __h
     return q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
 }
 
+__device__ __forceinline__ __half2 absmax2(__half2 m, uint32_t v) {
+    // NaN-propagating so that a NaN anywhere in the row is seen by the row classification below
+    return __hmax2_nan(m, __habs2(*reinterpret_cast<const __half2*>(&v)));
+}
+
 // grid: persistent CTAs striding over rows; block: 256 threads; dynamic smem: 2 * K * 2 bytes.
+// VPT = 16-byte vectors per thread (K <= VPT * 2048): the row lives in registers between the max
+// and the quantise pass and every loop has a compile-time trip count.
+template <int VPT>
 __global__ void __launch_bounds__(kQuantThreads)
 mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const int* __restrict__ ind, int n_ind,
                           int8_t* __restrict__ A8, __half* __restrict__ scale_a, __half* __restrict__ fp_A,
@@ -80,21 +84,22 @@ mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const 
     // The activations are produced by the previous kernel in the stream.
     ptx::pdl_wait_prior_grid();
 
+    auto prefetch = [&](int64_t r, int which) {
+        const uint4* src = reinterpret_cast<const uint4*>(A + r * K) + tid;
+        const uint32_t dst = ptx::smem_u32(buf0 + which * vec_per_row + tid);
+#pragma unroll
+        for (int j = 0; j < VPT; ++j)
+            if (tid + j * kQuantThreads < vec_per_row) ptx::cp_async_16(dst + j * kQuantThreads * 16, src + j * kQuantThreads);
+    };
+
     int64_t row = blockIdx.x;
-    if (row < M) {
-        const uint4* src = reinterpret_cast<const uint4*>(A + row * K);
-        for (int i = tid; i < vec_per_row; i += kQuantThreads) ptx::cp_async_16(ptx::smem_u32(buf0 + i), src + i);
-    }
+    if (row < M) prefetch(row, 0);
     ptx::cp_async_commit();
 
     int cur = 0;
     for (; row < M; row += gridDim.x, cur ^= 1) {
         const int64_t next = row + gridDim.x;
-        if (next < M) {
-            const uint4* src = reinterpret_cast<const uint4*>(A + next * K);
-            for (int i = tid; i < vec_per_row; i += kQuantThreads)
-                ptx::cp_async_16(ptx::smem_u32(buf0 + (cur ^ 1) * vec_per_row + i), src + i);
-        }
+        if (next < M) prefetch(next, cur ^ 1);
         ptx::cp_async_commit();
         ptx::cp_async_wait<1>();  // the current row has landed (the prefetch may still be in flight)
         __syncthreads();
@@ -103,29 +108,27 @@ mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const 
         __half* rowh = reinterpret_cast<__half*>(rowv);
 
         // outlier gather (and, in MixQ/src mode, zeroing: cult.cu:1588)
-        if (tid < n_ind) {
-            const int c = ind[tid];
-            fp_A[row * n_ind + tid] = rowh[c];
-        }
+        if (tid < n_ind) fp_A[row * n_ind + tid] = rowh[ind[tid]];
         if (mask_outliers) {
             __syncthreads();
             if (tid < n_ind) rowh[ind[tid]] = __ushort_as_half(0);
             __syncthreads();
         }
 
-        // per-token max of |x| on the bit patterns
-        uint32_t m = 0;
-        for (int i = tid; i < vec_per_row; i += kQuantThreads) {
-            const uint4 v = rowv[i];
-            m = __vmaxu2(m, v.x & 0x7FFF7FFFu);
-            m = __vmaxu2(m, v.y & 0x7FFF7FFFu);
-            m = __vmaxu2(m, v.z & 0x7FFF7FFFu);
-            m = __vmaxu2(m, v.w & 0x7FFF7FFFu);
+        // row -> registers, per-token max of |x|
+        uint4 v[VPT];
+        __half2 m2 = __half2half2(__ushort_as_half(0));
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            v[j] = (tid + j * kQuantThreads < vec_per_row) ? rowv[tid + j * kQuantThreads] : make_uint4(0u, 0u, 0u, 0u);
+            m2 = absmax2(absmax2(absmax2(absmax2(m2, v[j].x), v[j].y), v[j].z), v[j].w);
         }
-        m = max(m & 0xFFFFu, m >> 16);
+        // |x| bit patterns order like unsigned integers; NaN > Inf > every finite value
+        const uint32_t mb = *reinterpret_cast<const uint32_t*>(&m2);
+        uint32_t m = max(mb & 0xFFFFu, mb >> 16);
         m = __reduce_max_sync(0xFFFFFFFFu, m);
         if ((tid & 31) == 0) s_warp_max[tid >> 5] = m;
-        __syncthreads();
+        __syncthreads();  // also orders every read of this buffer before the prefetch two rows ahead
         uint32_t mx_bits = 0;
 #pragma unroll
         for (int w = 0; w < kQuantThreads / 32; ++w) mx_bits = max(mx_bits, s_warp_max[w]);
@@ -142,34 +145,46 @@ mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const 
         const __half scale = __hdiv(mx, __float2half(127.0f));
         if (tid == 0) scale_a[row] = scale;
 
-        uint2* dst = reinterpret_cast<uint2*>(A8 + row * K);
+        uint2* dst = reinterpret_cast<uint2*>(A8 + row * K) + tid;
         if (!nonfinite && __half_as_ushort(scale) != 0) {
             float rcp;
             const float fs = __half2float(scale);
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(fs));
-            for (int i = tid; i < vec_per_row; i += kQuantThreads) {
-                const uint4 v = rowv[i];
-                dst[i] = make_uint2(quant4_fast(v.x, v.y, rcp), quant4_fast(v.z, v.w, rcp));
-            }
+#pragma unroll
+            for (int j = 0; j < VPT; ++j)
+                if (tid + j * kQuantThreads < vec_per_row)
+                    dst[j * kQuantThreads] = make_uint2(quant4_fast(v[j].x, v[j].y, rcp), quant4_fast(v[j].z, v[j].w, rcp));
         } else {
-            for (int i = tid; i < vec_per_row; i += kQuantThreads) {
-                const uint4 v = rowv[i];
-                dst[i] = make_uint2(quant4_exact(v.x, v.y, scale), quant4_exact(v.z, v.w, scale));
-            }
+#pragma unroll
+            for (int j = 0; j < VPT; ++j)
+                if (tid + j * kQuantThreads < vec_per_row)
+                    dst[j * kQuantThreads] = make_uint2(quant4_exact(v[j].x, v[j].y, scale), quant4_exact(v[j].z, v[j].w, scale));
+            __syncthreads();  // the slow max above read the buffer after the barrier: re-order before reuse
         }
-        __syncthreads();  // everyone is done with buf[cur] before it is refilled two rows ahead
     }
     ptx::cp_async_wait<0>();
     // Let the dependent GEMM start its prologue.
     ptx::pdl_launch_dependents();
 }
 
+using QuantKernel = void (*)(const __half*, int64_t, int, const int*, int, int8_t*, __half*, __half*, int);
+struct QuantVariant {
+    int vpt;
+    QuantKernel fn;
+};
+const QuantVariant kQuantVariants[] = {
+    {1, mixq_quant_extract_kernel<1>},   {2, mixq_quant_extract_kernel<2>},   {3, mixq_quant_extract_kernel<3>},
+    {4, mixq_quant_extract_kernel<4>},   {6, mixq_quant_extract_kernel<6>},   {8, mixq_quant_extract_kernel<8>},
+    {10, mixq_quant_extract_kernel<10>}, {12, mixq_quant_extract_kernel<12>}, {14, mixq_quant_extract_kernel<14>},
+    {16, mixq_quant_extract_kernel<16>}, {24, mixq_quant_extract_kernel<24>}, {32, mixq_quant_extract_kernel<32>},
+};
+
 }  // namespace
 
 int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8, void* scale_a,
                          void* fp_A, unsigned flags, cudaStream_t stream, bool pdl) {
     if (M == 0) return MIXQ_OK;
-    if (K <= 0 || (K & 7) != 0 || K > (1 << 20)) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: K must be a positive multiple of 8");
+    if (K <= 0 || (K & 7) != 0) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: K must be a positive multiple of 8");
     if (n_ind < 0 || n_ind > kQuantThreads) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: n_ind must be in [0,256]");
     if (n_ind > 0 && (!ind || !fp_A)) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: ind/fp_A null");
     if (!A || !A8 || !scale_a) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: null pointer");
@@ -180,8 +195,16 @@ int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, i
     if (!dev.ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
     const size_t smem = static_cast<size_t>(K) * 2 * 2;
     if (smem + 1024 > dev.max_smem_optin) return set_error(MIXQ_ERR_UNSUPPORTED, "quant_extract: K too large for shared memory staging");
+    const int need_vpt = static_cast<int>((K / 8 + kQuantThreads - 1) / kQuantThreads);
+    QuantKernel kern = nullptr;
+    for (const QuantVariant& qv : kQuantVariants)
+        if (qv.vpt >= need_vpt) {
+            kern = qv.fn;
+            break;
+        }
+    if (!kern) return set_error(MIXQ_ERR_UNSUPPORTED, "quant_extract: K too large (max 65536)");
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(mixq_quant_extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem));
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(quant_extract)");
     }
@@ -202,7 +225,7 @@ int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, i
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     const int mask = (flags & MIXQ_FLAG_MASK_OUTLIERS) ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, mixq_quant_extract_kernel, static_cast<const __half*>(A), M,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<const __half*>(A), M,
                                        static_cast<int>(K), static_cast<const int*>(ind), n_ind,
                                        static_cast<int8_t*>(A8), static_cast<__half*>(scale_a),
                                        static_cast<__half*>(fp_A), mask);
