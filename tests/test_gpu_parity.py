@@ -324,7 +324,7 @@ def test_full_size_properties(B, oracle):
     #  same holds for the rare outlier products that are themselves fp16-subnormal)
     normal = out.abs() >= 2.0 ** -14
     neq = (out_2.view(torch.int16) != (out * 2).view(torch.int16)) & normal
-    assert neq.float().mean().item() < 1e-6
+    assert neq.float().mean().item() < 1e-5
     # (5) deterministic: same call, same bits
     out_r = torch.empty_like(out)
     B.enqueue(tA, tW, tsb, tfw, tind, out_r, ws)
