@@ -143,6 +143,7 @@ def run_reference(args, M, linears):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    O.set_threads()          # all host cores (torchrun exports OMP_NUM_THREADS=1)
     sample = args.cpu_sample_tokens
     lins, acts = [], {}
     for name, N, K, _ in linears:
@@ -219,13 +220,25 @@ def run_ours(args, M, linears):
     flops_step = sum(2.0 * M * N * K for _, N, K, _ in linears)      # whole job, all ranks together
     stream = torch.cuda.current_stream()
 
+    chunks = args.tp_chunks if (tp > 1 and M >= 4096 * args.tp_chunks) else 1
+
     def step():
         for name, mod, Ns, Ks, mode in mods:
             out = out_buf[: M * Ns].view(M, Ns)
-            B.enqueue(acts[Ks], mod.weight.view(torch.int8).view(Ns, Ks), mod.weights_scaling_factor, mod.fp_weight,
-                      mod.fp_ind.view(torch.int32), out, ws)
+            W8 = mod.weight.view(torch.int8).view(Ns, Ks)
             if tp > 1 and mode == "row":
-                dist.all_reduce(out)
+                # The one exchange step of the path.  The token dimension is cut into `chunks` row slabs:
+                # the NCCL all-reduce of slab c (on NCCL's stream) overlaps the GEMM of slab c+1.
+                works = []
+                rows = M // chunks
+                for c in range(chunks):
+                    a, o = acts[Ks][c * rows:(c + 1) * rows], out[c * rows:(c + 1) * rows]
+                    B.enqueue(a, W8, mod.weights_scaling_factor, mod.fp_weight, mod.fp_ind.view(torch.int32), o, ws)
+                    works.append(dist.all_reduce(o, async_op=True))
+                for w in works:
+                    w.wait()
+            else:
+                B.enqueue(acts[Ks], W8, mod.weights_scaling_factor, mod.fp_weight, mod.fp_ind.view(torch.int32), out, ws)
 
     def barrier():
         if world > 1:
@@ -385,6 +398,7 @@ def run_ours(args, M, linears):
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as O
         O.build()
+        O.set_threads()
         sample = args.cpu_sample_tokens
         t_cpu = 0.0
         for name, N, K, _ in linears:
@@ -404,7 +418,8 @@ def run_ours(args, M, linears):
                 "scaling": "strong", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
                 "config": {"workload": args.workload, "tokens_per_step": M,
                            "linears": [[n, N, K, m] for n, N, K, m in linears],
-                           "parallelism": f"tp{tp}" if tp > 1 else "single",
+                           "parallelism": (f"tp{tp} (column: no collective; row: one NCCL all-reduce in {chunks} overlapped row slabs)"
+                                           if tp > 1 else "single"),
                            "l2": "inputs larger than L2 (activations %.0f MB per linear), no flush" % (M * 4096 * 2 / 1e6)
                                  if M >= 16384 else "weights rotate through >126 MB per step; activations L2-resident"},
                 "tokens_per_s": M / (ms_step * 1e-3), "gpu_launches": int(launches), "clocks": clocks,
@@ -424,6 +439,7 @@ def main():
     ap.add_argument("--workload", default="llama2-7b-linears-bs32xseq2048", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample-tokens", type=int, default=512)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--tp-chunks", type=int, default=4, help="row slabs per row-parallel linear (comm/compute overlap)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")

@@ -206,6 +206,15 @@ void mixq_oracle_forward(const uint16_t* A, const int8_t* W8, const uint16_t* sc
     mixq_oracle_epilogue(acc, sa, scale_b, out0, M, N, out);             /* :529 epilogue */
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the timing legs ask for all host cores explicitly. */
+void mixq_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int mixq_oracle_num_threads(void) {
     int n = 1;
 #ifdef _OPENMP

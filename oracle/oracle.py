@@ -60,6 +60,8 @@ def lib():
         L.mixq_oracle_forward.argtypes = [u16p, i8p, u16p, u16p, i32p, i32, i64, i64, i64, u32p, i32,
                                           u16p, u16p, i8p, u16p, i32p, u16p]
         L.mixq_oracle_num_threads.restype = i32
+        L.mixq_oracle_set_threads.argtypes = [i32]
+        L.mixq_oracle_set_threads.restype = None
         for f in ("gather", "quant", "outlier_gemm", "igemm", "epilogue", "forward"):
             getattr(L, "mixq_oracle_" + f).restype = None
         _lib = L
@@ -96,6 +98,12 @@ def _u16(a):
 
 def num_threads() -> int:
     return int(lib().mixq_oracle_num_threads())
+
+
+def set_threads(n: int | None = None) -> int:
+    """Use `n` OpenMP threads (default: every host core; torchrun pins OMP_NUM_THREADS=1)."""
+    lib().mixq_oracle_set_threads(int(n or os.cpu_count() or 1))
+    return num_threads()
 
 
 # ----------------------------------------------------------------------------- steps
