@@ -74,7 +74,7 @@ int mixq_device_ok(void);
 
 /* Bytes of device workspace mixq_enqueue needs for (M, N, K). Layout (each
  * block 128-byte aligned, as nextWorkspacePtr does, TsinghuaMixQPlugin.cpp:206-215):
- *   A8 int8 [M,K] | scale_a fp16 [M] | fp_A fp16 [M,128]
+ *   A8 int8 [M,K] | scale_a fp16 [M] | fp_A fp16 [M,128] | stream-K scratch (~10 MB, M-independent)
  * Replaces the reference's max(M*K + 2M + 2*K*N, 16*M*N) (TsinghuaMixQPlugin.cpp:342-346). */
 size_t mixq_workspace_size(int64_t M, int64_t N, int64_t K);
 
@@ -110,6 +110,14 @@ int mixq_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int
 int mixq_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b,
                       const void* fp_A, const void* fp_weight, void* Out, int64_t M, int64_t N,
                       int64_t K, void* stream);
+
+/* Stage 2 with scratch for the stream-K schedule the library prefers for decode-sized M (tiles that do
+ * not fill the GPU evenly are cut along K; int32 partial sums meet in `workspace`).  Results are
+ * bit-identical to mixq_gemm_dequant.  workspace_bytes >= mixq_gemm_workspace_size(), 16-byte aligned. */
+size_t mixq_gemm_workspace_size(void);
+int mixq_gemm_dequant_ws(const void* A8, const void* W8, const void* scale_a, const void* scale_b,
+                         const void* fp_A, const void* fp_weight, void* Out, int64_t M, int64_t N,
+                         int64_t K, void* workspace, size_t workspace_bytes, void* stream);
 
 /* End-to-end call with HOST buffers for the per-call tensors: copies A (host,
  * fp16 [M,K]) to the device, runs mixq_enqueue with the device-resident weights

@@ -19,7 +19,8 @@ FLAG_FORCE_MIXED = 2
 # every symbol include/mixq_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_enqueue",
-    "mixq_quant_extract", "mixq_gemm_dequant", "mixq_host_scratch_size", "mixq_linear_host",
+    "mixq_quant_extract", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
+    "mixq_host_scratch_size", "mixq_linear_host",
     "mixq_launch_count", "mixq_set_gemm_config", "initOpenAiTritonPlugins", "mixq_plugin_create",
     "mixq_plugin_deserialize", "mixq_plugin_clone", "mixq_plugin_destroy", "mixq_plugin_type",
     "mixq_plugin_version", "mixq_plugin_namespace", "mixq_plugin_nb_outputs",
@@ -62,6 +63,10 @@ def load() -> ctypes.CDLL:
     L.mixq_quant_extract.argtypes = [vp, i64, i64, vp, ci, vp, vp, vp, u32, vp]
     L.mixq_gemm_dequant.restype = ci
     L.mixq_gemm_dequant.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
+    L.mixq_gemm_workspace_size.restype = sz
+    L.mixq_gemm_workspace_size.argtypes = []
+    L.mixq_gemm_dequant_ws.restype = ci
+    L.mixq_gemm_dequant_ws.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, sz, vp]
     L.mixq_host_scratch_size.restype = sz
     L.mixq_host_scratch_size.argtypes = [i64, i64, i64]
     L.mixq_linear_host.restype = ci
@@ -150,8 +155,14 @@ def quant_extract(A, ind, A8, scale_a, fp_A, flags: int = 0, stream=None) -> Non
                                     _stream(stream)), "mixq_quant_extract")
 
 
-def gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, stream=None) -> None:
+def gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, stream=None, workspace=None) -> None:
     M, K = A8.shape
     N = W8.shape[0]
-    check(load().mixq_gemm_dequant(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A), _ptr(fp_weight),
-                                   _ptr(Out), M, N, K, _stream(stream)), "mixq_gemm_dequant")
+    if workspace is None:
+        check(load().mixq_gemm_dequant(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A), _ptr(fp_weight),
+                                       _ptr(Out), M, N, K, _stream(stream)), "mixq_gemm_dequant")
+    else:
+        check(load().mixq_gemm_dequant_ws(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A),
+                                          _ptr(fp_weight), _ptr(Out), M, N, K, _ptr(workspace),
+                                          workspace.numel() * workspace.element_size(), _stream(stream)),
+              "mixq_gemm_dequant_ws")

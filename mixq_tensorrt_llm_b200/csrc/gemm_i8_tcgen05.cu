@@ -44,6 +44,9 @@ constexpr int kGemmThreads = 256;
 constexpr int kEpilogueWarp0 = 4;
 constexpr int kNumEpilogueThreads = 128;
 constexpr int kOutlierKBlocks = (MIXQ_NUM_OUTLIERS * 2) / kBlockKBytes;  // 2
+constexpr size_t kStreamKFlagBytes = 4096;                                 // stream-K: one flag per (worker, CTA rank)
+constexpr size_t kStreamKSlotBytes = 2 * 128 * 256 * 4;                    // int32 partial tile of one CTA pair
+constexpr int kStreamKMaxWorkers = 80;                                     // CTA pairs (148 SMs -> 74)
 constexpr int kStashEpiThreads = 256;                                      // wide-tile kernel: 8 epilogue warps
 constexpr int kStashThreads = kEpilogueWarp0 * 32 + kStashEpiThreads;      // 384
 
@@ -651,6 +654,423 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
     }
 }
 
+// =================================================================================================
+// Stream-K variant of the wide-tile kernel, for shapes whose tile count does not fill the machine
+// evenly (decode batches: M = 512 gives 96 tiles of 256x256 for 74 CTA pairs; M = 32 gives 48).
+// The iteration space (tile, K-block) is cut into one contiguous, equally long span per CTA pair.
+// A span may start in the middle of a tile and end in the middle of another one:
+//   * the segment that contains K-block 0 of a tile is the tile's FINISHER: it also runs the outlier
+//     MMAs, collects the int32 partial sums of the other segments and does the dequant epilogue;
+//   * every other segment is a PEER: its epilogue dumps the raw int32 accumulators to a per-worker
+//     slot in the workspace and raises a flag.
+// Integer accumulation is associative, so the result is bit-identical to the unsplit kernel.  The
+// finisher's segment is the LAST thing its worker does while peer segments are the FIRST thing their
+// workers do, so the finisher practically never waits.  All workers are co-resident (grid <= #SMs).
+// With stream_k = 0 the kernel degenerates to the strided whole-tile schedule of the stash kernel.
+struct SegIter {
+    int stream_k, num_tiles, num_kb, num_groups;
+    long long u, u_end;
+    int tile_cursor;
+    __device__ void init(int sk, int nt, int nkb, int gid, int ng) {
+        stream_k = sk; num_tiles = nt; num_kb = nkb; num_groups = ng;
+        const long long total = static_cast<long long>(nt) * nkb;
+        u = total * gid / ng;
+        u_end = total * (gid + 1) / ng;
+        tile_cursor = gid;
+    }
+    __device__ bool next(int& tile, int& kb0, int& kb1) {
+        if (stream_k) {
+            if (u >= u_end) return false;
+            tile = static_cast<int>(u / num_kb);
+            kb0 = static_cast<int>(u - static_cast<long long>(tile) * num_kb);
+            const long long rem = u_end - u;
+            kb1 = static_cast<int>(rem < num_kb - kb0 ? kb0 + rem : num_kb);
+            u += kb1 - kb0;
+            return true;
+        }
+        if (tile_cursor >= num_tiles) return false;
+        tile = tile_cursor;
+        tile_cursor += num_groups;
+        kb0 = 0;
+        kb1 = num_kb;
+        return true;
+    }
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <class T>
+__global__ void __launch_bounds__(kStashThreads, 1)
+mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_w8,
+                                 const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fw,
+                                 const __half* __restrict__ scale_a, const __half* __restrict__ scale_b,
+                                 __half* __restrict__ Out, int M, int N, int K, int has_outlier, int m_tiles,
+                                 int n_tiles, int group_m, int stream_k, uint4* __restrict__ sk_slots,
+                                 uint32_t* __restrict__ sk_flags) {
+    constexpr int BLOCK_N = T::kBlockN;
+    constexpr int CTA = T::kCta;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;
+    uint4* stash = reinterpret_cast<uint4*>(ring + static_cast<size_t>(T::kStages) * T::kStageBytes);
+    float* sb_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stash) + T::kStashBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sb_s + 2 * BLOCK_N);
+    uint64_t* empty_bar = full_bar + T::kStages;
+    uint64_t* tmem_full_bar = empty_bar + T::kStages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint64_t* f_full_bar = tmem_empty_bar + 2;
+    uint64_t* f_drained_bar = f_full_bar + 2;
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(f_drained_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CTA == 2) ? ptx::cluster_ctarank() : 0u;
+    const bool is_leader = cta_rank == 0;
+    const int group_id = blockIdx.x / CTA;
+    const int num_groups = gridDim.x / CTA;
+
+    if (warp_idx == 0 && ptx::elect_one()) {
+        ptx::prefetch_tensormap(&tm_a8);
+        ptx::prefetch_tensormap(&tm_w8);
+        if (has_outlier) {
+            ptx::prefetch_tensormap(&tm_fa);
+            ptx::prefetch_tensormap(&tm_fw);
+        }
+    }
+    if (warp_idx == 1 && ptx::elect_one()) {
+        for (int i = 0; i < T::kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tmem_full_bar[i], 1);
+            ptx::mbar_init(&f_full_bar[i], 1);
+            ptx::mbar_init(&tmem_empty_bar[i], CTA * kStashEpiThreads / 32);
+            ptx::mbar_init(&f_drained_bar[i], CTA * kStashEpiThreads / 32);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp_idx == 2) {
+        if constexpr (CTA == 2) {
+            ptx::tmem_alloc_2cta(tmem_ptr_s, T::kTmemCols);
+            ptx::tmem_relinquish_2cta();
+        } else {
+            ptx::tmem_alloc(tmem_ptr_s, T::kTmemCols);
+            ptx::tmem_relinquish();
+        }
+    }
+    ptx::tc_fence_before_sync();
+    if constexpr (CTA == 2) ptx::cluster_sync(); else __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    ptx::pdl_wait_prior_grid();
+
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = (K + kBlockKBytes - 1) / kBlockKBytes;
+    SegIter seg;
+    seg.init(stream_k, num_tiles, num_kb, group_id, num_groups);
+    int tile, kb0, kb1;
+
+    if (warp_idx == 0) {
+        if (ptx::elect_one()) {
+            // ===================== TMA producer (every CTA) =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            auto load_block = [&](const CUtensorMap* ma, const CUtensorMap* mb, int k0, int m0, int n0) {
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], T::kStageBytes * CTA);
+                uint8_t* sA = ring + static_cast<size_t>(stage) * T::kStageBytes;
+                uint8_t* sB = sA + T::kABytes;
+                if constexpr (CTA == 2) {
+                    ptx::tma_load_2d_2cta(sA, ma, &full_bar[stage], k0, m0, ptx::kEvictNormal);
+                    ptx::tma_load_2d_2cta(sB, mb, &full_bar[stage], k0, n0, ptx::kEvictNormal);
+                } else {
+                    ptx::tma_load_2d(sA, ma, &full_bar[stage], k0, m0, ptx::kEvictNormal);
+                    ptx::tma_load_2d(sB, mb, &full_bar[stage], k0, n0, ptx::kEvictNormal);
+                }
+                if (++stage == T::kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            };
+            while (seg.next(tile, kb0, kb1)) {
+                const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, group_m);
+                const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
+                const int n0 = tc.n_blk * BLOCK_N + static_cast<int>(cta_rank) * T::kLoadN;
+                const int n_f = (has_outlier && kb0 == 0) ? kOutlierKBlocks : 0;
+                const int split = kb0 + (kb1 - kb0) / 2;
+                for (int kb = kb0; kb < split; ++kb) load_block(&tm_a8, &tm_w8, kb * kBlockKBytes, m0, n0);
+                for (int it = 0; it < n_f; ++it) load_block(&tm_fa, &tm_fw, it * (kBlockKBytes / 2), m0, n0);
+                for (int kb = split; kb < kb1; ++kb) load_block(&tm_a8, &tm_w8, kb * kBlockKBytes, m0, n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp_idx == 1) {
+        if (is_leader && ptx::elect_one()) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            constexpr uint32_t idesc_i8 = ptx::make_idesc_i8(T::kTileM, BLOCK_N);
+            constexpr uint32_t idesc_f16 = ptx::make_idesc_f16(T::kTileM, BLOCK_N);
+            constexpr uint32_t kDescStep = kUmmaKBytes >> 4;
+            const uint64_t desc_a0 = ptx::make_smem_desc_sw128(ptx::smem_u32(ring));
+            const uint64_t desc_b0 = ptx::make_smem_desc_sw128(ptx::smem_u32(ring) + T::kABytes);
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ready = false;
+            auto issue_block = [&](auto kind_tag, uint32_t tmem_d, bool first) {
+                if (!ready) ptx::mbar_wait(&full_bar[stage], phase);
+                const int nstage = (stage + 1 == T::kStages) ? 0 : stage + 1;
+                const uint32_t nphase = (stage + 1 == T::kStages) ? phase ^ 1 : phase;
+                ready = ptx::mbar_try_wait(&full_bar[nstage], nphase);
+                ptx::tc_fence_after_sync();
+                const uint64_t da = desc_a0 + static_cast<uint64_t>(stage) * (T::kStageBytes >> 4);
+                const uint64_t db = desc_b0 + static_cast<uint64_t>(stage) * (T::kStageBytes >> 4);
+#pragma unroll
+                for (int k = 0; k < kBlockKBytes / kUmmaKBytes; ++k) {
+                    const uint32_t acc = (first && k == 0) ? 0u : 1u;
+                    if constexpr (decltype(kind_tag)::value == 0) {
+                        if constexpr (CTA == 2) ptx::umma_f16_2cta(tmem_d, da + k * kDescStep, db + k * kDescStep, idesc_f16, acc);
+                        else ptx::umma_f16(tmem_d, da + k * kDescStep, db + k * kDescStep, idesc_f16, acc);
+                    } else {
+                        if constexpr (CTA == 2) ptx::umma_i8_2cta(tmem_d, da + k * kDescStep, db + k * kDescStep, idesc_i8, acc);
+                        else ptx::umma_i8(tmem_d, da + k * kDescStep, db + k * kDescStep, idesc_i8, acc);
+                    }
+                }
+                if constexpr (CTA == 2) ptx::umma_commit_2cta(&empty_bar[stage]); else ptx::umma_commit(&empty_bar[stage]);
+                stage = nstage;
+                phase = nphase;
+            };
+            auto commit = [&](uint64_t* bar) {
+                if constexpr (CTA == 2) ptx::umma_commit_2cta(bar); else ptx::umma_commit(bar);
+            };
+            // completions this thread has caused / must have seen, per accumulator buffer
+            uint32_t n_int[2] = {0, 0};     // segments that used buffer x for int32 accumulators (= tmem_full commits)
+            uint32_t n_f[2] = {0, 0};       // outlier accumulators parked in buffer x (= f_full commits)
+            bool f_pending[2] = {false, false};
+            int s = 0;
+            while (seg.next(tile, kb0, kb1)) {
+                const int b = s & 1;
+                const bool has_f = has_outlier && kb0 == 0;
+                const uint32_t tmem_i = tmem_base + b * BLOCK_N;
+                const uint32_t tmem_f = tmem_base + (b ^ 1) * BLOCK_N;
+                // buffer b must be free: its previous int32 tenant read by the epilogue, a parked outlier
+                // accumulator drained
+                if (n_int[b] > 0) ptx::mbar_wait(&tmem_empty_bar[b], (n_int[b] - 1) & 1);
+                if (f_pending[b]) {
+                    ptx::mbar_wait(&f_drained_bar[b], (n_f[b] - 1) & 1);
+                    f_pending[b] = false;
+                }
+                ptx::tc_fence_after_sync();
+                const int split = kb0 + (kb1 - kb0) / 2;
+                for (int kb = kb0; kb < split; ++kb) issue_block(std::integral_constant<int, 1>{}, tmem_i, kb == kb0);
+                if (has_f) {
+                    if (n_int[b ^ 1] > 0) ptx::mbar_wait(&tmem_empty_bar[b ^ 1], (n_int[b ^ 1] - 1) & 1);
+                    ptx::tc_fence_after_sync();
+                    for (int it = 0; it < kOutlierKBlocks; ++it) issue_block(std::integral_constant<int, 0>{}, tmem_f, it == 0);
+                    commit(&f_full_bar[b ^ 1]);
+                    ++n_f[b ^ 1];
+                    f_pending[b ^ 1] = true;
+                }
+                for (int kb = split; kb < kb1; ++kb) issue_block(std::integral_constant<int, 1>{}, tmem_i, kb == kb0);
+                commit(&tmem_full_bar[b]);
+                ++n_int[b];
+                ++s;
+            }
+        }
+        __syncwarp();
+    } else if (warp_idx >= kEpilogueWarp0) {
+        // ===================== epilogue (8 warps; every CTA: its own 128 accumulator rows) =====================
+        const int quarter = warp_idx & 3;
+        const int half = (warp_idx - kEpilogueWarp0) >> 2;
+        const int et = threadIdx.x - kEpilogueWarp0 * 32;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+        constexpr int kCols = BLOCK_N / 2;
+        const int col0 = half * kCols;
+        uint4* my_stash = stash + et;
+        auto arrive = [&](uint64_t* bar) {
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CTA == 2) ptx::mbar_arrive_cluster(bar, 0); else ptx::mbar_arrive(bar);
+            }
+        };
+        // slot of worker w, CTA rank r: 32 vectors x 256 threads x 16 B = 128 KB, thread-major (coalesced)
+        auto slot_of = [&](int w) { return sk_slots + (static_cast<size_t>(w) * CTA + cta_rank) * (32 * kStashEpiThreads) + et; };
+        auto flag_of = [&](int w) { return sk_flags + static_cast<size_t>(w) * CTA + cta_rank; };
+        uint32_t n_int[2] = {0, 0}, n_f[2] = {0, 0};
+        int s = 0;
+        while (seg.next(tile, kb0, kb1)) {
+            const int b = s & 1;
+            const bool finisher = kb0 == 0;
+            const bool has_f = has_outlier && finisher;
+            const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, group_m);
+            const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
+            const int n0 = tc.n_blk * BLOCK_N;
+            const int gm = m0 + row;
+            const bool row_ok = gm < M;
+            float* sbt = sb_s + b * BLOCK_N;
+            float sa_f = 0.0f;
+            if (finisher) {
+                sbt[et] = (n0 + et < N) ? __half2float(scale_b[n0 + et]) : 0.0f;
+                sa_f = row_ok ? __half2float(scale_a[gm]) : 0.0f;
+            }
+            ptx::named_bar_sync(1, kStashEpiThreads);
+
+            if (has_f) {
+                // ---- drain the outlier accumulator (parked in the other buffer) into the stash as fp16
+                ptx::mbar_wait(&f_full_bar[b ^ 1], n_f[b ^ 1] & 1);
+                ++n_f[b ^ 1];
+                ptx::tc_fence_after_sync();
+                const uint32_t t_f = tmem_base + lane_base + (b ^ 1) * BLOCK_N + col0;
+                uint32_t va[32], vb[32];
+                ptx::tmem_ld_32x32(t_f, va);
+#pragma unroll
+                for (int c = 0; c < kCols / 32; c += 2) {
+                    ptx::tmem_ld_wait();
+                    ptx::tmem_ld_32x32(t_f + (c + 1) * 32, vb);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        uint32_t h[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const __half2 o = __floats2half2_rn(__uint_as_float(va[v * 8 + q * 2]), __uint_as_float(va[v * 8 + q * 2 + 1]));
+                            h[q] = *reinterpret_cast<const uint32_t*>(&o);
+                        }
+                        my_stash[(c * 4 + v) * kStashEpiThreads] = make_uint4(h[0], h[1], h[2], h[3]);
+                    }
+                    ptx::tmem_ld_wait();
+                    if (c + 2 < kCols / 32) ptx::tmem_ld_32x32(t_f + (c + 2) * 32, va);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        uint32_t h[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const __half2 o = __floats2half2_rn(__uint_as_float(vb[v * 8 + q * 2]), __uint_as_float(vb[v * 8 + q * 2 + 1]));
+                            h[q] = *reinterpret_cast<const uint32_t*>(&o);
+                        }
+                        my_stash[((c + 1) * 4 + v) * kStashEpiThreads] = make_uint4(h[0], h[1], h[2], h[3]);
+                    }
+                }
+                arrive(&f_drained_bar[b ^ 1]);
+            }
+
+            ptx::mbar_wait(&tmem_full_bar[b], n_int[b] & 1);
+            ++n_int[b];
+            ptx::tc_fence_after_sync();
+            const uint32_t t_i = tmem_base + lane_base + b * BLOCK_N + col0;
+
+            if (!finisher) {
+                // ---- PEER: dump the raw int32 partial sums, then raise this worker's flag
+                uint4* slot = slot_of(group_id);
+                uint32_t v[32];
+#pragma unroll 1
+                for (int c = 0; c < kCols / 32; ++c) {
+                    ptx::tmem_ld_32x32(t_i + c * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        slot[(c * 8 + g) * kStashEpiThreads] = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                }
+                arrive(&tmem_empty_bar[b]);
+                ptx::named_bar_sync(2, kStashEpiThreads);  // every thread's slot stores precede the flag
+                if (et == 0) {
+                    __threadfence();
+                    st_release_gpu(flag_of(group_id), 1u);
+                }
+            } else {
+                // ---- FINISHER: [collect the peers' partial sums,] dequantise and store
+                int n_peers = 0;
+                if (kb1 < num_kb) {
+                    // the rest of this tile [kb1, num_kb) was computed by the following workers
+                    const long long total = static_cast<long long>(num_tiles) * num_kb;
+                    const long long tile_end = static_cast<long long>(tile + 1) * num_kb;
+                    int p = group_id + 1;
+                    while (p < num_groups && total * p / num_groups < tile_end) {
+                        ++n_peers;
+                        ++p;
+                    }
+                    if (et == 0) {
+                        for (int q = 1; q <= n_peers; ++q) {
+                            uint32_t spins = 0;
+                            while (ld_acquire_gpu(flag_of(group_id + q)) == 0u) {
+                                if (++spins > (1u << 23)) __trap();
+                            }
+                        }
+                    }
+                    ptx::named_bar_sync(2, kStashEpiThreads);
+                }
+                __half* out_row = Out + static_cast<size_t>(gm) * N + n0 + col0;
+                const float4* sb4 = reinterpret_cast<const float4*>(sbt + col0);
+                uint32_t vi[2][32];
+                ptx::tmem_ld_32x32(t_i, vi[0]);
+#pragma unroll
+                for (int c = 0; c < kCols / 32; ++c) {
+                    ptx::tmem_ld_wait();
+                    if (c + 1 < kCols / 32) ptx::tmem_ld_32x32(t_i + (c + 1) * 32, vi[(c + 1) & 1]);
+                    uint32_t* v = vi[c & 1];
+                    for (int q = 1; q <= n_peers; ++q) {
+                        const uint4* slot = slot_of(group_id + q);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            const uint4 pv = __ldcg(slot + (c * 8 + g) * kStashEpiThreads);
+                            v[g * 4] += pv.x;
+                            v[g * 4 + 1] += pv.y;
+                            v[g * 4 + 2] += pv.z;
+                            v[g * 4 + 3] += pv.w;
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 f = make_uint4(0u, 0u, 0u, 0u);
+                        if (has_f) f = my_stash[(c * 4 + g) * kStashEpiThreads];
+                        const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
+                        const float4 s0 = sb4[c * 8 + g * 2], s1 = sb4[c * 8 + g * 2 + 1];
+                        const float sbv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                        uint32_t packed[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int j = g * 8 + q * 2;
+                            const float p0 = __fmul_rn(sbv[q * 2], sa_f);
+                            const float p1 = __fmul_rn(sbv[q * 2 + 1], sa_f);
+                            const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&fw[q]));
+                            const float r0 = __fmaf_rn(__int2float_rn(static_cast<int>(v[j])), p0, of.x);
+                            const float r1 = __fmaf_rn(__int2float_rn(static_cast<int>(v[j + 1])), p1, of.y);
+                            const __half2 r = __floats2half2_rn(r0, r1);
+                            packed[q] = *reinterpret_cast<const uint32_t*>(&r);
+                        }
+                        if (row_ok && n0 + col0 + c * 32 + g * 8 + 8 <= N)
+                            ptx::st_global_v4(out_row + c * 32 + g * 8, packed[0], packed[1], packed[2], packed[3]);
+                    }
+                }
+                arrive(&tmem_empty_bar[b]);
+                if (n_peers > 0) {
+                    // re-arm the flags for the next launch once every thread of this CTA has read the slots
+                    ptx::named_bar_sync(2, kStashEpiThreads);
+                    if (et == 0)
+                        for (int q = 1; q <= n_peers; ++q) *flag_of(group_id + q) = 0u;
+                }
+            }
+            ++s;
+        }
+    }
+
+    ptx::pdl_launch_dependents();
+    ptx::tc_fence_before_sync();
+    if constexpr (CTA == 2) ptx::cluster_sync(); else __syncthreads();
+    if (warp_idx == 2) {
+        if constexpr (CTA == 2) ptx::tmem_dealloc_2cta(tmem_base, T::kTmemCols);
+        else ptx::tmem_dealloc(tmem_base, T::kTmemCols);
+    }
+}
+
 // ---------------------------------------------------------------- host side
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -700,9 +1120,22 @@ struct KernelOf<StashTraits<CTA, STAGES>> {
     static auto get() { return mixq_gemm_dequant_stash_kernel<StashTraits<CTA, STAGES>>; }
 };
 
+template <int CTA, int STAGES>
+struct StreamKTraits : StashTraits<CTA, STAGES> {};
+template <int CTA, int STAGES>
+struct KernelOf<StreamKTraits<CTA, STAGES>> {
+    static constexpr int kThreads = kStashThreads;
+    static auto get() { return mixq_gemm_dequant_streamk_kernel<StashTraits<CTA, STAGES>>; }
+};
+template <class T>
+struct IsStreamK : std::false_type {};
+template <int CTA, int STAGES>
+struct IsStreamK<StreamKTraits<CTA, STAGES>> : std::true_type {};
+
 template <class T>
 int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
-               const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl) {
+               const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl,
+               void* sk_ws = nullptr, int stream_k = 0) {
     const DeviceInfo& dev = device_info();
     CUtensorMap tm_a8, tm_w8, tm_fa, tm_fw;
     int rc;
@@ -726,7 +1159,12 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     const int64_t num_tiles = static_cast<int64_t>(m_tiles) * n_tiles;
     if (num_tiles > (1ll << 30)) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: too many tiles");
     const int64_t max_groups = dev.num_sms / T::kCta;
-    const int grid = static_cast<int>(num_tiles < max_groups ? num_tiles : max_groups) * T::kCta;
+    int grid = static_cast<int>(num_tiles < max_groups ? num_tiles : max_groups) * T::kCta;
+    if (IsStreamK<T>::value && sk_ws && stream_k) {
+        // one equal span of (tile, K-block) units per CTA group; never more groups than units
+        const int64_t units = num_tiles * ((K + kBlockKBytes - 1) / kBlockKBytes);
+        grid = static_cast<int>(units < max_groups ? units : max_groups) * T::kCta;
+    }
     const int group_m = 8 / T::kCta;
 
     cudaLaunchConfig_t cfg{};
@@ -750,9 +1188,19 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, static_cast<const __half*>(scale_a),
-                           static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M),
-                           static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m);
+    if constexpr (IsStreamK<T>::value) {
+        uint32_t* flags = static_cast<uint32_t*>(sk_ws);
+        uint4* slots = reinterpret_cast<uint4*>(static_cast<uint8_t*>(sk_ws) + kStreamKFlagBytes);
+        // a worker is a peer at most once; spans shorter than a tile would need more than the reserved slots
+        e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, static_cast<const __half*>(scale_a),
+                               static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M),
+                               static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m,
+                               (sk_ws && stream_k) ? 1 : 0, slots, flags);
+    } else {
+        e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, static_cast<const __half*>(scale_a),
+                               static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M),
+                               static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m);
+    }
     if (e != cudaSuccess) return set_cuda_error(e, "launch gemm_dequant");
     count_launch();
     return MIXQ_OK;
@@ -760,9 +1208,11 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
 
 }  // namespace
 
+size_t streamk_workspace_bytes() { return kStreamKFlagBytes + static_cast<size_t>(kStreamKMaxWorkers) * kStreamKSlotBytes; }
+
 int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                         const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
-                        bool pdl) {
+                        bool pdl, void* sk_ws, size_t sk_ws_bytes, bool sk_flags_clean) {
     if (M == 0 || N == 0) return MIXQ_OK;
     if (!A8 || !W8 || !scale_a || !scale_b || !Out) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: null pointer");
     if ((fp_A == nullptr) != (fp_weight == nullptr))
@@ -777,14 +1227,24 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
     if (al & 15) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: tensors must be 16-byte aligned");
     if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
 
+    const bool sk_ok = sk_ws && sk_ws_bytes >= streamk_workspace_bytes() && (reinterpret_cast<uintptr_t>(sk_ws) & 15) == 0;
     int cfg = current_gemm_config();
     if (cfg == kCfgAuto) {
         // Measured on B200 (profiles/): a single row-block of tokens cannot use a CTA pair's 256 rows;
         // a few row-blocks (decode batches) want many small double-buffered tiles to fill 148 SMs;
         // prefill-sized M is tensor-bound and wants the widest tile (lowest operand traffic per MAC).
-        if (M <= 128) cfg = kCfgN128x2;
+        if (M < 2048 && sk_ok) cfg = kCfg2CtaN256StreamK;   // decode batches: stream-K over wide tiles
+        else if (M <= 128) cfg = kCfgN128x2;
         else if (M < 2048) cfg = kCfg2CtaN128x2;
         else cfg = kCfg2CtaN256Stash;
+    }
+    if (cfg == kCfg2CtaN256StreamK) {
+        if (!sk_ok) return set_error(MIXQ_ERR_WORKSPACE, "gemm_dequant: stream-K needs mixq_gemm_workspace_size() bytes of workspace");
+        if (!sk_flags_clean) {
+            cudaError_t e = cudaMemsetAsync(sk_ws, 0, kStreamKFlagBytes, stream);
+            if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(stream-K flags)");
+        }
+        return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, sk_ws, 1);
     }
     switch (cfg) {
         case kCfgN128x2:

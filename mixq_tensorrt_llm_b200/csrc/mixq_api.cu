@@ -19,7 +19,7 @@ constexpr size_t kAlign = 128;  // kCudaMemAlign, TsinghuaMixQPlugin.cpp:204
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 struct Carve {
-    size_t off_a8, off_sa, off_fpa, total;
+    size_t off_a8, off_sa, off_fpa, off_sk, total;
 };
 // int8_out | scale_a | fp_activation, in the reference's order (TsinghuaMixQPlugin.cpp:410-421)
 inline Carve carve(int64_t M, int64_t K) {
@@ -27,7 +27,8 @@ inline Carve carve(int64_t M, int64_t K) {
     c.off_a8 = 0;
     c.off_sa = align_up(static_cast<size_t>(M) * static_cast<size_t>(K));
     c.off_fpa = c.off_sa + align_up(static_cast<size_t>(M) * 2);
-    c.total = c.off_fpa + align_up(static_cast<size_t>(M) * MIXQ_NUM_OUTLIERS * 2);
+    c.off_sk = c.off_fpa + align_up(static_cast<size_t>(M) * MIXQ_NUM_OUTLIERS * 2);
+    c.total = c.off_sk + align_up(streamk_workspace_bytes());  // stream-K flags + partial-sum slots (kernel 2)
     return c;
 }
 }  // namespace
@@ -102,6 +103,15 @@ int mixq_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const
                                static_cast<cudaStream_t>(stream), /*pdl=*/false);
 }
 
+size_t mixq_gemm_workspace_size(void) { return streamk_workspace_bytes(); }
+
+int mixq_gemm_dequant_ws(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
+                         const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    return launch_gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K,
+                               static_cast<cudaStream_t>(stream), /*pdl=*/false, workspace, workspace_bytes, false);
+}
+
 int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes,
                  unsigned flags, void* stream) {
     if (!t) return set_error(MIXQ_ERR_BAD_ARG, "enqueue: null tensor table");
@@ -120,9 +130,11 @@ int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* w
     void* sa = ws + c.off_sa;
     void* fpA = ws + c.off_fpa;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int rc = launch_quant_extract(t->A, M, K, t->ind, MIXQ_NUM_OUTLIERS, A8, sa, fpA, flags, s, /*pdl=*/true);
+    void* sk = ws + c.off_sk;
+    int rc = launch_quant_extract(t->A, M, K, t->ind, MIXQ_NUM_OUTLIERS, A8, sa, fpA, flags, s, /*pdl=*/true, sk, 1024);
     if (rc) return rc;
-    return launch_gemm_dequant(A8, t->W8, sa, t->scale_b, fpA, t->fp_weight, t->Out, M, N, K, s, /*pdl=*/true);
+    return launch_gemm_dequant(A8, t->W8, sa, t->scale_b, fpA, t->fp_weight, t->Out, M, N, K, s, /*pdl=*/true, sk,
+                               streamk_workspace_bytes(), /*sk_flags_clean=*/true);
 }
 
 size_t mixq_host_scratch_size(int64_t M, int64_t N, int64_t K) {

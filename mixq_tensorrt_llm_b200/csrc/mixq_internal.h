@@ -26,16 +26,21 @@ int set_cuda_error(cudaError_t e, const char* what);
 void count_launch();
 
 // stage 1 (quant_extract.cu)
+// clear_words: optional, `n_clear` 32-bit words zeroed by CTA 0 (the stream-K flags of kernel 2)
 int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8, void* scale_a,
-                         void* fp_A, unsigned flags, cudaStream_t stream, bool pdl);
+                         void* fp_A, unsigned flags, cudaStream_t stream, bool pdl, void* clear_words = nullptr,
+                         int n_clear = 0);
 
 // stage 2 (gemm_i8_tcgen05.cu)
+// sk_ws: optional stream-K scratch (streamk_workspace_bytes(): flags first, then partial-sum slots);
+// sk_flags_clean: the flags are already zero (mixq_enqueue lets kernel 1 clear them).
 int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                         const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
-                        bool pdl);
+                        bool pdl, void* sk_ws = nullptr, size_t sk_ws_bytes = 0, bool sk_flags_clean = false);
+size_t streamk_workspace_bytes();
 
 // GEMM tile configuration ids (mixq_set_gemm_config); 0 = pick automatically.
-enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfgCount };
+enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfgCount };
 int current_gemm_config();
 
 }  // namespace mixq

@@ -74,7 +74,7 @@ template <int VPT>
 __global__ void __launch_bounds__(kQuantThreads)
 mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const int* __restrict__ ind, int n_ind,
                           int8_t* __restrict__ A8, __half* __restrict__ scale_a, __half* __restrict__ fp_A,
-                          int mask_outliers) {
+                          int mask_outliers, uint32_t* __restrict__ clear_words, int n_clear) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t s_warp_max[kQuantThreads / 32];
     const int tid = threadIdx.x;
@@ -83,6 +83,10 @@ mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const 
 
     // The activations are produced by the previous kernel in the stream.
     ptx::pdl_wait_prior_grid();
+
+    // kernel 2's stream-K flags live in the same workspace; clearing them here costs no extra launch
+    if (blockIdx.x == 0)
+        for (int i = tid; i < n_clear; i += kQuantThreads) clear_words[i] = 0u;
 
     auto prefetch = [&](int64_t r, int which) {
         const uint4* src = reinterpret_cast<const uint4*>(A + r * K) + tid;
@@ -167,7 +171,7 @@ mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const 
     ptx::pdl_launch_dependents();
 }
 
-using QuantKernel = void (*)(const __half*, int64_t, int, const int*, int, int8_t*, __half*, __half*, int);
+using QuantKernel = void (*)(const __half*, int64_t, int, const int*, int, int8_t*, __half*, __half*, int, uint32_t*, int);
 struct QuantVariant {
     int vpt;
     QuantKernel fn;
@@ -182,7 +186,7 @@ const QuantVariant kQuantVariants[] = {
 }  // namespace
 
 int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8, void* scale_a,
-                         void* fp_A, unsigned flags, cudaStream_t stream, bool pdl) {
+                         void* fp_A, unsigned flags, cudaStream_t stream, bool pdl, void* clear_words, int n_clear) {
     if (M == 0) return MIXQ_OK;
     if (K <= 0 || (K & 7) != 0) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: K must be a positive multiple of 8");
     if (n_ind < 0 || n_ind > kQuantThreads) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: n_ind must be in [0,256]");
@@ -228,7 +232,7 @@ int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, i
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<const __half*>(A), M,
                                        static_cast<int>(K), static_cast<const int*>(ind), n_ind,
                                        static_cast<int8_t*>(A8), static_cast<__half*>(scale_a),
-                                       static_cast<__half*>(fp_A), mask);
+                                       static_cast<__half*>(fp_A), mask, static_cast<uint32_t*>(clear_words), n_clear);
     if (e != cudaSuccess) return set_cuda_error(e, "launch quant_extract");
     count_launch();
     return MIXQ_OK;

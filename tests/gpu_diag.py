@@ -18,7 +18,16 @@ from oracle import oracle as O  # noqa: E402
 
 DEV = "cuda"
 res = {}
-CFGS = (1, 2, 4, 5, 6, 7)
+CFGS = (1, 5, 6, 8)
+
+
+_gws = []
+
+
+def GWS():
+    if not _gws:
+        _gws.append(torch.zeros(B.load().mixq_gemm_workspace_size(), dtype=torch.uint8, device=DEV))
+    return _gws[0]
 
 
 def t(x):
@@ -42,7 +51,8 @@ def run_gemm(cfg, q, w, sa, sb, fpA=None, fpW=None):
     out = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
     prev = lib.mixq_set_gemm_config(cfg)
     try:
-        B.gemm_dequant(t(q), t(w), t(sa), t(sb), None if fpA is None else t(fpA), None if fpW is None else t(fpW), out)
+        B.gemm_dequant(t(q), t(w), t(sa), t(sb), None if fpA is None else t(fpA), None if fpW is None else t(fpW), out,
+                       workspace=GWS())
         torch.cuda.synchronize()
     finally:
         lib.mixq_set_gemm_config(prev)
@@ -96,8 +106,8 @@ def timeit(fn, iters=20, warm=3):
 
 def timings():
     lib = B.load()
-    for (M, N, K) in [(512, 12288, 4096), (32, 12288, 4096), (8192, 12288, 4096), (65536, 12288, 4096),
-                      (512, 4096, 11008), (8192, 4096, 11008)]:
+    for (M, N, K) in [(512, 12288, 4096), (32, 12288, 4096), (128, 12288, 4096), (1024, 12288, 4096), (2048, 12288, 4096),
+                      (4096, 12288, 4096), (8192, 12288, 4096), (512, 4096, 4096), (512, 4096, 11008), (32, 4096, 11008)]:
         key = f"time_{M}x{N}x{K}"
         try:
             A = (torch.randn(M, K, device=DEV) * 0.5).half()
@@ -115,10 +125,10 @@ def timings():
             r["quant_GBps"] = (3 * M * K + 258 * M) / r["quant_us"] / 1e3
             for cfg in CFGS:
                 lib.mixq_set_gemm_config(cfg)
-                us = timeit(lambda: B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out))
+                us = timeit(lambda: B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=GWS()))
                 r[f"gemm_cfg{cfg}_us"] = us
                 r[f"gemm_cfg{cfg}_TOPS"] = 2.0 * M * N * K / us / 1e6
-                us = timeit(lambda: B.gemm_dequant(A8, W8, sa, sb, None, None, out))
+                us = timeit(lambda: B.gemm_dequant(A8, W8, sa, sb, None, None, out, workspace=GWS()))
                 r[f"gemm_cfg{cfg}_noout_TOPS"] = 2.0 * M * N * K / us / 1e6
             lib.mixq_set_gemm_config(0)
             r["enqueue_us"] = timeit(lambda: B.enqueue(A, W8, sb, fw, ind, out, ws))

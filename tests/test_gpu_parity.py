@@ -36,6 +36,17 @@ def _t(x):
     return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
 
 
+_GEMM_WS = {}
+
+
+def _gemm_ws(lib):
+    """stream-K scratch for mixq_gemm_dequant_ws, deliberately filled with garbage once: the library
+    must clear / re-arm its flags itself."""
+    if "ws" not in _GEMM_WS:
+        _GEMM_WS["ws"] = torch.randint(0, 255, (lib.mixq_gemm_workspace_size(),), dtype=torch.uint8, device=DEV)
+    return _GEMM_WS["ws"]
+
+
 def _assert_mixed_close(got, ref, out0, what="", mag=None):
     """Tolerance of the mixed output: the fp16-rounded outlier product `out0` may
     differ from the checker's by one fp16 ulp *of out0* (accumulation order of its 128-term dot
@@ -128,10 +139,11 @@ def test_quant_only_no_outliers(B, oracle):
 
 # ----------------------------------------------------------------------------- stage 2
 GEMM_SHAPES = [(128, 128, 128), (128, 128, 256), (256, 256, 512), (1, 8, 16), (100, 136, 144), (5, 4096, 4096),
-               (130, 264, 4096), (512, 1024, 4096), (300, 512, 11008), (257, 1280, 8192)]
+               (130, 264, 4096), (512, 1024, 4096), (300, 512, 11008), (257, 1280, 8192), (32, 12288, 4096),
+               (512, 256, 28672)]
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     """No outlier slab: int32 accumulation is exact, the epilogue is one fma + one rounding, so
@@ -144,7 +156,7 @@ def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     out = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
     prev = lib.mixq_set_gemm_config(cfg)
     try:
-        B.gemm_dequant(_t(q), _t(w), _t(sa), _t(sb), None, None, out)
+        B.gemm_dequant(_t(q), _t(w), _t(sa), _t(sb), None, None, out, workspace=_gemm_ws(lib))
         torch.cuda.synchronize()
     finally:
         lib.mixq_set_gemm_config(prev)
@@ -154,7 +166,7 @@ def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     assert bad.size == 0, f"{len(bad)} mismatches, first at {bad[:5].tolist()}: got {got[tuple(bad[0])]} want {ref[tuple(bad[0])]}"
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (100, 136, 144), (300, 520, 1040), (64, 512, 4096), (512, 1024, 4096)])
 def test_gemm_dequant_with_outlier_slab(B, lib, oracle, cfg, M, N, K):
     rng = np.random.default_rng(M + N + K)
@@ -167,7 +179,7 @@ def test_gemm_dequant_with_outlier_slab(B, lib, oracle, cfg, M, N, K):
     out = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
     prev = lib.mixq_set_gemm_config(cfg)
     try:
-        B.gemm_dequant(_t(q), _t(w), _t(sa), _t(sb), _t(fpA), _t(fpW), out)
+        B.gemm_dequant(_t(q), _t(w), _t(sa), _t(sb), _t(fpA), _t(fpW), out, workspace=_gemm_ws(lib))
         torch.cuda.synchronize()
     finally:
         lib.mixq_set_gemm_config(prev)
