@@ -134,6 +134,11 @@ int mixq_linear_host(const mixq_tensors* t, const void* A_host, void* Out_host, 
  * reads it to fill `gpu_launches`. */
 uint64_t mixq_launch_count(void);
 
+/* Debug only: device buffer of 8 x uint64 %globaltimer stamps per CTA written by the stream-K GEMM
+ * kernel (entry, prologue done, first TMA, first tile issued, MMA done, first/last accumulator ready,
+ * epilogue done); NULL (default) disables it. */
+int mixq_debug_set_trace(void* dev_buf);
+
 /* GEMM tile configuration override for tuning/tests: 0 = auto. Returns the
  * previous value. Valid ids are listed in DESIGN.md. */
 int mixq_set_gemm_config(int config_id);

@@ -667,6 +667,17 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
 // finisher's segment is the LAST thing its worker does while peer segments are the FIRST thing their
 // workers do, so the finisher practically never waits.  All workers are co-resident (grid <= #SMs).
 // With stream_k = 0 the kernel degenerates to the strided whole-tile schedule of the stash kernel.
+// Debug timeline (mixq_debug_set_trace): 8 x uint64 nanosecond stamps per CTA; null in production.
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_stamp(int slot) {
+    unsigned long long* t = g_trace;
+    if (t) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        t[blockIdx.x * 8 + slot] = now;
+    }
+}
+
 struct SegIter {
     int stream_k, num_tiles, num_kb, num_groups;
     long long u, u_end;
@@ -710,6 +721,7 @@ template <class T>
 __global__ void __launch_bounds__(kStashThreads, 1)
 mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_w8,
                                  const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fw,
+                                 const __grid_constant__ CUtensorMap tm_out,
                                  const __half* __restrict__ scale_a, const __half* __restrict__ scale_b,
                                  __half* __restrict__ Out, int M, int N, int K, int has_outlier, int m_tiles,
                                  int n_tiles, int group_m, int stream_k, uint4* __restrict__ sk_slots,
@@ -735,10 +747,12 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
     const bool is_leader = cta_rank == 0;
     const int group_id = blockIdx.x / CTA;
     const int num_groups = gridDim.x / CTA;
+    if (threadIdx.x == 0) trace_stamp(0);
 
     if (warp_idx == 0 && ptx::elect_one()) {
         ptx::prefetch_tensormap(&tm_a8);
         ptx::prefetch_tensormap(&tm_w8);
+        ptx::prefetch_tensormap(&tm_out);
         if (has_outlier) {
             ptx::prefetch_tensormap(&tm_fa);
             ptx::prefetch_tensormap(&tm_fw);
@@ -771,6 +785,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr_s;
 
+    if (threadIdx.x == 0) trace_stamp(1);
     ptx::pdl_wait_prior_grid();
 
     const int num_tiles = m_tiles * n_tiles;
@@ -801,6 +816,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                     phase ^= 1;
                 }
             };
+            trace_stamp(2);
             while (seg.next(tile, kb0, kb1)) {
                 const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, group_m);
                 const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
@@ -880,21 +896,34 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                 }
                 for (int kb = split; kb < kb1; ++kb) issue_block(std::integral_constant<int, 1>{}, tmem_i, kb == kb0);
                 commit(&tmem_full_bar[b]);
+                if (s == 0) trace_stamp(3);
                 ++n_int[b];
                 ++s;
             }
+            trace_stamp(4);
         }
         __syncwarp();
     } else if (warp_idx >= kEpilogueWarp0) {
         // ===================== epilogue (8 warps; every CTA: its own 128 accumulator rows) =====================
+        // Each warp owns 32 rows x 128 columns = 4 chunks of 32 rows x 32 columns.  A chunk has a 2 KB
+        // shared-memory tile (32 rows x 64 B, SWIZZLE_64B so that the row-per-thread accesses are
+        // conflict free).  The tile first holds the fp16 outlier product (the "stash"), is overwritten
+        // in place with the fp16 result, and leaves through one TMA store per chunk: no per-thread
+        // global stores, and the tensor map clips rows >= M / columns >= N.
         const int quarter = warp_idx & 3;
         const int half = (warp_idx - kEpilogueWarp0) >> 2;
-        const int et = threadIdx.x - kEpilogueWarp0 * 32;
+        const int ew = warp_idx - kEpilogueWarp0;           // 0..7
+        const int et = threadIdx.x - kEpilogueWarp0 * 32;   // 0..255
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
         constexpr int kCols = BLOCK_N / 2;
+        constexpr int kChunks = kCols / 32;                 // 4
         const int col0 = half * kCols;
-        uint4* my_stash = stash + et;
+        uint8_t* warp_tiles = reinterpret_cast<uint8_t*>(stash) + ew * (kChunks * 2048);
+        const uint32_t swz = static_cast<uint32_t>((lane >> 1) & 3);
+        auto vec_ptr = [&](int c, int v) {                  // 16-byte vector v (8 columns) of this thread's row in chunk c
+            return reinterpret_cast<uint4*>(warp_tiles + c * 2048 + lane * 64 + ((static_cast<uint32_t>(v) ^ swz) << 4));
+        };
         auto arrive = [&](uint64_t* bar) {
             ptx::tc_fence_before_sync();
             __syncwarp();
@@ -915,27 +944,29 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
             const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
             const int n0 = tc.n_blk * BLOCK_N;
             const int gm = m0 + row;
-            const bool row_ok = gm < M;
             float* sbt = sb_s + b * BLOCK_N;
             float sa_f = 0.0f;
             if (finisher) {
                 sbt[et] = (n0 + et < N) ? __half2float(scale_b[n0 + et]) : 0.0f;
-                sa_f = row_ok ? __half2float(scale_a[gm]) : 0.0f;
+                sa_f = gm < M ? __half2float(scale_a[gm]) : 0.0f;
+                // the previous tile's TMA stores must have finished READING this warp's tiles
+                if (lane == 0) ptx::tma_store_wait_read<0>();
             }
             ptx::named_bar_sync(1, kStashEpiThreads);
 
             if (has_f) {
-                // ---- drain the outlier accumulator (parked in the other buffer) into the stash as fp16
+                // ---- drain the outlier accumulator (parked in the other buffer) into the tiles as fp16
                 ptx::mbar_wait(&f_full_bar[b ^ 1], n_f[b ^ 1] & 1);
                 ++n_f[b ^ 1];
                 ptx::tc_fence_after_sync();
                 const uint32_t t_f = tmem_base + lane_base + (b ^ 1) * BLOCK_N + col0;
-                uint32_t va[32], vb[32];
-                ptx::tmem_ld_32x32(t_f, va);
+                uint32_t vf[2][32];
+                ptx::tmem_ld_32x32(t_f, vf[0]);
 #pragma unroll
-                for (int c = 0; c < kCols / 32; c += 2) {
+                for (int c = 0; c < kChunks; ++c) {
                     ptx::tmem_ld_wait();
-                    ptx::tmem_ld_32x32(t_f + (c + 1) * 32, vb);
+                    if (c + 1 < kChunks) ptx::tmem_ld_32x32(t_f + (c + 1) * 32, vf[(c + 1) & 1]);
+                    const uint32_t* va = vf[c & 1];
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
                         uint32_t h[4];
@@ -944,19 +975,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                             const __half2 o = __floats2half2_rn(__uint_as_float(va[v * 8 + q * 2]), __uint_as_float(va[v * 8 + q * 2 + 1]));
                             h[q] = *reinterpret_cast<const uint32_t*>(&o);
                         }
-                        my_stash[(c * 4 + v) * kStashEpiThreads] = make_uint4(h[0], h[1], h[2], h[3]);
-                    }
-                    ptx::tmem_ld_wait();
-                    if (c + 2 < kCols / 32) ptx::tmem_ld_32x32(t_f + (c + 2) * 32, va);
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        uint32_t h[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const __half2 o = __floats2half2_rn(__uint_as_float(vb[v * 8 + q * 2]), __uint_as_float(vb[v * 8 + q * 2 + 1]));
-                            h[q] = *reinterpret_cast<const uint32_t*>(&o);
-                        }
-                        my_stash[((c + 1) * 4 + v) * kStashEpiThreads] = make_uint4(h[0], h[1], h[2], h[3]);
+                        *vec_ptr(c, v) = make_uint4(h[0], h[1], h[2], h[3]);
                     }
                 }
                 arrive(&f_drained_bar[b ^ 1]);
@@ -965,6 +984,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
             ptx::mbar_wait(&tmem_full_bar[b], n_int[b] & 1);
             ++n_int[b];
             ptx::tc_fence_after_sync();
+            if (et == 0) trace_stamp(s == 0 ? 5 : 6);
             const uint32_t t_i = tmem_base + lane_base + b * BLOCK_N + col0;
 
             if (!finisher) {
@@ -972,7 +992,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                 uint4* slot = slot_of(group_id);
                 uint32_t v[32];
 #pragma unroll 1
-                for (int c = 0; c < kCols / 32; ++c) {
+                for (int c = 0; c < kChunks; ++c) {
                     ptx::tmem_ld_32x32(t_i + c * 32, v);
                     ptx::tmem_ld_wait();
 #pragma unroll
@@ -986,7 +1006,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                     st_release_gpu(flag_of(group_id), 1u);
                 }
             } else {
-                // ---- FINISHER: [collect the peers' partial sums,] dequantise and store
+                // ---- FINISHER: [collect the peers' partial sums,] dequantise, TMA-store
                 int n_peers = 0;
                 if (kb1 < num_kb) {
                     // the rest of this tile [kb1, num_kb) was computed by the following workers
@@ -1007,30 +1027,39 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                     }
                     ptx::named_bar_sync(2, kStashEpiThreads);
                 }
-                __half* out_row = Out + static_cast<size_t>(gm) * N + n0 + col0;
                 const float4* sb4 = reinterpret_cast<const float4*>(sbt + col0);
                 uint32_t vi[2][32];
                 ptx::tmem_ld_32x32(t_i, vi[0]);
 #pragma unroll
-                for (int c = 0; c < kCols / 32; ++c) {
+                for (int c = 0; c < kChunks; ++c) {
+                    uint4 pv[8];
+                    if (n_peers > 0) {  // issue the first peer's loads before waiting for TMEM
+                        const uint4* slot = slot_of(group_id + 1);
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) pv[g] = __ldcg(slot + (c * 8 + g) * kStashEpiThreads);
+                    }
                     ptx::tmem_ld_wait();
-                    if (c + 1 < kCols / 32) ptx::tmem_ld_32x32(t_i + (c + 1) * 32, vi[(c + 1) & 1]);
+                    if (c + 1 < kChunks) ptx::tmem_ld_32x32(t_i + (c + 1) * 32, vi[(c + 1) & 1]);
                     uint32_t* v = vi[c & 1];
                     for (int q = 1; q <= n_peers; ++q) {
-                        const uint4* slot = slot_of(group_id + q);
+                        if (q > 1) {
+                            const uint4* slot = slot_of(group_id + q);
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) pv[g] = __ldcg(slot + (c * 8 + g) * kStashEpiThreads);
+                        }
 #pragma unroll
                         for (int g = 0; g < 8; ++g) {
-                            const uint4 pv = __ldcg(slot + (c * 8 + g) * kStashEpiThreads);
-                            v[g * 4] += pv.x;
-                            v[g * 4 + 1] += pv.y;
-                            v[g * 4 + 2] += pv.z;
-                            v[g * 4 + 3] += pv.w;
+                            v[g * 4] += pv[g].x;
+                            v[g * 4 + 1] += pv[g].y;
+                            v[g * 4 + 2] += pv[g].z;
+                            v[g * 4 + 3] += pv[g].w;
                         }
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
+                        uint4* tp = vec_ptr(c, g);
                         uint4 f = make_uint4(0u, 0u, 0u, 0u);
-                        if (has_f) f = my_stash[(c * 4 + g) * kStashEpiThreads];
+                        if (has_f) f = *tp;
                         const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
                         const float4 s0 = sb4[c * 8 + g * 2], s1 = sb4[c * 8 + g * 2 + 1];
                         const float sbv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
@@ -1046,8 +1075,14 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                             const __half2 r = __floats2half2_rn(r0, r1);
                             packed[q] = *reinterpret_cast<const uint32_t*>(&r);
                         }
-                        if (row_ok && n0 + col0 + c * 32 + g * 8 + 8 <= N)
-                            ptx::st_global_v4(out_row + c * 32 + g * 8, packed[0], packed[1], packed[2], packed[3]);
+                        *tp = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    }
+                    // hand the finished 32x32 tile to the TMA engine
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tm_out, warp_tiles + c * 2048, n0 + col0 + c * 32, m0 + quarter * 32);
+                        ptx::tma_store_commit();
                     }
                 }
                 arrive(&tmem_empty_bar[b]);
@@ -1060,8 +1095,10 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
             }
             ++s;
         }
+        if (lane == 0) ptx::tma_store_wait_all<0>();  // outstanding output tiles fully written before the CTA retires
     }
 
+    if (threadIdx.x == kEpilogueWarp0 * 32) trace_stamp(7);
     ptx::pdl_launch_dependents();
     ptx::tc_fence_before_sync();
     if constexpr (CTA == 2) ptx::cluster_sync(); else __syncthreads();
@@ -1089,17 +1126,19 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2D row-major [rows, cols] tensor of `elem_bytes` elements, box = 128 bytes x box_rows, 128B swizzle.
+// 2D row-major [rows, cols] tensor of `elem_bytes` elements, box = `box_bytes` x box_rows with the matching
+// swizzle (128 B for the operand tiles, 64 B for the output tiles).
 int make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols,
-              uint32_t box_rows) {
+              uint32_t box_rows, int box_bytes = kBlockKBytes) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return set_error(MIXQ_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {cols * static_cast<uint64_t>(elem_bytes)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockKBytes / elem_bytes), box_rows};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_bytes / elem_bytes), box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         static thread_local char buf[160];
         snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed: CUresult %d (rows=%llu cols=%llu elem=%d)", (int)r,
@@ -1189,10 +1228,12 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     cfg.attrs = attr;
     cfg.numAttrs = na;
     if constexpr (IsStreamK<T>::value) {
+        CUtensorMap tm_out;
+        if ((rc = make_tmap(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Out, M, N, 32, 64))) return rc;
         uint32_t* flags = static_cast<uint32_t*>(sk_ws);
         uint4* slots = reinterpret_cast<uint4*>(static_cast<uint8_t*>(sk_ws) + kStreamKFlagBytes);
         // a worker is a peer at most once; spans shorter than a tile would need more than the reserved slots
-        e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, static_cast<const __half*>(scale_a),
+        e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, tm_out, static_cast<const __half*>(scale_a),
                                static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M),
                                static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m,
                                (sk_ws && stream_k) ? 1 : 0, slots, flags);
@@ -1207,6 +1248,12 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
 }
 
 }  // namespace
+
+int set_trace_buffer(void* dev_buf) {
+    unsigned long long* p = static_cast<unsigned long long*>(dev_buf);
+    cudaError_t e = cudaMemcpyToSymbol(g_trace, &p, sizeof(p));
+    return e == cudaSuccess ? MIXQ_OK : set_cuda_error(e, "cudaMemcpyToSymbol(g_trace)");
+}
 
 size_t streamk_workspace_bytes() { return kStreamKFlagBytes + static_cast<size_t>(kStreamKMaxWorkers) * kStreamKSlotBytes; }
 

@@ -103,6 +103,8 @@ int mixq_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const
                                static_cast<cudaStream_t>(stream), /*pdl=*/false);
 }
 
+int mixq_debug_set_trace(void* dev_buf) { return set_trace_buffer(dev_buf); }
+
 size_t mixq_gemm_workspace_size(void) { return streamk_workspace_bytes(); }
 
 int mixq_gemm_dequant_ws(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,

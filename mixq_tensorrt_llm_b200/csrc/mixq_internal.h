@@ -38,6 +38,7 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
                         const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
                         bool pdl, void* sk_ws = nullptr, size_t sk_ws_bytes = 0, bool sk_flags_clean = false);
 size_t streamk_workspace_bytes();
+int set_trace_buffer(void* dev_buf);
 
 // GEMM tile configuration ids (mixq_set_gemm_config); 0 = pick automatically.
 enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfgCount };

@@ -1,0 +1,40 @@
+"""Per-CTA timeline of the stream-K kernel (debug).  python tests/gpu_trace.py M N K"""
+import sys
+from pathlib import Path
+import numpy as np
+import torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from mixq_tensorrt_llm_b200 import binding as B  # noqa: E402
+M, N, K = (int(x) for x in sys.argv[1:4])
+dev = "cuda"
+lib = B.load()
+A8 = torch.randint(-127, 128, (M, K), dtype=torch.int8, device=dev)
+W8 = torch.randint(-127, 128, (N, K), dtype=torch.int8, device=dev)
+sa = (torch.rand(M, device=dev) * 0.01 + 1e-3).half()
+sb = (torch.rand(N, device=dev) * 0.002 + 1e-4).half()
+fpA = torch.randn(M, 128, device=dev).half()
+fw = (torch.randn(N, 128, device=dev) * 0.02).half()
+out = torch.empty(M, N, dtype=torch.float16, device=dev)
+ws = torch.zeros(lib.mixq_gemm_workspace_size(), dtype=torch.uint8, device=dev)
+trace = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+lib.mixq_set_gemm_config(8)
+for it in range(4):
+    B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws)
+torch.cuda.synchronize()
+B.check(lib.mixq_debug_set_trace(trace.data_ptr()), "trace")
+B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws)
+torch.cuda.synchronize()
+lib.mixq_debug_set_trace(None)
+t = trace.cpu().numpy().reshape(148, 8).astype(np.float64)
+t0 = t[:, 0][t[:, 0] > 0].min()
+names = ["entry", "prologue", "firstTMA", "tile0issued", "mmaDone", "acc0ready", "accLast", "epiDone"]
+rel = np.where(t > 0, (t - t0) / 1e3, np.nan)
+print("shape", M, N, K, "us relative to first CTA entry")
+for i, n in enumerate(names):
+    col = rel[:, i]
+    ok = ~np.isnan(col)
+    if ok.any():
+        print(f"{n:12s} min {np.nanmin(col):7.2f} med {np.nanmedian(col):7.2f} max {np.nanmax(col):7.2f}  (n={ok.sum()})")
+for c in (0, 1, 2, 3, 72, 73, 146, 147):
+    print("cta", c, np.round(rel[c], 2).tolist())
