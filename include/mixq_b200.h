@@ -104,6 +104,16 @@ int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* w
 int mixq_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8,
                        void* scale_a, void* fp_A, unsigned flags, void* stream);
 
+/* Stage 1 fused with its producer (SURVEY.md 8f "next #1"): RMSNorm -> outlier extract -> per-token INT8
+ * quantise in one pass over the hidden state X [M,K].  Restates generalT5LayerNorm_extract_outliers
+ * (MixQ/src/kernel/mix_cuda/layernorm/layernorm.cu:121-198):
+ *   y[m,k] = fp16( clamp( (float(X[m,k]) * rsqrtf(sum_k X[m,k]^2 / K + eps)) * float(gamma[k]) ) )
+ * then exactly mixq_quant_extract on y.  The reference kernel always zeroes the outlier columns of y
+ * (pass MIXQ_FLAG_MASK_OUTLIERS for that); Y (fp16 [M,K], may be NULL) receives y before that zeroing. */
+int mixq_rmsnorm_quant_extract(const void* X, const void* gamma, float eps, int64_t M, int64_t K,
+                               const void* ind, int n_ind, void* A8, void* scale_a, void* fp_A, void* Y,
+                               unsigned flags, void* stream);
+
 /* Stage 2 alone. Replaces cublasGemmEx fp16 (TsinghuaMixQPlugin.cpp:122-161) +
  * int8FusedDequantizeCUDA (kernel/i8gemm.cu:151-194) in one kernel.
  * fp_A/fp_weight may both be NULL: then the addend is 0 (plain W8A8 dequant GEMM). */

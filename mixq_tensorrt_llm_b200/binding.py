@@ -19,7 +19,7 @@ FLAG_FORCE_MIXED = 2
 # every symbol include/mixq_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_enqueue",
-    "mixq_quant_extract", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
+    "mixq_quant_extract", "mixq_rmsnorm_quant_extract", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
     "mixq_host_scratch_size", "mixq_linear_host",
     "mixq_launch_count", "mixq_set_gemm_config", "mixq_debug_set_trace", "initOpenAiTritonPlugins", "mixq_plugin_create",
     "mixq_plugin_deserialize", "mixq_plugin_clone", "mixq_plugin_destroy", "mixq_plugin_type",
@@ -61,6 +61,8 @@ def load() -> ctypes.CDLL:
     L.mixq_enqueue.argtypes = [ctypes.POINTER(Tensors), i64, i64, i64, vp, sz, u32, vp]
     L.mixq_quant_extract.restype = ci
     L.mixq_quant_extract.argtypes = [vp, i64, i64, vp, ci, vp, vp, vp, u32, vp]
+    L.mixq_rmsnorm_quant_extract.restype = ci
+    L.mixq_rmsnorm_quant_extract.argtypes = [vp, vp, ctypes.c_float, i64, i64, vp, ci, vp, vp, vp, vp, u32, vp]
     L.mixq_gemm_dequant.restype = ci
     L.mixq_gemm_dequant.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
     L.mixq_gemm_workspace_size.restype = sz
@@ -155,6 +157,14 @@ def quant_extract(A, ind, A8, scale_a, fp_A, flags: int = 0, stream=None) -> Non
     n_ind = 0 if ind is None else ind.numel()
     check(load().mixq_quant_extract(_ptr(A), M, K, _ptr(ind), n_ind, _ptr(A8), _ptr(scale_a), _ptr(fp_A), flags,
                                     _stream(stream)), "mixq_quant_extract")
+
+
+def rmsnorm_quant_extract(X, gamma, eps, ind, A8, scale_a, fp_A, Y=None, flags: int = 0, stream=None) -> None:
+    M, K = X.shape
+    n_ind = 0 if ind is None else ind.numel()
+    check(load().mixq_rmsnorm_quant_extract(_ptr(X), _ptr(gamma), float(eps), M, K, _ptr(ind), n_ind, _ptr(A8),
+                                            _ptr(scale_a), _ptr(fp_A), _ptr(Y), flags, _stream(stream)),
+          "mixq_rmsnorm_quant_extract")
 
 
 def gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, stream=None, workspace=None) -> None:

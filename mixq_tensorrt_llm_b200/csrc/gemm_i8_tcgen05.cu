@@ -27,6 +27,7 @@
 // Barriers: full[kStages] (TMA -> MMA, tx bytes), empty[kStages] (MMA -> TMA, tcgen05.commit),
 //           tmem_full[kAccStages] (MMA -> epilogue), tmem_empty[kAccStages] (epilogue -> MMA).
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <type_traits>
 
@@ -667,14 +668,14 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
 // finisher's segment is the LAST thing its worker does while peer segments are the FIRST thing their
 // workers do, so the finisher practically never waits.  All workers are co-resident (grid <= #SMs).
 // With stream_k = 0 the kernel degenerates to the strided whole-tile schedule of the stash kernel.
-// Debug timeline (mixq_debug_set_trace): 8 x uint64 nanosecond stamps per CTA; null in production.
+// Debug timeline (mixq_debug_set_trace): 16 x uint64 nanosecond stamps per CTA; null in production.
 __device__ unsigned long long* g_trace = nullptr;
 __device__ __forceinline__ void trace_stamp(int slot) {
     unsigned long long* t = g_trace;
     if (t) {
         unsigned long long now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        t[blockIdx.x * 8 + slot] = now;
+        t[blockIdx.x * 16 + slot] = now;
     }
 }
 
@@ -1027,6 +1028,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                     }
                     ptx::named_bar_sync(2, kStashEpiThreads);
                 }
+                if (et == 0) trace_stamp(8);
                 const float4* sb4 = reinterpret_cast<const float4*>(sbt + col0);
                 uint32_t vi[2][32];
                 ptx::tmem_ld_32x32(t_i, vi[0]);
@@ -1085,6 +1087,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                         ptx::tma_store_commit();
                     }
                 }
+                if (et == 0) trace_stamp(9);
                 arrive(&tmem_empty_bar[b]);
                 if (n_peers > 0) {
                     // re-arm the flags for the next launch once every thread of this CTA has read the slots
@@ -1095,7 +1098,9 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
             }
             ++s;
         }
+        if (et == 0) trace_stamp(10);
         if (lane == 0) ptx::tma_store_wait_all<0>();  // outstanding output tiles fully written before the CTA retires
+        if (et == 0) trace_stamp(11);
     }
 
     if (threadIdx.x == kEpilogueWarp0 * 32) trace_stamp(7);
@@ -1204,7 +1209,12 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
         const int64_t units = num_tiles * ((K + kBlockKBytes - 1) / kBlockKBytes);
         grid = static_cast<int>(units < max_groups ? units : max_groups) * T::kCta;
     }
-    const int group_m = 8 / T::kCta;
+    // band height of the grouped rasterisation in tiles (1024 rows by default); MIXQ_GROUP_M overrides for tuning
+    static const int env_group_m = [] {
+        const char* e = getenv("MIXQ_GROUP_M");
+        return e ? atoi(e) : 0;
+    }();
+    const int group_m = env_group_m > 0 ? env_group_m : 8 / T::kCta;
 
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -1280,11 +1290,12 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
         // Measured on B200 (profiles/): a single row-block of tokens cannot use a CTA pair's 256 rows;
         // a few row-blocks (decode batches) want many small double-buffered tiles to fill 148 SMs;
         // prefill-sized M is tensor-bound and wants the widest tile (lowest operand traffic per MAC).
-        if (M < 2048 && sk_ok) cfg = kCfg2CtaN256StreamK;   // decode batches: stream-K over wide tiles
-        else if (M <= 128) cfg = kCfgN128x2;
+        if (M <= 128) cfg = kCfgN128x2;
         else if (M < 2048) cfg = kCfg2CtaN128x2;
         else cfg = kCfg2CtaN256Stash;
     }
+    if (cfg == kCfg2CtaN256Tma)  // the stream-K kernel with whole tiles: TMA-store epilogue, no scratch needed
+        return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0);
     if (cfg == kCfg2CtaN256StreamK) {
         if (!sk_ok) return set_error(MIXQ_ERR_WORKSPACE, "gemm_dequant: stream-K needs mixq_gemm_workspace_size() bytes of workspace");
         if (!sk_flags_clean) {

@@ -97,6 +97,14 @@ int mixq_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int
                                 /*pdl=*/false);
 }
 
+int mixq_rmsnorm_quant_extract(const void* X, const void* gamma, float eps, int64_t M, int64_t K, const void* ind,
+                               int n_ind, void* A8, void* scale_a, void* fp_A, void* Y, unsigned flags, void* stream) {
+    if (M < 0) return set_error(MIXQ_ERR_BAD_ARG, "rmsnorm_quant_extract: M < 0");
+    if (!gamma) return set_error(MIXQ_ERR_BAD_ARG, "rmsnorm_quant_extract: gamma is null");
+    return launch_quant_extract(X, M, K, ind, n_ind, A8, scale_a, fp_A, flags, static_cast<cudaStream_t>(stream),
+                                /*pdl=*/false, nullptr, 0, gamma, eps, Y);
+}
+
 int mixq_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                       const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, void* stream) {
     return launch_gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K,

@@ -29,7 +29,7 @@ void count_launch();
 // clear_words: optional, `n_clear` 32-bit words zeroed by CTA 0 (the stream-K flags of kernel 2)
 int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8, void* scale_a,
                          void* fp_A, unsigned flags, cudaStream_t stream, bool pdl, void* clear_words = nullptr,
-                         int n_clear = 0);
+                         int n_clear = 0, const void* gamma = nullptr, float eps = 0.0f, void* y_out = nullptr);
 
 // stage 2 (gemm_i8_tcgen05.cu)
 // sk_ws: optional stream-K scratch (streamk_workspace_bytes(): flags first, then partial-sum slots);
@@ -41,7 +41,7 @@ size_t streamk_workspace_bytes();
 int set_trace_buffer(void* dev_buf);
 
 // GEMM tile configuration ids (mixq_set_gemm_config); 0 = pick automatically.
-enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfgCount };
+enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfg2CtaN256Tma = 9, kCfgCount };
 int current_gemm_config();
 
 }  // namespace mixq

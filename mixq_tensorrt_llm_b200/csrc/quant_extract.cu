@@ -70,13 +70,19 @@ __device__ __forceinline__ __half2 absmax2(__half2 m, uint32_t v) {
 // grid: persistent CTAs striding over rows; block: 256 threads; dynamic smem: 2 * K * 2 bytes.
 // VPT = 16-byte vectors per thread (K <= VPT * 2048): the row lives in registers between the max
 // and the quantise pass and every loop has a compile-time trip count.
-template <int VPT>
+// NORM = true fuses the producer of the activations into the same pass (SURVEY.md 8f "next #1", the
+// reference's generalT5LayerNorm_extract_outliers, MixQ/src/kernel/mix_cuda/layernorm/layernorm.cu:121-198):
+//   y[k] = fp16( clamp( (float(x[k]) * rsqrtf(sum_k x[k]^2 / K + eps)) * float(gamma[k]) ) )
+// and the gather / scale / INT8 codes are taken from y (optionally also written out).
+template <int VPT, bool NORM>
 __global__ void __launch_bounds__(kQuantThreads)
 mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const int* __restrict__ ind, int n_ind,
                           int8_t* __restrict__ A8, __half* __restrict__ scale_a, __half* __restrict__ fp_A,
-                          int mask_outliers, uint32_t* __restrict__ clear_words, int n_clear) {
+                          int mask_outliers, uint32_t* __restrict__ clear_words, int n_clear,
+                          const __half* __restrict__ gamma, float eps, __half* __restrict__ y_out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t s_warp_max[kQuantThreads / 32];
+    __shared__ float s_warp_sum[kQuantThreads / 32];
     const int tid = threadIdx.x;
     const int vec_per_row = K >> 3;  // 16-byte vectors (K % 8 == 0 is checked on the host)
     uint4* const buf0 = reinterpret_cast<uint4*>(smem_raw);
@@ -110,6 +116,58 @@ mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const 
 
         uint4* rowv = buf0 + cur * vec_per_row;
         __half* rowh = reinterpret_cast<__half*>(rowv);
+
+        if constexpr (NORM) {
+            // RMSNorm in place (shared memory): sum of squares in fp32, one rsqrt per token
+            uint4 x[VPT];
+            float ss = 0.0f;
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+                x[j] = (tid + j * kQuantThreads < vec_per_row) ? rowv[tid + j * kQuantThreads] : make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t w[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+                    ss = fmaf(f.x, f.x, ss);
+                    ss = fmaf(f.y, f.y, ss);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+            if ((tid & 31) == 0) s_warp_sum[tid >> 5] = ss;
+            __syncthreads();
+            float tot = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kQuantThreads / 32; ++w) tot += s_warp_sum[w];
+            const float rs = rsqrtf(tot / static_cast<float>(K) + eps);
+            const uint4* gv = reinterpret_cast<const uint4*>(gamma);
+            uint4* yv = y_out ? reinterpret_cast<uint4*>(y_out + row * K) : nullptr;
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+                const int idx = tid + j * kQuantThreads;
+                if (idx < vec_per_row) {
+                    const uint4 g4 = __ldg(gv + idx);
+                    const uint32_t xw[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
+                    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+                    uint32_t yw[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xw[q]));
+                        const float2 g = __half22float2(*reinterpret_cast<const __half2*>(&gw[q]));
+                        float y0 = __fmul_rn(__fmul_rn(f.x, rs), g.x), y1 = __fmul_rn(__fmul_rn(f.y, rs), g.y);
+                        // clamp_inf_for_half (reduction.cuh:111-115)
+                        y0 = y0 > 0.0f ? fminf(y0, 64504.0f) : fmaxf(y0, -64504.0f);
+                        y1 = y1 > 0.0f ? fminf(y1, 64504.0f) : fmaxf(y1, -64504.0f);
+                        const __half2 h = __floats2half2_rn(y0, y1);
+                        yw[q] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    const uint4 y4 = make_uint4(yw[0], yw[1], yw[2], yw[3]);
+                    rowv[idx] = y4;
+                    if (yv) yv[idx] = y4;
+                }
+            }
+            __syncthreads();  // the normalised row is what the gather and the quantiser see
+        }
 
         // outlier gather (and, in MixQ/src mode, zeroing: cult.cu:1588)
         if (tid < n_ind) fp_A[row * n_ind + tid] = rowh[ind[tid]];
@@ -171,29 +229,30 @@ mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const 
     ptx::pdl_launch_dependents();
 }
 
-using QuantKernel = void (*)(const __half*, int64_t, int, const int*, int, int8_t*, __half*, __half*, int, uint32_t*, int);
+using QuantKernel = void (*)(const __half*, int64_t, int, const int*, int, int8_t*, __half*, __half*, int, uint32_t*, int,
+                             const __half*, float, __half*);
 struct QuantVariant {
     int vpt;
-    QuantKernel fn;
+    QuantKernel fn, fn_norm;
 };
-const QuantVariant kQuantVariants[] = {
-    {1, mixq_quant_extract_kernel<1>},   {2, mixq_quant_extract_kernel<2>},   {3, mixq_quant_extract_kernel<3>},
-    {4, mixq_quant_extract_kernel<4>},   {6, mixq_quant_extract_kernel<6>},   {8, mixq_quant_extract_kernel<8>},
-    {10, mixq_quant_extract_kernel<10>}, {12, mixq_quant_extract_kernel<12>}, {14, mixq_quant_extract_kernel<14>},
-    {16, mixq_quant_extract_kernel<16>}, {24, mixq_quant_extract_kernel<24>}, {32, mixq_quant_extract_kernel<32>},
-};
+#define MIXQ_QV(n) {n, mixq_quant_extract_kernel<n, false>, mixq_quant_extract_kernel<n, true>}
+const QuantVariant kQuantVariants[] = {MIXQ_QV(1),  MIXQ_QV(2),  MIXQ_QV(3),  MIXQ_QV(4),  MIXQ_QV(6),  MIXQ_QV(8),
+                                       MIXQ_QV(10), MIXQ_QV(12), MIXQ_QV(14), MIXQ_QV(16), MIXQ_QV(24), MIXQ_QV(32)};
+#undef MIXQ_QV
 
 }  // namespace
 
 int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8, void* scale_a,
-                         void* fp_A, unsigned flags, cudaStream_t stream, bool pdl, void* clear_words, int n_clear) {
+                         void* fp_A, unsigned flags, cudaStream_t stream, bool pdl, void* clear_words, int n_clear,
+                         const void* gamma, float eps, void* y_out) {
     if (M == 0) return MIXQ_OK;
     if (K <= 0 || (K & 7) != 0) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: K must be a positive multiple of 8");
     if (n_ind < 0 || n_ind > kQuantThreads) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: n_ind must be in [0,256]");
     if (n_ind > 0 && (!ind || !fp_A)) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: ind/fp_A null");
     if (!A || !A8 || !scale_a) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: null pointer");
-    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(A8) & 7))
-        return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: A must be 16-byte and A8 8-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(A8) & 7) ||
+        (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(y_out) & 15))
+        return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: A/gamma/Y must be 16-byte and A8 8-byte aligned");
 
     const DeviceInfo& dev = device_info();
     if (!dev.ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
@@ -203,7 +262,7 @@ int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, i
     QuantKernel kern = nullptr;
     for (const QuantVariant& qv : kQuantVariants)
         if (qv.vpt >= need_vpt) {
-            kern = qv.fn;
+            kern = gamma ? qv.fn_norm : qv.fn;
             break;
         }
     if (!kern) return set_error(MIXQ_ERR_UNSUPPORTED, "quant_extract: K too large (max 65536)");
@@ -232,7 +291,8 @@ int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, i
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<const __half*>(A), M,
                                        static_cast<int>(K), static_cast<const int*>(ind), n_ind,
                                        static_cast<int8_t*>(A8), static_cast<__half*>(scale_a),
-                                       static_cast<__half*>(fp_A), mask, static_cast<uint32_t*>(clear_words), n_clear);
+                                       static_cast<__half*>(fp_A), mask, static_cast<uint32_t*>(clear_words), n_clear,
+                                       static_cast<const __half*>(gamma), eps, static_cast<__half*>(y_out));
     if (e != cudaSuccess) return set_cuda_error(e, "launch quant_extract");
     count_launch();
     return MIXQ_OK;

@@ -191,6 +191,28 @@ void mixq_oracle_epilogue(const int32_t* acc, const uint16_t* scale_a, const uin
     }
 }
 
+/* "next #1" producer fusion -- MixQ/src/kernel/mix_cuda/layernorm/layernorm.cu:121-157
+ * (generalT5LayerNorm_extract_outliers, RMSNorm part):
+ *   s = rsqrtf(sum_k x^2 / n + eps);  y = clamp_inf_for_half((float(x) * s) * float(gamma))
+ * The device sums in fp32 in tree order and uses the approximate rsqrt; the oracle sums in double and
+ * uses 1/sqrtf, so y may differ from the device in the last fp16 bit on a small fraction of elements. */
+void mixq_oracle_rmsnorm(const uint16_t* X, const uint16_t* gamma, float eps, int64_t M, int64_t K, uint16_t* Y) {
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < M; ++m) {
+        double ss = 0.0;
+        for (int64_t k = 0; k < K; ++k) {
+            const double x = (double)(float)bits_to_f16(X[m * K + k]);
+            ss += x * x;
+        }
+        const float s = 1.0f / sqrtf((float)ss / (float)K + eps);
+        for (int64_t k = 0; k < K; ++k) {
+            float y = ((float)bits_to_f16(X[m * K + k]) * s) * (float)bits_to_f16(gamma[k]);
+            y = y > 0.0f ? fminf(y, 65504.0f - 1000.0f) : fmaxf(y, -65504.0f + 1000.0f); /* reduction.cuh:111-115 */
+            Y[m * K + k] = f16_to_bits((f16)y);
+        }
+    }
+}
+
 /* MixQPlugin::enqueueImpl M>4 branch, TsinghuaMixQPlugin.cpp:518-532, in call order.
  * scratch buffers are caller-provided so the timing legs do not measure malloc:
  *   fp_A [M,128] u16 | out0 [M,N] u16 | q [M,K] i8 | sa [M] u16 | acc [M,N] i32 */

@@ -59,6 +59,8 @@ def lib():
         L.mixq_oracle_epilogue.argtypes = [i32p, u16p, u16p, u16p, i64, i64, u16p]
         L.mixq_oracle_forward.argtypes = [u16p, i8p, u16p, u16p, i32p, i32, i64, i64, i64, u32p, i32,
                                           u16p, u16p, i8p, u16p, i32p, u16p]
+        L.mixq_oracle_rmsnorm.argtypes = [u16p, u16p, ctypes.c_float, i64, i64, u16p]
+        L.mixq_oracle_rmsnorm.restype = None
         L.mixq_oracle_num_threads.restype = i32
         L.mixq_oracle_set_threads.argtypes = [i32]
         L.mixq_oracle_set_threads.restype = None
@@ -129,6 +131,15 @@ def quant(A: np.ndarray, ind: np.ndarray | None = None, mask: bool = False, use_
                             _P(ind, ctypes.c_int32), ind.size, int(mask), _P(q, ctypes.c_int8),
                             _P(sa.view(np.uint16), ctypes.c_uint16))
     return q, sa
+
+
+def rmsnorm(X: np.ndarray, gamma: np.ndarray, eps: float) -> np.ndarray:
+    """layernorm.cu:121-157 -- T5-style RMSNorm, fp32 math, fp16 result (the producer of the linear's input)."""
+    M, K = X.shape
+    Y = np.empty((M, K), dtype=np.float16)
+    lib().mixq_oracle_rmsnorm(_P(_u16(X), ctypes.c_uint16), _P(_u16(gamma), ctypes.c_uint16), float(eps), M, K,
+                              _P(Y.view(np.uint16), ctypes.c_uint16))
+    return Y
 
 
 def outlier_gemm(fp_A: np.ndarray, fp_weight: np.ndarray) -> np.ndarray:

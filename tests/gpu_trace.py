@@ -17,7 +17,7 @@ fpA = torch.randn(M, 128, device=dev).half()
 fw = (torch.randn(N, 128, device=dev) * 0.02).half()
 out = torch.empty(M, N, dtype=torch.float16, device=dev)
 ws = torch.zeros(lib.mixq_gemm_workspace_size(), dtype=torch.uint8, device=dev)
-trace = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 lib.mixq_set_gemm_config(8)
 for it in range(4):
     B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws)
@@ -26,9 +26,10 @@ B.check(lib.mixq_debug_set_trace(trace.data_ptr()), "trace")
 B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws)
 torch.cuda.synchronize()
 lib.mixq_debug_set_trace(None)
-t = trace.cpu().numpy().reshape(148, 8).astype(np.float64)
+t = trace.cpu().numpy().reshape(148, 16).astype(np.float64)
 t0 = t[:, 0][t[:, 0] > 0].min()
-names = ["entry", "prologue", "firstTMA", "tile0issued", "mmaDone", "acc0ready", "accLast", "epiDone"]
+names = ["entry", "prologue", "firstTMA", "tile0issued", "mmaDone", "acc0ready", "accLast", "epiDone",
+         "peersIn", "chunksDone", "loopExit", "storesDone"]
 rel = np.where(t > 0, (t - t0) / 1e3, np.nan)
 print("shape", M, N, K, "us relative to first CTA entry")
 for i, n in enumerate(names):
@@ -36,5 +37,5 @@ for i, n in enumerate(names):
     ok = ~np.isnan(col)
     if ok.any():
         print(f"{n:12s} min {np.nanmin(col):7.2f} med {np.nanmedian(col):7.2f} max {np.nanmax(col):7.2f}  (n={ok.sum()})")
-for c in (0, 1, 2, 3, 72, 73, 146, 147):
-    print("cta", c, np.round(rel[c], 2).tolist())
+for c in (0, 2, 72, 146):
+    print("cta", c, np.round(rel[c][:12], 2).tolist())

@@ -137,13 +137,47 @@ def test_quant_only_no_outliers(B, oracle):
     assert (A8.cpu().numpy() != oq).mean() < (1e-4 if oracle.rcp_table() is None else 1e-12)
 
 
+@pytest.mark.parametrize("M,K", [(7, 256), (64, 4096), (300, 3584), (40, 11008)])
+@pytest.mark.parametrize("mask", [True, False])
+def test_rmsnorm_quant_extract(B, oracle, M, K, mask):
+    """'next #1': RMSNorm fused into stage 1 (layernorm.cu:121-198).  The normalised row may differ from the
+    CPU restatement in the last fp16 bit (fp32 tree sum + MUFU.RSQ on the device); everything downstream of
+    it (gather, scale, INT8 codes) must be bit-exact given the device's own normalised row."""
+    rng = np.random.default_rng(M + K)
+    X = (rng.standard_normal((M, K)) * 1.5).astype(np.float16)
+    X[:, rng.choice(K, 16, replace=False)] *= 30
+    if M > 4:
+        X[1] = 0
+    gamma = (1 + 0.2 * rng.standard_normal(K)).astype(np.float16)
+    ind = rng.choice(K, size=128, replace=False).astype(np.int32)
+    A8 = torch.empty(M, K, dtype=torch.int8, device=DEV)
+    sa = torch.empty(M, dtype=torch.float16, device=DEV)
+    fpA = torch.empty(M, 128, dtype=torch.float16, device=DEV)
+    Y = torch.empty(M, K, dtype=torch.float16, device=DEV)
+    B.rmsnorm_quant_extract(_t(X), _t(gamma), 1e-5, _t(ind), A8, sa, fpA, Y, flags=B.FLAG_MASK_OUTLIERS if mask else 0)
+    torch.cuda.synchronize()
+    y = Y.cpu().numpy()
+    yo = oracle.rmsnorm(X, gamma, 1e-5)
+    assert _ulp_diff(y, yo).max() <= 1.0
+    assert (y.view(np.uint16) != yo.view(np.uint16)).mean() < 0.02
+    oq, osa = oracle.quant(y, ind=ind, mask=mask)
+    assert np.array_equal(fpA.cpu().numpy().view(np.uint16), y[:, ind].view(np.uint16))
+    assert np.array_equal(sa.cpu().numpy().view(np.uint16), osa.view(np.uint16))
+    assert np.array_equal(A8.cpu().numpy(), oq)
+    # and it equals the unfused sequence on the device: mixq_quant_extract applied to the same y
+    A8b, sab, fpAb = torch.empty_like(A8), torch.empty_like(sa), torch.empty_like(fpA)
+    B.quant_extract(Y, _t(ind), A8b, sab, fpAb, flags=B.FLAG_MASK_OUTLIERS if mask else 0)
+    torch.cuda.synchronize()
+    assert torch.equal(A8, A8b) and torch.equal(sa.view(torch.int16), sab.view(torch.int16))
+
+
 # ----------------------------------------------------------------------------- stage 2
 GEMM_SHAPES = [(128, 128, 128), (128, 128, 256), (256, 256, 512), (1, 8, 16), (100, 136, 144), (5, 4096, 4096),
                (130, 264, 4096), (512, 1024, 4096), (300, 512, 11008), (257, 1280, 8192), (32, 12288, 4096),
                (512, 256, 28672)]
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     """No outlier slab: int32 accumulation is exact, the epilogue is one fma + one rounding, so
@@ -166,7 +200,7 @@ def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     assert bad.size == 0, f"{len(bad)} mismatches, first at {bad[:5].tolist()}: got {got[tuple(bad[0])]} want {ref[tuple(bad[0])]}"
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (100, 136, 144), (300, 520, 1040), (64, 512, 4096), (512, 1024, 4096)])
 def test_gemm_dequant_with_outlier_slab(B, lib, oracle, cfg, M, N, K):
     rng = np.random.default_rng(M + N + K)

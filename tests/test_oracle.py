@@ -142,6 +142,20 @@ def test_forward_composition_and_accuracy(oracle):
     assert rel2 < 1e-3, rel2   # fp16 output rounding only
 
 
+def test_rmsnorm_against_numpy(oracle):
+    rng = np.random.default_rng(5)
+    X = (rng.standard_normal((9, 640)) * 2).astype(np.float16)
+    X[3] = 0
+    X[4, 7] = 60000.0
+    g = (1 + 0.1 * rng.standard_normal(640)).astype(np.float16)
+    Y = oracle.rmsnorm(X, g, 1e-5)
+    x32 = X.astype(np.float32)
+    s = (1.0 / np.sqrt((x32.astype(np.float64) ** 2).sum(1).astype(np.float32) / np.float32(640) + np.float32(1e-5))).astype(np.float32)
+    ref = np.clip((x32 * s[:, None]) * g.astype(np.float32)[None, :], -64504, 64504).astype(np.float16)
+    assert np.array_equal(Y.view(np.uint16), ref.view(np.uint16))
+    assert (Y[3] == 0).all() and np.isfinite(Y.astype(np.float32)).all()
+
+
 def test_rcp_table_fixture(oracle):
     """The captured rcp.approx table (when present) is within 1 ulp of the exact reciprocal."""
     t = oracle.rcp_table()
