@@ -123,7 +123,7 @@ def traffic_from_profile():
     p = ROOT / "profiles" / "r1_traffic.json"
     if not p.exists():
         return None
-    d = json.loads(p.read_text())["mixq_gemm_dequant_stash_kernel"]
+    d = json.loads(p.read_text())["gemm"]
     return {"bytes": d["dram_read_bytes"] + d["dram_write_bytes"], "algorithmic_bytes": d["algorithmic_bytes"],
             "shape": d["shape"], "source": "profiles/r1_ncu_summary.csv"}
 
@@ -306,7 +306,7 @@ def run_ours(args, M, linears):
     int8_peak = 2.0 * pk["bf16_sustained"]
     gemm_flops = sum(2.0 * M * Ns * Ks for _, _, Ns, Ks, _ in mods)
     achieved = gemm_flops / tot_gemm / 1e6
-    roofline = {"bound": "tensor", "kernel": "mixq_gemm_dequant_stash_kernel (tcgen05 kind::i8 + kind::f16, cta_group::2)",
+    roofline = {"bound": "tensor", "kernel": "mixq_gemm_dequant_streamk_kernel, whole-tile schedule (tcgen05 kind::i8 + kind::f16, cta_group::2, TMA-store epilogue)",
                 "achieved": round(achieved, 1), "peak": round(int8_peak, 1), "unit": "TFLOP/s",
                 "frac": round(achieved / int8_peak, 4),
                 "peak_source": f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({pk['src']}); INT8 dense = 2 x BF16 dense",
