@@ -121,11 +121,12 @@ def traffic_from_profile():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (qkv shape at
     M=65536), from the committed ncu --set full capture (profiles/r1_traffic.json); None if absent."""
     p = ROOT / "profiles" / "r1_traffic.json"
-    if not p.exists():
+    try:
+        d = json.loads(p.read_text())["gemm"]
+        return {"bytes": d["dram_read_bytes"] + d["dram_write_bytes"], "algorithmic_bytes": d["algorithmic_bytes"],
+                "shape": d["shape"], "source": "profiles/r1_ncu_summary.csv"}
+    except (OSError, KeyError, ValueError):
         return None
-    d = json.loads(p.read_text())["gemm"]
-    return {"bytes": d["dram_read_bytes"] + d["dram_write_bytes"], "algorithmic_bytes": d["algorithmic_bytes"],
-            "shape": d["shape"], "source": "profiles/r1_ncu_summary.csv"}
 
 
 def shard(N, K, mode, tp):
