@@ -249,8 +249,25 @@ def run_ours(args, M, linears):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    nl0 = lib.mixq_launch_count()
+    step()
+    launches_per_step = lib.mixq_launch_count() - nl0
+    # Decode-sized steps are a handful of 10-30 us kernels: replay them from a CUDA graph, as a serving
+    # runtime (TensorRT) would, so the step is not bounded by Python/launch latency.
+    use_graph = args.graph == "on" or (args.graph == "auto" and M <= 2048 and world == 1)
+    run_step = step
+    if use_graph:
+        gs = torch.cuda.Stream()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(gs):
+            step()
+            gs.synchronize()
+            with torch.cuda.graph(graph, stream=gs):
+                step()
+        torch.cuda.synchronize()
+        run_step = graph.replay
     for _ in range(max(args.warmup, 3)):
-        step()
+        run_step()
     barrier()
     n0 = lib.mixq_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -258,12 +275,12 @@ def run_ours(args, M, linears):
     sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
-        step()
+        run_step()
     e1.record()
     barrier()
     sampler.mark_end()
     ms = e0.elapsed_time(e1)
-    launches = lib.mixq_launch_count() - n0
+    launches = launches_per_step * args.steps if use_graph else lib.mixq_launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -419,6 +436,7 @@ def run_ours(args, M, linears):
                 "scaling": "strong", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
                 "config": {"workload": args.workload, "tokens_per_step": M,
                            "linears": [[n, N, K, m] for n, N, K, m in linears],
+                           "launch": "cuda-graph replay of the step" if use_graph else "direct launches",
                            "parallelism": (f"tp{tp} (column: no collective; row: one NCCL all-reduce in {chunks} overlapped row slabs)"
                                            if tp > 1 else "single"),
                            "l2": "inputs larger than L2 (activations %.0f MB per linear), no flush" % (M * 4096 * 2 / 1e6)
@@ -441,6 +459,8 @@ def main():
     ap.add_argument("--cpu-sample-tokens", type=int, default=512)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--tp-chunks", type=int, default=4, help="row slabs per row-parallel linear (comm/compute overlap)")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step from a CUDA graph (auto: decode-sized M on one GPU)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")

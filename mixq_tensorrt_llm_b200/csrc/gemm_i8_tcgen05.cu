@@ -26,6 +26,7 @@
 //            tile i overlaps the main loop of tile i+1.
 // Barriers: full[kStages] (TMA -> MMA, tx bytes), empty[kStages] (MMA -> TMA, tcgen05.commit),
 //           tmem_full[kAccStages] (MMA -> epilogue), tmem_empty[kAccStages] (epilogue -> MMA).
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -1133,8 +1134,8 @@ EncodeTiledFn get_encode_fn() {
 
 // 2D row-major [rows, cols] tensor of `elem_bytes` elements, box = `box_bytes` x box_rows with the matching
 // swizzle (128 B for the operand tiles, 64 B for the output tiles).
-int make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols,
-              uint32_t box_rows, int box_bytes = kBlockKBytes) {
+int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols,
+                uint32_t box_rows, int box_bytes) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return set_error(MIXQ_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t gdim[2] = {cols, rows};
@@ -1150,6 +1151,66 @@ int make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const vo
                  (unsigned long long)rows, (unsigned long long)cols, elem_bytes);
         return set_error(MIXQ_ERR_CUDA, buf);
     }
+    return MIXQ_OK;
+}
+
+// Tensor maps are pure functions of (base, shape, box): a small cache keeps the per-enqueue host cost at a few
+// compares once a layer's pointers have been seen (weights are engine constants, the workspace is reused).
+struct TmapKey {
+    const void* base;
+    uint64_t rows, cols;
+    uint32_t box_rows;
+    int dt, elem_bytes, box_bytes;
+    bool operator==(const TmapKey& o) const {
+        return base == o.base && rows == o.rows && cols == o.cols && box_rows == o.box_rows && dt == o.dt &&
+               elem_bytes == o.elem_bytes && box_bytes == o.box_bytes;
+    }
+};
+constexpr int kTmapCacheSize = 256;
+struct TmapCache {
+    std::mutex lock;
+    TmapKey keys[kTmapCacheSize];
+    CUtensorMap maps[kTmapCacheSize];
+    bool valid[kTmapCacheSize] = {};
+    unsigned next = 0;
+};
+TmapCache& tmap_cache() {
+    static TmapCache c;
+    return c;
+}
+
+// 2D row-major [rows, cols] tensor of `elem_bytes` elements, box = `box_bytes` x box_rows with the matching
+// swizzle (128 B for the operand tiles, 64 B for the output tiles).
+int make_tmap(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols,
+              uint32_t box_rows, int box_bytes = kBlockKBytes) {
+    const TmapKey key{base, rows, cols, box_rows, static_cast<int>(dt), elem_bytes, box_bytes};
+    TmapCache& c = tmap_cache();
+    const unsigned h = static_cast<unsigned>((reinterpret_cast<uintptr_t>(base) >> 8) * 2654435761u + rows * 40503u + box_rows) % kTmapCacheSize;
+    {
+        std::lock_guard<std::mutex> g(c.lock);
+        for (int probe = 0; probe < 4; ++probe) {
+            const unsigned i = (h + probe) % kTmapCacheSize;
+            if (c.valid[i] && c.keys[i] == key) {
+                *map = c.maps[i];
+                return MIXQ_OK;
+            }
+        }
+    }
+    const int rc = encode_tmap(map, dt, elem_bytes, base, rows, cols, box_rows, box_bytes);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(c.lock);
+    unsigned slot = h;
+    for (int probe = 0; probe < 4; ++probe) {
+        const unsigned i = (h + probe) % kTmapCacheSize;
+        if (!c.valid[i]) {
+            slot = i;
+            break;
+        }
+        if (probe == 3) slot = (h + (c.next++ & 3)) % kTmapCacheSize;
+    }
+    c.keys[slot] = key;
+    c.maps[slot] = *map;
+    c.valid[slot] = true;
     return MIXQ_OK;
 }
 
@@ -1195,8 +1256,13 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
         tm_fw = tm_w8;
     }
     auto kern = KernelOf<T>::get();
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::kSmemBytes));
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_dequant)");
+    cudaError_t e = cudaSuccess;
+    static std::atomic<int> attr_set_for_device{-1};   // per template instantiation
+    if (attr_set_for_device.load(std::memory_order_acquire) != dev.device) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::kSmemBytes));
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_dequant)");
+        attr_set_for_device.store(dev.device, std::memory_order_release);
+    }
 
     const int m_tiles = static_cast<int>((M + T::kTileM - 1) / T::kTileM);
     const int n_tiles = static_cast<int>((N + T::kBlockN - 1) / T::kBlockN);
