@@ -352,10 +352,11 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
 //                                       -> wait tmem_full(b) -> out = fma(float(I), sa*sb, stash) -> release b
 // f_drained(b^1) gates the main loop of tile t+1 (which accumulates into b^1); both happen half a
 // main loop earlier than needed, so in steady state the tensor core never waits.
-template <int CTA, int STAGES>
+template <int CTA, int STAGES, int BLOCK_N = 256>
 struct StashTraits {
     static constexpr int kCta = CTA;
-    static constexpr int kBlockN = 256;
+    static constexpr int kBlockN = BLOCK_N;   // 256, or 192 for decode-sized M (more, smaller tiles per wave)
+    static_assert(BLOCK_N % 64 == 0 && BLOCK_N <= 256 && (BLOCK_N / CTA) % 8 == 0, "two column halves of whole 32-column chunks");
     static constexpr int kLoadN = kBlockN / CTA;
     static constexpr int kTileM = kBlockM * CTA;
     static constexpr int kStages = STAGES;
@@ -934,7 +935,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
             }
         };
         // slot of worker w, CTA rank r: 32 vectors x 256 threads x 16 B = 128 KB, thread-major (coalesced)
-        auto slot_of = [&](int w) { return sk_slots + (static_cast<size_t>(w) * CTA + cta_rank) * (32 * kStashEpiThreads) + et; };
+        auto slot_of = [&](int w) { return sk_slots + (static_cast<size_t>(w) * CTA + cta_rank) * (32 * kStashEpiThreads) + et; };  // 32 >= kCols / 4
         auto flag_of = [&](int w) { return sk_flags + static_cast<size_t>(w) * CTA + cta_rank; };
         uint32_t n_int[2] = {0, 0}, n_f[2] = {0, 0};
         int s = 0;
@@ -949,7 +950,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
             float* sbt = sb_s + b * BLOCK_N;
             float sa_f = 0.0f;
             if (finisher) {
-                sbt[et] = (n0 + et < N) ? __half2float(scale_b[n0 + et]) : 0.0f;
+                if (et < BLOCK_N) sbt[et] = (n0 + et < N) ? __half2float(scale_b[n0 + et]) : 0.0f;
                 sa_f = gm < M ? __half2float(scale_a[gm]) : 0.0f;
                 // the previous tile's TMA stores must have finished READING this warp's tiles
                 if (lane == 0) ptx::tma_store_wait_read<0>();
@@ -1220,22 +1221,22 @@ struct KernelOf {
     static auto get() { return mixq_gemm_dequant_kernel<T>; }
 };
 template <int CTA, int STAGES>
-struct KernelOf<StashTraits<CTA, STAGES>> {
+struct KernelOf<StashTraits<CTA, STAGES, 256>> {
     static constexpr int kThreads = kStashThreads;
-    static auto get() { return mixq_gemm_dequant_stash_kernel<StashTraits<CTA, STAGES>>; }
+    static auto get() { return mixq_gemm_dequant_stash_kernel<StashTraits<CTA, STAGES, 256>>; }
 };
 
-template <int CTA, int STAGES>
-struct StreamKTraits : StashTraits<CTA, STAGES> {};
-template <int CTA, int STAGES>
-struct KernelOf<StreamKTraits<CTA, STAGES>> {
+template <int CTA, int STAGES, int BLOCK_N = 256>
+struct StreamKTraits : StashTraits<CTA, STAGES, BLOCK_N> {};
+template <int CTA, int STAGES, int BLOCK_N>
+struct KernelOf<StreamKTraits<CTA, STAGES, BLOCK_N>> {
     static constexpr int kThreads = kStashThreads;
-    static auto get() { return mixq_gemm_dequant_streamk_kernel<StashTraits<CTA, STAGES>>; }
+    static auto get() { return mixq_gemm_dequant_streamk_kernel<StashTraits<CTA, STAGES, BLOCK_N>>; }
 };
 template <class T>
 struct IsStreamK : std::false_type {};
-template <int CTA, int STAGES>
-struct IsStreamK<StreamKTraits<CTA, STAGES>> : std::true_type {};
+template <int CTA, int STAGES, int BLOCK_N>
+struct IsStreamK<StreamKTraits<CTA, STAGES, BLOCK_N>> : std::true_type {};
 
 template <class T>
 int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
@@ -1361,6 +1362,8 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
         else if (M < 2048) cfg = kCfg2CtaN128x2;
         else cfg = kCfg2CtaN256Tma;
     }
+    if (cfg == kCfg2CtaN192Tma)  // 256x192 pair tiles: more tiles per wave for decode-sized M
+        return launch_cfg<StreamKTraits<2, 5, 192>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0);
     if (cfg == kCfg2CtaN256Tma)  // the stream-K kernel with whole tiles: TMA-store epilogue, no scratch needed
         return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0);
     if (cfg == kCfg2CtaN256StreamK) {

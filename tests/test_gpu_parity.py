@@ -177,7 +177,7 @@ GEMM_SHAPES = [(128, 128, 128), (128, 128, 256), (256, 256, 512), (1, 8, 16), (1
                (512, 256, 28672)]
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     """No outlier slab: int32 accumulation is exact, the epilogue is one fma + one rounding, so
@@ -200,7 +200,7 @@ def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     assert bad.size == 0, f"{len(bad)} mismatches, first at {bad[:5].tolist()}: got {got[tuple(bad[0])]} want {ref[tuple(bad[0])]}"
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (100, 136, 144), (300, 520, 1040), (64, 512, 4096), (512, 1024, 4096)])
 def test_gemm_dequant_with_outlier_slab(B, lib, oracle, cfg, M, N, K):
     rng = np.random.default_rng(M + N + K)
