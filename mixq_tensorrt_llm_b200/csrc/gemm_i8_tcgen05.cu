@@ -1355,12 +1355,31 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
     const bool sk_ok = sk_ws && sk_ws_bytes >= streamk_workspace_bytes() && (reinterpret_cast<uintptr_t>(sk_ws) & 15) == 0;
     int cfg = current_gemm_config();
     if (cfg == kCfgAuto) {
-        // Measured on B200 (profiles/): a single row-block of tokens cannot use a CTA pair's 256 rows;
-        // a few row-blocks (decode batches) want many small double-buffered tiles to fill 148 SMs;
-        // prefill-sized M is tensor-bound and wants the widest tile (lowest operand traffic per MAC).
-        if (M <= 128) cfg = kCfgN128x2;
-        else if (M < 2048) cfg = kCfg2CtaN128x2;
-        else cfg = kCfg2CtaN256Tma;
+        // Pick the tile shape with the lowest estimated time = waves x (cycles per K-block) x K-blocks + exposed
+        // tail.  Cycles per K-block are the measured steady-state figures (profiles/): the 128-wide
+        // tiles are shared-memory bound, only the 256-wide pair tile runs near the tensor peak, and wider tiles
+        // leave a longer un-overlapped final epilogue.  A single row-block of tokens cannot use a CTA pair.
+        const DeviceInfo& dev = device_info();
+        const int64_t nkb = (K + kBlockKBytes - 1) / kBlockKBytes + kOutlierKBlocks;
+        struct Cand {
+            int id, tile_m, tile_n, cta;
+            int64_t kb_cycles, tail_cycles;
+        };
+        const Cand cands[] = {{kCfgN128x2, 128, 128, 1, 512, 3000},
+                              {kCfg2CtaN128x2, 256, 128, 2, 384, 3000},
+                              {kCfg2CtaN192Tma, 256, 192, 2, 436, 4500},
+                              {kCfg2CtaN256Tma, 256, 256, 2, 556, 6000}};
+        int64_t best = INT64_MAX;
+        for (const Cand& c : cands) {
+            if (M <= 128 && c.cta == 2) continue;
+            const int64_t tiles = ((M + c.tile_m - 1) / c.tile_m) * ((N + c.tile_n - 1) / c.tile_n);
+            const int64_t workers = dev.num_sms / c.cta;
+            const int64_t est = ((tiles + workers - 1) / workers) * c.kb_cycles * nkb + c.tail_cycles;
+            if (est < best) {
+                best = est;
+                cfg = c.id;
+            }
+        }
     }
     if (cfg == kCfg2CtaN192Tma)  // 256x192 pair tiles: more tiles per wave for decode-sized M
         return launch_cfg<StreamKTraits<2, 5, 192>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0);
