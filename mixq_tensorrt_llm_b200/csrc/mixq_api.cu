@@ -153,28 +153,84 @@ size_t mixq_host_scratch_size(int64_t M, int64_t N, int64_t K) {
            mixq_workspace_size(M, N, K) + kAlign;
 }
 
-int mixq_linear_host(const mixq_tensors* t, const void* A_host, void* Out_host, int64_t M, int64_t N, int64_t K,
-                     void* dev_scratch, size_t dev_scratch_bytes, unsigned flags, void* stream) {
+}  // extern "C" (part 1)
+
+// Host-buffer path.  The rows are cut into slabs and pipelined over three streams -- H2D of slab c+1, the two
+// kernels of slab c (on the caller's stream) and D2H of slab c-1 run concurrently -- so a call costs
+// max(H2D, D2H) over PCIe instead of their sum plus the compute.
+namespace {
+struct HostPipe {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t entry = nullptr, up[64] = {}, done[64] = {}, drained = nullptr;
+    bool ok = false;
+    HostPipe() {
+        ok = cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&entry, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&drained, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; ok && i < 64; ++i)
+            ok = cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+};
+HostPipe& host_pipe() {
+    static thread_local HostPipe p;  // streams/events are cheap to keep; one set per calling thread
+    return p;
+}
+}  // namespace
+
+extern "C" int mixq_linear_host(const mixq_tensors* t, const void* A_host, void* Out_host, int64_t M, int64_t N, int64_t K,
+                                void* dev_scratch, size_t dev_scratch_bytes, unsigned flags, void* stream) {
     if (!t || !A_host || !Out_host || !dev_scratch) return set_error(MIXQ_ERR_BAD_ARG, "linear_host: null pointer");
     if (M <= 0 || N <= 0 || K <= 0) return set_error(MIXQ_ERR_BAD_ARG, "linear_host: bad dimensions");
     if (dev_scratch_bytes < mixq_host_scratch_size(M, N, K)) return set_error(MIXQ_ERR_WORKSPACE, "linear_host: scratch too small");
+    if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
+    HostPipe& hp = host_pipe();
+    if (!hp.ok) return set_error(MIXQ_ERR_CUDA, "linear_host: could not create the copy streams");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     uintptr_t base = (reinterpret_cast<uintptr_t>(dev_scratch) + kAlign - 1) / kAlign * kAlign;
     uint8_t* dA = reinterpret_cast<uint8_t*>(base);
     uint8_t* dOut = dA + align_up(static_cast<size_t>(M) * K * 2);
     uint8_t* ws = dOut + align_up(static_cast<size_t>(M) * N * 2);
-    cudaError_t e = cudaMemcpyAsync(dA, A_host, static_cast<size_t>(M) * K * 2, cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) return set_cuda_error(e, "H2D activations");
-    mixq_tensors d = *t;
-    d.A = dA;
-    d.Out = dOut;
-    int rc = mixq_enqueue(&d, M, N, K, ws, mixq_workspace_size(M, N, K), flags, stream);
-    if (rc) return rc;
-    e = cudaMemcpyAsync(Out_host, dOut, static_cast<size_t>(M) * N * 2, cudaMemcpyDeviceToHost, s);
-    if (e != cudaSuccess) return set_cuda_error(e, "D2H output");
-    e = cudaStreamSynchronize(s);
+    const size_t ws_bytes = mixq_workspace_size(M, N, K);
+
+    // slabs of >= 2048 rows (a multiple of the 256-row tile), at most 64 of them
+    int64_t rows = (M + 7) / 8;
+    rows = rows < 2048 ? 2048 : (rows + 255) / 256 * 256;
+    while ((M + rows - 1) / rows > 64) rows *= 2;
+    const int n_slabs = static_cast<int>((M + rows - 1) / rows);
+
+    cudaError_t e = cudaEventRecord(hp.entry, s);  // earlier work on the caller's stream may still use the scratch
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.h2d, hp.entry, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.d2h, hp.entry, 0);
+    if (e != cudaSuccess) return set_cuda_error(e, "linear_host: stream setup");
+    const uint8_t* hA = static_cast<const uint8_t*>(A_host);
+    uint8_t* hO = static_cast<uint8_t*>(Out_host);
+    for (int c = 0; c < n_slabs; ++c) {
+        const int64_t r0 = c * rows, nr = (r0 + rows <= M) ? rows : M - r0;
+        e = cudaMemcpyAsync(dA + r0 * K * 2, hA + r0 * K * 2, static_cast<size_t>(nr) * K * 2, cudaMemcpyHostToDevice, hp.h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(hp.up[c], hp.h2d);
+        if (e != cudaSuccess) return set_cuda_error(e, "H2D activations");
+    }
+    for (int c = 0; c < n_slabs; ++c) {
+        const int64_t r0 = c * rows, nr = (r0 + rows <= M) ? rows : M - r0;
+        e = cudaStreamWaitEvent(s, hp.up[c], 0);
+        if (e != cudaSuccess) return set_cuda_error(e, "linear_host: wait H2D");
+        mixq_tensors d = *t;
+        d.A = dA + r0 * K * 2;
+        d.Out = dOut + r0 * N * 2;
+        const int rc = mixq_enqueue(&d, nr, N, K, ws, ws_bytes, flags, stream);
+        if (rc) return rc;
+        e = cudaEventRecord(hp.done[c], s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.d2h, hp.done[c], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(hO + r0 * N * 2, dOut + r0 * N * 2, static_cast<size_t>(nr) * N * 2, cudaMemcpyDeviceToHost, hp.d2h);
+        if (e != cudaSuccess) return set_cuda_error(e, "D2H output");
+    }
+    e = cudaEventRecord(hp.drained, hp.d2h);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, hp.drained, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return set_cuda_error(e, "stream synchronize");
     return MIXQ_OK;
 }
 
-}  // extern "C"

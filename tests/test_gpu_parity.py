@@ -314,6 +314,30 @@ def test_enqueue_is_graph_capturable_and_async(B, oracle):
     _assert_mixed_close(out.cpu().numpy(), r["out"], r["out0"], "graph replay")
 
 
+@pytest.mark.parametrize("M", [7, 2048, 5000])
+def test_linear_host_pipeline(B, lib, oracle, M):
+    """mixq_linear_host (host buffers in, host buffers out; row slabs pipelined over three streams) must return
+    exactly what mixq_enqueue writes for the same activations."""
+    N, K = 264, 400
+    lin = _packed(oracle, "synthetic", N, K)
+    A = oracle.synth_activations(M, lin["act_scale"], seed=M)
+    tW, tsb, tfw, tind = _t(lin["W8"]), _t(lin["scale_b"]), _t(lin["fp_weight"]), _t(lin["ind"])
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    ws = torch.empty(B.workspace_size(M, N, K), dtype=torch.uint8, device=DEV)
+    B.enqueue(_t(A), tW, tsb, tfw, tind, out, ws)
+    hA = torch.from_numpy(A).pin_memory()
+    hO = torch.full((M, N), float("nan"), dtype=torch.float16).pin_memory()
+    scratch = torch.empty(lib.mixq_host_scratch_size(M, N, K), dtype=torch.uint8, device=DEV)
+    t = B.make_tensors(None, tW, tsb, tfw, tind, None)
+    for _ in range(2):       # second call reuses the pipe's streams/events
+        hO.fill_(float("nan"))
+        B.check(lib.mixq_linear_host(ctypes.byref(t), hA.data_ptr(), hO.data_ptr(), M, N, K, scratch.data_ptr(),
+                                     scratch.numel(), 0, torch.cuda.current_stream().cuda_stream), "mixq_linear_host")
+        assert torch.equal(hO.view(torch.int16), out.cpu().view(torch.int16))
+    small = torch.empty(1024, dtype=torch.uint8, device=DEV)
+    assert lib.mixq_linear_host(ctypes.byref(t), hA.data_ptr(), hO.data_ptr(), M, N, K, small.data_ptr(), 1024, 0, None) == -2
+
+
 def test_python_plugin_mirror(B, oracle):
     """MixQLinear / mixgemm (reference plugin.py) end to end, 3-D activations, bias outside the plugin."""
     from mixq_tensorrt_llm_b200.plugin import MixQLinear
