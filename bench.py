@@ -222,6 +222,9 @@ def run_ours(args, M, linears):
     stream = torch.cuda.current_stream()
 
     chunks = args.tp_chunks if (tp > 1 and M >= 4096 * args.tp_chunks) else 1
+    if tp > 1 and chunks > 1 and args.comm_sms > 0:
+        # the GEMM is persistent (one CTA per SM): keep a few SMs free so NCCL's kernels can run beside it
+        lib.mixq_set_sm_limit(torch.cuda.get_device_properties(dev).multi_processor_count - args.comm_sms)
 
     def step():
         for name, mod, Ns, Ks, mode in mods:
@@ -436,6 +439,7 @@ def run_ours(args, M, linears):
                 "scaling": "strong", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
                 "config": {"workload": args.workload, "tokens_per_step": M,
                            "linears": [[n, N, K, m] for n, N, K, m in linears],
+                           "comm_sms": args.comm_sms if (tp > 1 and chunks > 1) else 0,
                            "launch": "cuda-graph replay of the step" if use_graph else "direct launches",
                            "parallelism": (f"tp{tp} (column: no collective; row: one NCCL all-reduce in {chunks} overlapped row slabs)"
                                            if tp > 1 else "single"),
@@ -459,6 +463,7 @@ def main():
     ap.add_argument("--cpu-sample-tokens", type=int, default=512)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--tp-chunks", type=int, default=4, help="row slabs per row-parallel linear (comm/compute overlap)")
+    ap.add_argument("--comm-sms", type=int, default=16, help="SMs left free for NCCL when slabs overlap (tensor parallel only)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto: decode-sized M on one GPU)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -149,6 +149,11 @@ uint64_t mixq_launch_count(void);
  * epilogue done); NULL (default) disables it. */
 int mixq_debug_set_trace(void* dev_buf);
 
+/* Cap the number of SMs the persistent kernels occupy (0 = all).  Leaving a few SMs free lets a
+ * communication kernel (the NCCL all-reduce of a row-parallel linear) run concurrently with the GEMM of the
+ * next row slab instead of queueing behind it.  Returns the previous value. */
+int mixq_set_sm_limit(int num_sms);
+
 /* GEMM tile configuration override for tuning/tests: 0 = auto. Returns the
  * previous value. Valid ids are listed in DESIGN.md. */
 int mixq_set_gemm_config(int config_id);

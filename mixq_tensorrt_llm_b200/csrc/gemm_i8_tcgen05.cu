@@ -1269,7 +1269,7 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     const int n_tiles = static_cast<int>((N + T::kBlockN - 1) / T::kBlockN);
     const int64_t num_tiles = static_cast<int64_t>(m_tiles) * n_tiles;
     if (num_tiles > (1ll << 30)) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: too many tiles");
-    const int64_t max_groups = dev.num_sms / T::kCta;
+    const int64_t max_groups = usable_sms() / T::kCta;
     int grid = static_cast<int>(num_tiles < max_groups ? num_tiles : max_groups) * T::kCta;
     if (IsStreamK<T>::value && sk_ws && stream_k) {
         // one equal span of (tile, K-block) units per CTA group; never more groups than units
@@ -1373,7 +1373,7 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
         for (const Cand& c : cands) {
             if (M <= 128 && c.cta == 2) continue;
             const int64_t tiles = ((M + c.tile_m - 1) / c.tile_m) * ((N + c.tile_n - 1) / c.tile_n);
-            const int64_t workers = dev.num_sms / c.cta;
+            const int64_t workers = usable_sms() / c.cta;
             const int64_t est = ((tiles + workers - 1) / workers) * c.kb_cycles * nkb + c.tail_cycles;
             if (est < best) {
                 best = est;

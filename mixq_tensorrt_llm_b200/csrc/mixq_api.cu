@@ -14,6 +14,7 @@ namespace {
 thread_local char g_err[256] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_gemm_cfg{0};
+std::atomic<int> g_sm_limit{0};
 
 constexpr size_t kAlign = 128;  // kCudaMemAlign, TsinghuaMixQPlugin.cpp:204
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
@@ -43,6 +44,10 @@ int set_cuda_error(cudaError_t e, const char* what) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int current_gemm_config() { return g_gemm_cfg.load(std::memory_order_relaxed); }
+int usable_sms() {
+    const int n = device_info().num_sms, lim = g_sm_limit.load(std::memory_order_relaxed);
+    return (lim > 0 && lim < n) ? lim : n;
+}
 
 const DeviceInfo& device_info() {
     static DeviceInfo info;
@@ -78,6 +83,11 @@ const char* mixq_version(void) { return "mixq-b200 0.1.0 (sm_100a; tcgen05 W8A8O
 const char* mixq_last_error(void) { return g_err; }
 int mixq_device_ok(void) { return device_info().ok ? 1 : 0; }
 uint64_t mixq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int mixq_set_sm_limit(int num_sms) {
+    if (num_sms < 0) return -1;
+    return g_sm_limit.exchange(num_sms);
+}
 
 int mixq_set_gemm_config(int config_id) {
     if (config_id < 0 || config_id >= kCfgCount) return -1;

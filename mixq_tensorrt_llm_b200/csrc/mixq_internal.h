@@ -43,5 +43,7 @@ int set_trace_buffer(void* dev_buf);
 // GEMM tile configuration ids (mixq_set_gemm_config); 0 = pick automatically.
 enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfg2CtaN256Tma = 9, kCfg2CtaN192Tma = 10, kCfgCount };
 int current_gemm_config();
+// SMs the persistent kernels may occupy (mixq_set_sm_limit; default: all)
+int usable_sms();
 
 }  // namespace mixq

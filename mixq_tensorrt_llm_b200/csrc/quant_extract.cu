@@ -274,7 +274,7 @@ int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, i
     // resident CTAs per SM: limited by threads (2048/256 = 8) and by shared memory
     int per_sm = static_cast<int>(dev.smem_per_sm / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
-    int64_t grid = static_cast<int64_t>(dev.num_sms) * per_sm;
+    int64_t grid = static_cast<int64_t>(usable_sms()) * per_sm;
     if (grid > M) grid = M;
 
     cudaLaunchConfig_t cfg{};
