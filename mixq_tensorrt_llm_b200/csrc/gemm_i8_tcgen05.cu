@@ -47,7 +47,7 @@ constexpr int kEpilogueWarp0 = 4;
 constexpr int kNumEpilogueThreads = 128;
 constexpr int kOutlierKBlocks = (MIXQ_NUM_OUTLIERS * 2) / kBlockKBytes;  // 2
 constexpr size_t kStreamKFlagBytes = 4096;                                 // stream-K: one flag per (worker, CTA rank)
-constexpr size_t kStreamKSlotBytes = 2 * 128 * 256 * 4;                    // int32 partial tile of one CTA pair
+constexpr size_t kStreamKSlotBytes = 2 * (128 * 256 * 4 + 128 * 256 * 2);  // int32 partial tile + fp16 outlier product of one CTA pair
 constexpr int kStreamKMaxWorkers = 80;                                     // CTA pairs (148 SMs -> 74)
 constexpr int kStashEpiThreads = 256;                                      // wide-tile kernel: 8 epilogue warps
 constexpr int kStashThreads = kEpilogueWarp0 * 32 + kStashEpiThreads;      // 384
@@ -820,12 +820,15 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                 }
             };
             trace_stamp(2);
+            int s = 0;
             while (seg.next(tile, kb0, kb1)) {
                 const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, group_m);
                 const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
                 const int n0 = tc.n_blk * BLOCK_N + static_cast<int>(cta_rank) * T::kLoadN;
-                const int n_f = (has_outlier && kb0 == 0) ? kOutlierKBlocks : 0;
-                const int split = kb0 + (kb1 - kb0) / 2;
+                // the outlier K-blocks belong to the segment that holds the LAST K-block of the tile; they come
+                // first in a worker's first segment (both accumulator buffers are free) and mid-way otherwise
+                const int n_f = (has_outlier && kb1 == num_kb) ? kOutlierKBlocks : 0;
+                const int split = (s++ == 0) ? kb0 : kb0 + (kb1 - kb0) / 2;
                 for (int kb = kb0; kb < split; ++kb) load_block(&tm_a8, &tm_w8, kb * kBlockKBytes, m0, n0);
                 for (int it = 0; it < n_f; ++it) load_block(&tm_fa, &tm_fw, it * (kBlockKBytes / 2), m0, n0);
                 for (int kb = split; kb < kb1; ++kb) load_block(&tm_a8, &tm_w8, kb * kBlockKBytes, m0, n0);
@@ -876,7 +879,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
             int s = 0;
             while (seg.next(tile, kb0, kb1)) {
                 const int b = s & 1;
-                const bool has_f = has_outlier && kb0 == 0;
+                const bool has_f = has_outlier && kb1 == num_kb;
                 const uint32_t tmem_i = tmem_base + b * BLOCK_N;
                 const uint32_t tmem_f = tmem_base + (b ^ 1) * BLOCK_N;
                 // buffer b must be free: its previous int32 tenant read by the epilogue, a parked outlier
@@ -887,7 +890,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                     f_pending[b] = false;
                 }
                 ptx::tc_fence_after_sync();
-                const int split = kb0 + (kb1 - kb0) / 2;
+                const int split = (s == 0) ? kb0 : kb0 + (kb1 - kb0) / 2;
                 for (int kb = kb0; kb < split; ++kb) issue_block(std::integral_constant<int, 1>{}, tmem_i, kb == kb0);
                 if (has_f) {
                     if (n_int[b ^ 1] > 0) ptx::mbar_wait(&tmem_empty_bar[b ^ 1], (n_int[b ^ 1] - 1) & 1);
@@ -935,14 +938,16 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
             }
         };
         // slot of worker w, CTA rank r: 32 vectors x 256 threads x 16 B = 128 KB, thread-major (coalesced)
-        auto slot_of = [&](int w) { return sk_slots + (static_cast<size_t>(w) * CTA + cta_rank) * (32 * kStashEpiThreads) + et; };  // 32 >= kCols / 4
+        auto slot_of = [&](int w) { return sk_slots + (static_cast<size_t>(w) * CTA + cta_rank) * (48 * kStashEpiThreads) + et; };  // 32 >= kCols / 4
+        // ... followed by 16 vectors x 256 threads x 16 B = 64 KB for the fp16 outlier product of a tail segment
+        auto fslot_of = [&](int w) { return slot_of(w) + 32 * kStashEpiThreads; };
         auto flag_of = [&](int w) { return sk_flags + static_cast<size_t>(w) * CTA + cta_rank; };
         uint32_t n_int[2] = {0, 0}, n_f[2] = {0, 0};
         int s = 0;
         while (seg.next(tile, kb0, kb1)) {
             const int b = s & 1;
             const bool finisher = kb0 == 0;
-            const bool has_f = has_outlier && finisher;
+            const bool has_f = has_outlier && kb1 == num_kb;   // this segment computed the outlier product
             const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, group_m);
             const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
             const int n0 = tc.n_blk * BLOCK_N;
@@ -978,7 +983,8 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                             const __half2 o = __floats2half2_rn(__uint_as_float(va[v * 8 + q * 2]), __uint_as_float(va[v * 8 + q * 2 + 1]));
                             h[q] = *reinterpret_cast<const uint32_t*>(&o);
                         }
-                        *vec_ptr(c, v) = make_uint4(h[0], h[1], h[2], h[3]);
+                        if (finisher) *vec_ptr(c, v) = make_uint4(h[0], h[1], h[2], h[3]);
+                        else fslot_of(group_id)[(c * 4 + v) * kStashEpiThreads] = make_uint4(h[0], h[1], h[2], h[3]);  // ship it
                     }
                 }
                 arrive(&f_drained_bar[b ^ 1]);
@@ -1063,7 +1069,8 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                     for (int g = 0; g < 4; ++g) {
                         uint4* tp = vec_ptr(c, g);
                         uint4 f = make_uint4(0u, 0u, 0u, 0u);
-                        if (has_f) f = *tp;
+                        if (has_f) f = *tp;                                            // own outlier product (stash)
+                        else if (has_outlier) f = __ldcg(fslot_of(group_id + n_peers) + (c * 4 + g) * kStashEpiThreads);  // the tail segment's
                         const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
                         const float4 s0 = sb4[c * 8 + g * 2], s1 = sb4[c * 8 + g * 2 + 1];
                         const float sbv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
