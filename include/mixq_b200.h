@@ -129,6 +129,35 @@ int mixq_gemm_dequant_ws(const void* A8, const void* W8, const void* scale_a, co
                          const void* fp_A, const void* fp_weight, void* Out, int64_t M, int64_t N,
                          int64_t K, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- row-parallel linear with the all-reduce fused into the GEMM kernel ----
+ * Replaces "plugin, then allreduce(x, tp_group)" (reference plugin.py:152-156) for the row-parallel shards of a
+ * tensor-parallel layer by ONE kernel per rank: every rank's epilogue pushes its fp16 partial tiles straight into
+ * the staging area of the rank that owns the tile (peer memory over NVLink), owners sum the `world` partials in
+ * fp32 in rank order (deterministic; one rounding to fp16) and write the result into every rank's Out.  When the
+ * call's kernel completes on a rank, that rank's Out holds the reduced [M,N] result.
+ *
+ * All ranks must issue the same sequence of fused calls with the same (M, N).  The pointers are addresses valid in
+ * THIS process for every rank's buffers (CUDA IPC / cuMem fabric handles / torch symmetric memory: whatever the host
+ * uses to map peer memory); index `rank` is the local buffer.  `counters` must be zeroed once after allocation and is
+ * re-armed by the kernel itself.  Buffers are M/N dependent only through the two size functions. */
+#define MIXQ_MAX_RANKS 8
+typedef struct mixq_peer_group {
+    int world, rank;
+    void* out[MIXQ_MAX_RANKS];      /* every rank's Out [M,N] fp16                                        */
+    void* staging[MIXQ_MAX_RANKS];  /* every rank's staging area, >= mixq_allreduce_staging_size() bytes  */
+    void* counters[MIXQ_MAX_RANKS]; /* every rank's counter block, >= mixq_allreduce_counter_size() bytes */
+    size_t staging_bytes, counter_bytes;
+} mixq_peer_group;
+size_t mixq_allreduce_staging_size(int64_t M, int64_t N, int world);
+size_t mixq_allreduce_counter_size(int64_t M, int64_t N, int world);
+/* mixq_enqueue with the reduction fused in: t->Out is ignored, the result lands in g->out[i] on every rank i. */
+int mixq_enqueue_allreduce(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace,
+                           size_t workspace_bytes, const mixq_peer_group* g, unsigned flags, void* stream);
+/* Stage 2 alone with the reduction fused in (tests, callers that share one quantised A). */
+int mixq_gemm_dequant_allreduce(const void* A8, const void* W8, const void* scale_a, const void* scale_b,
+                                const void* fp_A, const void* fp_weight, int64_t M, int64_t N, int64_t K,
+                                const mixq_peer_group* g, void* stream);
+
 /* End-to-end call with HOST buffers for the per-call tensors: copies A (host,
  * fp16 [M,K]) to the device, runs mixq_enqueue with the device-resident weights
  * in `t` (t->A and t->Out are ignored), copies Out back to `Out_host`

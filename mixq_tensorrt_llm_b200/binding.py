@@ -21,6 +21,7 @@ EXPORTS = [
     "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_enqueue",
     "mixq_quant_extract", "mixq_rmsnorm_quant_extract", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
     "mixq_host_scratch_size", "mixq_linear_host",
+    "mixq_allreduce_staging_size", "mixq_allreduce_counter_size", "mixq_enqueue_allreduce", "mixq_gemm_dequant_allreduce",
     "mixq_launch_count", "mixq_set_gemm_config", "mixq_set_sm_limit", "mixq_debug_set_trace", "initOpenAiTritonPlugins", "mixq_plugin_create",
     "mixq_plugin_deserialize", "mixq_plugin_clone", "mixq_plugin_destroy", "mixq_plugin_type",
     "mixq_plugin_version", "mixq_plugin_namespace", "mixq_plugin_nb_outputs",
@@ -37,6 +38,17 @@ class Tensors(ctypes.Structure):
     """struct mixq_tensors"""
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("A", "W8", "scale_b", "fp_weight", "ind", "q_weight", "scaling_factors", "Out")]
+
+
+MAX_RANKS = 8
+
+
+class PeerGroup(ctypes.Structure):
+    """struct mixq_peer_group"""
+    _fields_ = [("world", ctypes.c_int), ("rank", ctypes.c_int),
+                ("out", ctypes.c_void_p * MAX_RANKS), ("staging", ctypes.c_void_p * MAX_RANKS),
+                ("counters", ctypes.c_void_p * MAX_RANKS),
+                ("staging_bytes", ctypes.c_size_t), ("counter_bytes", ctypes.c_size_t)]
 
 
 _lib = None
@@ -73,6 +85,14 @@ def load() -> ctypes.CDLL:
     L.mixq_host_scratch_size.argtypes = [i64, i64, i64]
     L.mixq_linear_host.restype = ci
     L.mixq_linear_host.argtypes = [ctypes.POINTER(Tensors), vp, vp, i64, i64, i64, vp, sz, u32, vp]
+    L.mixq_allreduce_staging_size.restype = sz
+    L.mixq_allreduce_staging_size.argtypes = [i64, i64, ci]
+    L.mixq_allreduce_counter_size.restype = sz
+    L.mixq_allreduce_counter_size.argtypes = [i64, i64, ci]
+    L.mixq_enqueue_allreduce.restype = ci
+    L.mixq_enqueue_allreduce.argtypes = [ctypes.POINTER(Tensors), i64, i64, i64, vp, sz, ctypes.POINTER(PeerGroup), u32, vp]
+    L.mixq_gemm_dequant_allreduce.restype = ci
+    L.mixq_gemm_dequant_allreduce.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, ctypes.POINTER(PeerGroup), vp]
     L.mixq_launch_count.restype = ctypes.c_uint64
     L.mixq_debug_set_trace.restype = ci
     L.mixq_debug_set_trace.argtypes = [vp]
@@ -180,3 +200,29 @@ def gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, stream=None, wo
                                           _ptr(fp_weight), _ptr(Out), M, N, K, _ptr(workspace),
                                           workspace.numel() * workspace.element_size(), _stream(stream)),
               "mixq_gemm_dequant_ws")
+
+
+def make_peer_group(world: int, rank: int, out_ptrs, staging_ptrs, counter_ptrs, staging_bytes: int, counter_bytes: int) -> PeerGroup:
+    """struct mixq_peer_group from raw addresses (ints) of every rank's Out / staging / counter buffers."""
+    g = PeerGroup()
+    g.world, g.rank = world, rank
+    for i in range(world):
+        g.out[i], g.staging[i], g.counters[i] = out_ptrs[i], staging_ptrs[i], counter_ptrs[i]
+    g.staging_bytes, g.counter_bytes = staging_bytes, counter_bytes
+    return g
+
+
+def enqueue_allreduce(A, W8, scale_b, fp_weight, ind, workspace, group: PeerGroup, flags: int = 0, stream=None) -> None:
+    """mixq_enqueue_allreduce: the reduced [M,N] result lands in group.out[i] on every rank i."""
+    M, K = A.shape
+    N = W8.shape[0]
+    t = make_tensors(A, W8, scale_b, fp_weight, ind, None)
+    check(load().mixq_enqueue_allreduce(ctypes.byref(t), M, N, K, _ptr(workspace), workspace.numel() * workspace.element_size(),
+                                        ctypes.byref(group), flags, _stream(stream)), "mixq_enqueue_allreduce")
+
+
+def gemm_dequant_allreduce(A8, W8, scale_a, scale_b, fp_A, fp_weight, group: PeerGroup, stream=None) -> None:
+    M, K = A8.shape
+    N = W8.shape[0]
+    check(load().mixq_gemm_dequant_allreduce(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A), _ptr(fp_weight),
+                                             M, N, K, ctypes.byref(group), _stream(stream)), "mixq_gemm_dequant_allreduce")

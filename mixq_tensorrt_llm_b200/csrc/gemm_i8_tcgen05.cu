@@ -720,7 +720,44 @@ __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <class T>
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// publish everything this thread has observed/written (cumulativity) and bump a counter that may live on a peer GPU
+__device__ __forceinline__ void signal_add_sys(uint32_t* p, uint32_t v) {
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- fused all-reduce of a row-parallel linear -------------------------------------------------
+// Every rank computes the fp16 partial of every output tile; tile t is OWNED by rank t % world.
+//   phase A (GEMM epilogue):  the partial tile leaves shared memory through one TMA store per 32x32 chunk straight
+//                             into the OWNER's staging area (peer memory over NVLink; tm_stage[owner] describes the
+//                             region reserved for THIS rank's partials), then each epilogue warp bumps the owner's
+//                             arrival counter of its 32-row group (release, system scope).
+//   phase B (same kernel):    the 32-row groups of the tiles this rank owns are spread over all CTAs; a group is
+//                             reduced as soon as 2 * world arrivals are in: fp32 sum in rank order 0..world-1 (so the
+//                             result is deterministic and identical on every rank), one rounding to fp16, and the
+//                             finished rows are written into EVERY rank's Out (peer stores), followed by a release
+//                             bump of every rank's `done` counter.
+//   exit:                     CTA 0 leaves only when its own `done` counter shows every row group of every tile,
+//                             i.e. when this rank's Out is complete; counters are re-armed to 0 by their waiter.
+// Counter block of a rank: word 0 = done, words [32, 32 + 8 * slots) = arrivals per (owned slot, 32-row group).
+constexpr int kArCounterBase = 32;
+struct alignas(64) ArParams {
+    CUtensorMap tm_stage[MIXQ_MAX_RANKS];   // staging region for this rank's partials on rank i: [slots * 256, BLOCK_N] fp16
+    __half* out[MIXQ_MAX_RANKS];            // every rank's Out [M, N]
+    uint32_t* counters[MIXQ_MAX_RANKS];     // every rank's counter block
+    const __half* stage_local;              // this rank's whole staging area: [world][slots][256][BLOCK_N] fp16
+    int world, rank, slots;
+};
+struct ArNone {
+    int unused;
+};
+
+template <class T, bool AR>
 __global__ void __launch_bounds__(kStashThreads, 1)
 mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_w8,
                                  const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fw,
@@ -728,7 +765,8 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                                  const __half* __restrict__ scale_a, const __half* __restrict__ scale_b,
                                  __half* __restrict__ Out, int M, int N, int K, int has_outlier, int m_tiles,
                                  int n_tiles, int group_m, int stream_k, uint4* __restrict__ sk_slots,
-                                 uint32_t* __restrict__ sk_flags) {
+                                 uint32_t* __restrict__ sk_flags,
+                                 const __grid_constant__ std::conditional_t<AR, ArParams, ArNone> ar) {
     constexpr int BLOCK_N = T::kBlockN;
     constexpr int CTA = T::kCta;
     extern __shared__ uint8_t smem_raw[];
@@ -943,6 +981,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
         auto fslot_of = [&](int w) { return slot_of(w) + 32 * kStashEpiThreads; };
         auto flag_of = [&](int w) { return sk_flags + static_cast<size_t>(w) * CTA + cta_rank; };
         uint32_t n_int[2] = {0, 0}, n_f[2] = {0, 0};
+        uint32_t* ar_pending = nullptr;   // AR: arrival counter (on the owner) of the tile whose stores are in flight
         int s = 0;
         while (seg.next(tile, kb0, kb1)) {
             const int b = s & 1;
@@ -958,7 +997,21 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                 if (et < BLOCK_N) sbt[et] = (n0 + et < N) ? __half2float(scale_b[n0 + et]) : 0.0f;
                 sa_f = gm < M ? __half2float(scale_a[gm]) : 0.0f;
                 // the previous tile's TMA stores must have finished READING this warp's tiles
-                if (lane == 0) ptx::tma_store_wait_read<0>();
+                if (lane == 0) {
+                    if constexpr (AR) {
+                        // ... and, fused all-reduce, have LANDED in the owner's staging area: announce them
+                        ptx::tma_store_wait_all<0>();
+                        if (ar_pending) signal_add_sys(ar_pending, 1u);
+                    } else {
+                        ptx::tma_store_wait_read<0>();
+                    }
+                }
+            }
+            int ar_owner = 0, ar_slot = 0;
+            if constexpr (AR) {
+                ar_owner = tile % ar.world;
+                ar_slot = tile / ar.world;
+                ar_pending = ar.counters[ar_owner] + kArCounterBase + ar_slot * 8 + static_cast<int>(cta_rank) * 4 + quarter;
             }
             ptx::named_bar_sync(1, kStashEpiThreads);
 
@@ -1092,7 +1145,11 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        ptx::tma_store_2d(&tm_out, warp_tiles + c * 2048, n0 + col0 + c * 32, m0 + quarter * 32);
+                        if constexpr (AR)   // the partial goes to the tile owner's staging area (peer memory)
+                            ptx::tma_store_2d(&ar.tm_stage[ar_owner], warp_tiles + c * 2048, col0 + c * 32,
+                                              ar_slot * T::kTileM + static_cast<int>(cta_rank) * kBlockM + quarter * 32);
+                        else
+                            ptx::tma_store_2d(&tm_out, warp_tiles + c * 2048, n0 + col0 + c * 32, m0 + quarter * 32);
                         ptx::tma_store_commit();
                     }
                 }
@@ -1110,6 +1167,82 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
         if (et == 0) trace_stamp(10);
         if (lane == 0) ptx::tma_store_wait_all<0>();  // outstanding output tiles fully written before the CTA retires
         if (et == 0) trace_stamp(11);
+
+        if constexpr (AR) {
+            // ===================== phase B: reduce the row groups this rank owns, broadcast the result ===========
+            if (lane == 0 && ar_pending) signal_add_sys(ar_pending, 1u);
+            const int world = ar.world;
+            const int owned = num_tiles > ar.rank ? (num_tiles - ar.rank + world - 1) / world : 0;
+            const int units = owned * 8;                       // (owned slot, 32-row group)
+            uint32_t* my_cnt = ar.counters[ar.rank];
+            const size_t region = static_cast<size_t>(ar.slots) * T::kTileM * BLOCK_N;   // elements per source rank
+            const int colv = lane * 8;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int j = u >> 3, rg = u & 7;
+                const TileCoord tc = tile_coord(ar.rank + j * world, m_tiles, n_tiles, group_m);
+                const int n0 = tc.n_blk * BLOCK_N;
+                if (et == 0) {
+                    uint32_t* c = my_cnt + kArCounterBase + u;
+                    uint32_t spins = 0;
+                    while (ld_acquire_sys(c) < 2u * static_cast<uint32_t>(world)) {
+                        if (++spins > (1u << 24)) __trap();
+                    }
+                    *c = 0u;   // re-arm: the next arrivals can only come from the next launch
+                }
+                ptx::named_bar_sync(2, kStashEpiThreads);
+                const bool col_ok = colv < BLOCK_N && n0 + colv < N;
+#pragma unroll 1
+                for (int i = 0; i < 4; i += 2) {
+                    const int r = rg * 32 + ew * 4 + i;
+                    const int gm = tc.m_blk * T::kTileM + r;
+                    const __half* src = ar.stage_local + (static_cast<size_t>(j) * T::kTileM + r) * BLOCK_N + colv;
+                    uint4 v[2][MIXQ_MAX_RANKS];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int sr = 0; sr < MIXQ_MAX_RANKS; ++sr)
+                            if (sr < world && col_ok && gm + q < M)
+                                v[q][sr] = __ldcg(reinterpret_cast<const uint4*>(src + sr * region + static_cast<size_t>(q) * BLOCK_N));
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (!(col_ok && gm + q < M)) continue;
+                        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int sr = 0; sr < MIXQ_MAX_RANKS; ++sr) {
+                            if (sr < world) {
+                                const uint32_t w[4] = {v[q][sr].x, v[q][sr].y, v[q][sr].z, v[q][sr].w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                                    acc[2 * e] = sr == 0 ? f.x : acc[2 * e] + f.x;       // rank order; world = 1 is the identity
+                                    acc[2 * e + 1] = sr == 0 ? f.y : acc[2 * e + 1] + f.y;
+                                }
+                            }
+                        }
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __half2 h = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
+                            pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        const size_t off = static_cast<size_t>(gm + q) * N + n0 + colv;
+                        for (int pr = 0; pr < world; ++pr) ptx::st_global_v4(ar.out[pr] + off, pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                ptx::named_bar_sync(2, kStashEpiThreads);
+                if (et == 0)
+                    for (int pr = 0; pr < world; ++pr) signal_add_sys(ar.counters[pr], 1u);   // one more row group of Out complete
+            }
+            if (blockIdx.x == 0 && et == 0) {
+                // this rank's Out is complete when every row group of every tile has been delivered
+                const uint32_t expect = static_cast<uint32_t>(num_tiles) * 8u;
+                uint32_t spins = 0;
+                while (ld_acquire_sys(my_cnt) < expect) {
+                    if (++spins > (1u << 24)) __trap();
+                }
+                *my_cnt = 0u;
+            }
+        }
     }
 
     if (threadIdx.x == kEpilogueWarp0 * 32) trace_stamp(7);
@@ -1238,7 +1371,8 @@ struct StreamKTraits : StashTraits<CTA, STAGES, BLOCK_N> {};
 template <int CTA, int STAGES, int BLOCK_N>
 struct KernelOf<StreamKTraits<CTA, STAGES, BLOCK_N>> {
     static constexpr int kThreads = kStashThreads;
-    static auto get() { return mixq_gemm_dequant_streamk_kernel<StashTraits<CTA, STAGES, BLOCK_N>>; }
+    static auto get() { return mixq_gemm_dequant_streamk_kernel<StashTraits<CTA, STAGES, BLOCK_N>, false>; }
+    static auto get_ar() { return mixq_gemm_dequant_streamk_kernel<StashTraits<CTA, STAGES, BLOCK_N>, true>; }
 };
 template <class T>
 struct IsStreamK : std::false_type {};
@@ -1248,7 +1382,7 @@ struct IsStreamK<StreamKTraits<CTA, STAGES, BLOCK_N>> : std::true_type {};
 template <class T>
 int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl,
-               void* sk_ws = nullptr, int stream_k = 0) {
+               void* sk_ws = nullptr, int stream_k = 0, const mixq_peer_group* pg = nullptr) {
     const DeviceInfo& dev = device_info();
     CUtensorMap tm_a8, tm_w8, tm_fa, tm_fw;
     int rc;
@@ -1313,6 +1447,44 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     cfg.attrs = attr;
     cfg.numAttrs = na;
     if constexpr (IsStreamK<T>::value) {
+        if (pg) {
+            // fused all-reduce: the epilogue stores partial tiles into the owners' staging areas (see ArParams)
+            ArParams ar{};
+            ar.world = pg->world;
+            ar.rank = pg->rank;
+            ar.slots = static_cast<int>((num_tiles + pg->world - 1) / pg->world);
+            const size_t region = static_cast<size_t>(ar.slots) * T::kTileM * T::kBlockN * 2;   // bytes per source rank
+            if (region * pg->world > pg->staging_bytes)
+                return set_error(MIXQ_ERR_WORKSPACE, "gemm_dequant_allreduce: staging area too small (mixq_allreduce_staging_size)");
+            if ((kArCounterBase + static_cast<size_t>(ar.slots) * 8) * 4 > pg->counter_bytes)
+                return set_error(MIXQ_ERR_WORKSPACE, "gemm_dequant_allreduce: counter block too small (mixq_allreduce_counter_size)");
+            for (int i = 0; i < pg->world; ++i) {
+                if (!pg->out[i] || !pg->staging[i] || !pg->counters[i])
+                    return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_allreduce: null peer pointer");
+                ar.out[i] = static_cast<__half*>(pg->out[i]);
+                ar.counters[i] = static_cast<uint32_t*>(pg->counters[i]);
+                const uint8_t* base = static_cast<const uint8_t*>(pg->staging[i]) + region * pg->rank;
+                if ((rc = make_tmap(&ar.tm_stage[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base,
+                                    static_cast<uint64_t>(ar.slots) * T::kTileM, T::kBlockN, 32, 64)))
+                    return rc;
+            }
+            ar.stage_local = static_cast<const __half*>(pg->staging[pg->rank]);
+            auto kern_ar = KernelOf<T>::get_ar();
+            static std::atomic<int> ar_attr_set_for_device{-1};
+            if (ar_attr_set_for_device.load(std::memory_order_acquire) != dev.device) {
+                e = cudaFuncSetAttribute(kern_ar, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::kSmemBytes));
+                if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_dequant_allreduce)");
+                ar_attr_set_for_device.store(dev.device, std::memory_order_release);
+            }
+            e = cudaLaunchKernelEx(&cfg, kern_ar, tm_a8, tm_w8, tm_fa, tm_fw, tm_a8 /* tm_out unused */,
+                                   static_cast<const __half*>(scale_a), static_cast<const __half*>(scale_b),
+                                   static_cast<__half*>(Out), static_cast<int>(M), static_cast<int>(N),
+                                   static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m, 0,
+                                   static_cast<uint4*>(nullptr), static_cast<uint32_t*>(nullptr), ar);
+            if (e != cudaSuccess) return set_cuda_error(e, "launch gemm_dequant_allreduce");
+            count_launch();
+            return MIXQ_OK;
+        }
         CUtensorMap tm_out;
         if ((rc = make_tmap(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Out, M, N, 32, 64))) return rc;
         uint32_t* flags = static_cast<uint32_t*>(sk_ws);
@@ -1321,7 +1493,7 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
         e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, tm_out, static_cast<const __half*>(scale_a),
                                static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M),
                                static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m,
-                               (sk_ws && stream_k) ? 1 : 0, slots, flags);
+                               (sk_ws && stream_k) ? 1 : 0, slots, flags, ArNone{0});
     } else {
         e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, static_cast<const __half*>(scale_a),
                                static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M),
@@ -1418,6 +1590,48 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
         default:
             return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: unknown config id");
     }
+}
+
+
+size_t allreduce_staging_bytes(int64_t M, int64_t N, int world) {
+    if (M <= 0 || N <= 0 || world <= 0) return 0;
+    using T = StreamKTraits<2, 4>;
+    const int64_t tiles = ((M + T::kTileM - 1) / T::kTileM) * ((N + T::kBlockN - 1) / T::kBlockN);
+    const int64_t slots = (tiles + world - 1) / world;
+    return static_cast<size_t>(slots) * world * T::kTileM * T::kBlockN * 2;
+}
+size_t allreduce_counter_bytes(int64_t M, int64_t N, int world) {
+    if (M <= 0 || N <= 0 || world <= 0) return 0;
+    using T = StreamKTraits<2, 4>;
+    const int64_t tiles = ((M + T::kTileM - 1) / T::kTileM) * ((N + T::kBlockN - 1) / T::kBlockN);
+    const int64_t slots = (tiles + world - 1) / world;
+    return (kArCounterBase + static_cast<size_t>(slots) * 8) * 4;
+}
+
+int launch_gemm_dequant_allreduce(const void* A8, const void* W8, const void* scale_a, const void* scale_b,
+                                  const void* fp_A, const void* fp_weight, int64_t M, int64_t N, int64_t K,
+                                  const mixq_peer_group* pg, cudaStream_t stream, bool pdl) {
+    if (!pg) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_allreduce: null peer group");
+    if (pg->world < 1 || pg->world > MIXQ_MAX_RANKS || pg->rank < 0 || pg->rank >= pg->world)
+        return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_allreduce: bad world/rank");
+    if (M == 0 || N == 0) return MIXQ_OK;
+    if (!A8 || !W8 || !scale_a || !scale_b) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_allreduce: null pointer");
+    if ((fp_A == nullptr) != (fp_weight == nullptr))
+        return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_allreduce: fp_A and fp_weight must both be given or both be null");
+    if (M < 0 || N < 0 || K <= 0 || M > INT32_MAX || N > INT32_MAX || K > INT32_MAX)
+        return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_allreduce: bad dimensions");
+    if ((K & 15) != 0 || (N & 7) != 0)
+        return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant_allreduce: K must be a multiple of 16 and N of 8");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(A8) | reinterpret_cast<uintptr_t>(W8) | reinterpret_cast<uintptr_t>(fp_A) |
+                         reinterpret_cast<uintptr_t>(fp_weight);
+    if (al & 15) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_allreduce: tensors must be 16-byte aligned");
+    for (int i = 0; i < pg->world; ++i)
+        if ((reinterpret_cast<uintptr_t>(pg->out[i]) | reinterpret_cast<uintptr_t>(pg->staging[i]) |
+             reinterpret_cast<uintptr_t>(pg->counters[i])) & 15)
+            return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_allreduce: peer buffers must be 16-byte aligned");
+    if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
+    return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, pg->out[pg->rank], M, N, K, stream, pdl,
+                                           nullptr, 0, pg);
 }
 
 }  // namespace mixq

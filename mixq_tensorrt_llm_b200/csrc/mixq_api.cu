@@ -157,6 +157,36 @@ int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* w
                                streamk_workspace_bytes(), /*sk_flags_clean=*/true);
 }
 
+size_t mixq_allreduce_staging_size(int64_t M, int64_t N, int world) { return allreduce_staging_bytes(M, N, world); }
+size_t mixq_allreduce_counter_size(int64_t M, int64_t N, int world) { return allreduce_counter_bytes(M, N, world); }
+
+int mixq_gemm_dequant_allreduce(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
+                                const void* fp_weight, int64_t M, int64_t N, int64_t K, const mixq_peer_group* g, void* stream) {
+    return launch_gemm_dequant_allreduce(A8, W8, scale_a, scale_b, fp_A, fp_weight, M, N, K, g,
+                                         static_cast<cudaStream_t>(stream), /*pdl=*/false);
+}
+
+int mixq_enqueue_allreduce(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes,
+                           const mixq_peer_group* g, unsigned flags, void* stream) {
+    if (!t || !g) return set_error(MIXQ_ERR_BAD_ARG, "enqueue_allreduce: null tensor table / peer group");
+    if (M < 0 || N <= 0 || K <= 0) return set_error(MIXQ_ERR_BAD_ARG, "enqueue_allreduce: bad dimensions");
+    if (M == 0) return MIXQ_OK;
+    if (!t->A || !t->W8 || !t->scale_b || !t->fp_weight || !t->ind)
+        return set_error(MIXQ_ERR_BAD_ARG, "enqueue_allreduce: null tensor (A, W8, scale_b, fp_weight and ind are required)");
+    if (!workspace) return set_error(MIXQ_ERR_WORKSPACE, "enqueue_allreduce: null workspace");
+    const Carve c = carve(M, K);
+    uintptr_t base = reinterpret_cast<uintptr_t>(workspace);
+    const uintptr_t aligned = (base + kAlign - 1) / kAlign * kAlign;
+    if (workspace_bytes < (aligned - base) + c.total) return set_error(MIXQ_ERR_WORKSPACE, "enqueue_allreduce: workspace too small");
+    uint8_t* ws = reinterpret_cast<uint8_t*>(aligned);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = launch_quant_extract(t->A, M, K, t->ind, MIXQ_NUM_OUTLIERS, ws + c.off_a8, ws + c.off_sa, ws + c.off_fpa, flags, s,
+                                  /*pdl=*/true);
+    if (rc) return rc;
+    return launch_gemm_dequant_allreduce(ws + c.off_a8, t->W8, ws + c.off_sa, t->scale_b, ws + c.off_fpa, t->fp_weight, M, N, K, g,
+                                         s, /*pdl=*/true);
+}
+
 size_t mixq_host_scratch_size(int64_t M, int64_t N, int64_t K) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     return align_up(static_cast<size_t>(M) * K * 2) + align_up(static_cast<size_t>(M) * N * 2) +

@@ -38,6 +38,12 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
                         const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
                         bool pdl, void* sk_ws = nullptr, size_t sk_ws_bytes = 0, bool sk_flags_clean = false);
 size_t streamk_workspace_bytes();
+// stage 2 with the row-parallel all-reduce fused in (peer memory; see ArParams in gemm_i8_tcgen05.cu)
+int launch_gemm_dequant_allreduce(const void* A8, const void* W8, const void* scale_a, const void* scale_b,
+                                  const void* fp_A, const void* fp_weight, int64_t M, int64_t N, int64_t K,
+                                  const mixq_peer_group* pg, cudaStream_t stream, bool pdl);
+size_t allreduce_staging_bytes(int64_t M, int64_t N, int world);
+size_t allreduce_counter_bytes(int64_t M, int64_t N, int world);
 int set_trace_buffer(void* dev_buf);
 
 // GEMM tile configuration ids (mixq_set_gemm_config); 0 = pick automatically.
