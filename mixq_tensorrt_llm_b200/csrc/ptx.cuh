@@ -92,6 +92,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                  : "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// 1D bulk copy shared -> global (contiguous bytes; 16-byte aligned, size a multiple of 16; bulk-group completion).
+__device__ __forceinline__ void bulk_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :
+                 : "l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {

@@ -72,8 +72,8 @@ def main():
                 print(f"MISMATCH it={it} shape={M}x{N}x{K} rank={r}: {int(bad.sum())} of {M*N}; first {nz[:4].tolist()} "
                       f"got {got[bad][:4].tolist()} want {ref[bad][:4].tolist()}")
                 sys.exit(1)
-        for c in cnts:
-            assert int(c.abs().sum()) == 0, "counters not re-armed"
+        for c in cnts:   # words: 0 done, 1 launch epoch, 2..3 pushed[parity]
+            assert int(c[0]) == 0 and int(c[2]) == 0 and int(c[3]) == 0 and int(c[1]) == (it + 1) % 2, "counters not re-armed"
         print(f"ok it={it} world={world} shape={M}x{N}x{K} sm_limit={lim}")
     print("PASS")
 

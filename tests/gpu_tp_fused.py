@@ -1,0 +1,127 @@
+"""Multi-GPU check + timing of the fused row-parallel GEMM + all-reduce (mixq_enqueue_allreduce) against the
+unfused path (mixq_enqueue, then one NCCL all-reduce).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tests/gpu_tp_fused.py [MxNxK ...]          (K = the UNSHARDED input width)
+
+Parity: the fused result must equal fp16(sum_r fp32(partial_r)) (rank order) bit for bit on every rank, where the
+partials are what mixq_enqueue produces on each rank (gathered with NCCL for the comparison only).
+"""
+import json
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from mixq_tensorrt_llm_b200 import binding as B  # noqa: E402
+from mixq_tensorrt_llm_b200.peer import PeerBuffers  # noqa: E402
+
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+lib = B.load()
+B.require_device()
+shapes = [tuple(int(x) for x in s.split("x")) for s in sys.argv[1:]] or [(512, 8192, 8192), (512, 4096, 4096), (8192, 4096, 4096)]
+maxM, maxN = max(s[0] for s in shapes), max(s[1] for s in shapes)
+pb = PeerBuffers(maxM, maxN, device=dev)
+results = []
+
+
+def timeit(fn, iters):
+    for _ in range(3):
+        fn()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) * 1e3   # us
+
+
+for (M, N, K) in shapes:
+    Kr = K // world
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    A = torch.randn(M, Kr, device=dev, generator=g).half()
+    W8 = torch.randint(-127, 128, (N, Kr), dtype=torch.int8, device=dev, generator=g)
+    sb = (torch.rand(N, device=dev, generator=g) * 2e-4 + 1e-4).half()
+    fw = (torch.randn(N, 128, device=dev, generator=g) * 0.02).half()
+    ind = torch.randperm(Kr, device=dev, generator=g)[:128].int()
+    A[:, ind.long()] *= 20.0
+    ws = torch.empty(B.workspace_size(M, N, Kr), dtype=torch.uint8, device=dev)
+    part = torch.empty(M, N, dtype=torch.float16, device=dev)
+    B.enqueue(A, W8, sb, fw, ind, part, ws)
+    parts = [torch.empty_like(part) for _ in range(world)]
+    dist.all_gather(parts, part)
+    ref = parts[0].float()
+    for r in range(1, world):
+        ref = ref + parts[r].float()
+    ref = ref.half()
+    grp = pb.peer_group(M, N)
+    out = pb.out(M, N)
+    out.fill_(float("nan"))
+    torch.cuda.synchronize()
+    dist.barrier()
+    B.enqueue_allreduce(A, W8, sb, fw, ind, ws, grp)
+    torch.cuda.synchronize()
+    bad = int((out.view(torch.int16) != ref.view(torch.int16)).sum())
+    nccl_out = part.clone()
+    dist.all_reduce(nccl_out)
+    nccl_diff = float((nccl_out.float() - ref.float()).abs().max())
+    t_bad = torch.tensor([bad], device=dev)
+    dist.all_reduce(t_bad)
+
+    def unfused():
+        B.enqueue(A, W8, sb, fw, ind, part, ws)
+        dist.all_reduce(part)
+
+    def fused():
+        B.enqueue_allreduce(A, W8, sb, fw, ind, ws, grp)
+
+    def gemm_only():
+        B.enqueue(A, W8, sb, fw, ind, part, ws)
+
+    def nccl_only():
+        dist.all_reduce(part)
+
+    iters = 50 if M <= 2048 else 10
+    res = dict(shape=[M, N, K], world=world, mismatches=int(t_bad.item()), nccl_vs_fp32sum_maxabs=nccl_diff,
+               unfused_us=timeit(unfused, iters), fused_us=timeit(fused, iters), gemm_only_us=timeit(gemm_only, iters),
+               nccl_only_us=timeit(nccl_only, iters))
+    # per-CTA timeline of one fused launch (debug stamps of the kernel), rank 0
+    import numpy as np
+    trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+    dist.barrier()
+    B.check(lib.mixq_debug_set_trace(trace.data_ptr()), "trace")
+    fused()
+    torch.cuda.synchronize()
+    lib.mixq_debug_set_trace(None)
+    tr = trace.cpu().numpy().reshape(148, 16).astype(np.float64)
+    t0 = tr[:, 0][tr[:, 0] > 0].min()
+    rel = np.where(tr > 0, (tr - t0) / 1e3, np.nan)
+    tl = {}
+    for nm, i in (("mmaDone", 4), ("epiLoopExit", 10), ("storesLanded", 11), ("phaseA_signalled", 12), ("firstUnitReady", 13),
+                  ("phaseB_issued", 14), ("exit", 15)):
+        col = rel[:, i]
+        if (~np.isnan(col)).any():
+            tl[nm] = [round(float(np.nanmin(col)), 1), round(float(np.nanmedian(col)), 1), round(float(np.nanmax(col)), 1)]
+    res["timeline_us_min_med_max"] = tl
+    res["speedup"] = res["unfused_us"] / res["fused_us"]
+    res["allreduce_bytes"] = M * N * 2
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    results.append(res)
+dist.barrier()
+if rank == 0:
+    ok = all(r["mismatches"] == 0 for r in results)
+    print("PASS" if ok else "FAIL", flush=True)
+dist.destroy_process_group()
