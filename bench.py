@@ -223,12 +223,22 @@ def run_ours(args, M, linears):
 
     chunks = args.tp_chunks if (tp > 1 and M >= 4096 * args.tp_chunks) else 1
     nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+    # Row-parallel linears: the all-reduce is fused into the GEMM kernel (partial tiles pushed to their owner over
+    # NVLink peer memory, fp32 reduce, result written to every rank) -- mixq_enqueue_allreduce.  --tp-reduce nccl keeps
+    # the unfused baseline (mixq_enqueue + NCCL all-reduce in overlapped row slabs) for comparison.
+    peer = None
+    if tp > 1 and args.tp_reduce == "fused":
+        from mixq_tensorrt_llm_b200.peer import PeerBuffers
+        peer = PeerBuffers(M, max(Ns for _, _, Ns, _, mode in mods if mode == "row"), device=dev)
 
     def step():
         for name, mod, Ns, Ks, mode in mods:
             out = out_buf[: M * Ns].view(M, Ns)
             W8 = mod.weight.view(torch.int8).view(Ns, Ks)
-            if tp > 1 and mode == "row":
+            if tp > 1 and mode == "row" and peer is not None:
+                B.enqueue_allreduce(acts[Ks], W8, mod.weights_scaling_factor, mod.fp_weight, mod.fp_ind.view(torch.int32),
+                                    ws, peer.peer_group(M, Ns))
+            elif tp > 1 and mode == "row":
                 # The one exchange step of the path.  The token dimension is cut into `chunks` row slabs:
                 # the NCCL all-reduce of slab c (on NCCL's stream) overlaps the GEMM of slab c+1.
                 works = []
@@ -260,11 +270,13 @@ def run_ours(args, M, linears):
     launches_per_step = lib.mixq_launch_count() - nl0
     # Decode-sized steps are a handful of 10-30 us kernels: replay them from a CUDA graph, as a serving
     # runtime (TensorRT) would, so the step is not bounded by Python/launch latency.
-    use_graph = args.graph == "on" or (args.graph == "auto" and M <= 2048 and world == 1)
+    # With the all-reduce fused into the GEMM kernel a tensor-parallel step holds no NCCL call and is capturable too.
+    use_graph = args.graph == "on" or (args.graph == "auto" and M <= 2048 and (world == 1 or peer is not None))
     run_step = step
     if use_graph:
         gs = torch.cuda.Stream()
         graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()      # the step above ran on another stream: fused all-reduce launches must not overlap
         with torch.cuda.stream(gs):
             step()
             gs.synchronize()
@@ -369,8 +381,31 @@ def run_ours(args, M, linears):
             h2d = sum(M * k * 2 for _, _, _, k, _ in mods)
             d2h = sum(M * n * 2 for _, _, n, _, _ in mods)
 
+            dA_buf = torch.empty(M * maxK, dtype=torch.float16, device=dev) if peer is not None else None
+            s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+            ev_down = None
+
             def e2e_step():
+                nonlocal ev_down
                 for name, mod, Ns, Ks, mode in mods:
+                    if peer is not None and mode == "row":
+                        # row-parallel shard: H2D (copy stream), fused GEMM + all-reduce, D2H of the reduced result (copy
+                        # stream; overlaps the next linear).  The peer Out buffer is reused: wait for its last D2H.
+                        dA = dA_buf[: M * Ks].view(M, Ks)
+                        s_up.wait_stream(stream)
+                        with torch.cuda.stream(s_up):
+                            dA.copy_(hA[Ks], non_blocking=True)
+                        stream.wait_stream(s_up)
+                        if ev_down is not None:
+                            stream.wait_event(ev_down)
+                        B.enqueue_allreduce(dA, mod.weight.view(torch.int8).view(Ns, Ks), mod.weights_scaling_factor, mod.fp_weight,
+                                            mod.fp_ind.view(torch.int32), ws, peer.peer_group(M, Ns))
+                        s_down.wait_stream(stream)
+                        with torch.cuda.stream(s_down):
+                            hO[: M * Ns].view(M, Ns).copy_(peer.out(M, Ns), non_blocking=True)
+                            ev_down = torch.cuda.Event()
+                            ev_down.record(s_down)
+                        continue
                     t_ = B.make_tensors(None, mod.weight, mod.weights_scaling_factor, mod.fp_weight, mod.fp_ind, None)
                     B.check(lib.mixq_linear_host(ctypes.byref(t_), hA[Ks].data_ptr(), hO.data_ptr(), M, Ns, Ks,
                                                  scratch.data_ptr(), scratch.numel(), 0, stream.cuda_stream), "mixq_linear_host")
@@ -442,10 +477,12 @@ def run_ours(args, M, linears):
                 "scaling": "strong", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
                 "config": {"workload": args.workload, "tokens_per_step": M,
                            "linears": [[n, N, K, m] for n, N, K, m in linears],
-                           "comm_sms": args.comm_sms if (tp > 1 and chunks > 1) else 0,
+                           "comm_sms": args.comm_sms if (tp > 1 and chunks > 1 and peer is None) else 0,
                            "launch": "cuda-graph replay of the step" if use_graph else "direct launches",
-                           "parallelism": (f"tp{tp} (column: no collective; row: one NCCL all-reduce in {chunks} overlapped row slabs)"
-                                           if tp > 1 else "single"),
+                           "parallelism": ("single" if tp == 1 else
+                                           f"tp{tp} (column: no collective; row: all-reduce fused into the GEMM kernel over NVLink peer memory)"
+                                           if peer is not None else
+                                           f"tp{tp} (column: no collective; row: one NCCL all-reduce in {chunks} overlapped row slabs)"),
                            "l2": "inputs larger than L2 (activations %.0f MB per linear), no flush" % (M * 4096 * 2 / 1e6)
                                  if M >= 16384 else "weights rotate through >126 MB per step; activations L2-resident"},
                 "tokens_per_s": M / (ms_step * 1e-3), "gpu_launches": int(launches), "clocks": clocks,
@@ -467,6 +504,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--tp-chunks", type=int, default=4, help="row slabs per row-parallel linear (comm/compute overlap)")
     ap.add_argument("--comm-sms", type=int, default=40, help="SMs left free for NCCL when slabs overlap (tensor parallel only)")
+    ap.add_argument("--tp-reduce", default="fused", choices=["fused", "nccl"],
+                    help="row-parallel linears: all-reduce fused into the GEMM kernel (default) or NCCL after it")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto: decode-sized M on one GPU)")
     ap.add_argument("--no-e2e", action="store_true")

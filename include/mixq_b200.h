@@ -136,7 +136,10 @@ int mixq_gemm_dequant_ws(const void* A8, const void* W8, const void* scale_a, co
  * fp32 in rank order (deterministic; one rounding to fp16) and write the result into every rank's Out.  When the
  * call's kernel completes on a rank, that rank's Out holds the reduced [M,N] result.
  *
- * All ranks must issue the same sequence of fused calls with the same (M, N).  The pointers are addresses valid in
+ * All ranks must issue the same sequence of fused calls with the same (M, N), and on each rank the calls that share
+ * a peer group must be ordered (one stream, or event-ordered streams): two of them in flight at once on one rank
+ * would share the staging area and the counters.  The calls are CUDA-graph capturable (no NCCL, no host state:
+ * the launch epoch lives in the counter block).  The pointers are addresses valid in
  * THIS process for every rank's buffers (CUDA IPC / cuMem fabric handles / torch symmetric memory: whatever the host
  * uses to map peer memory); index `rank` is the local buffer.  `counters` must be zeroed once after allocation and is
  * re-armed by the kernel itself.  Buffers are M/N dependent only through the two size functions. */

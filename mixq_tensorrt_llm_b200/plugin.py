@@ -143,6 +143,16 @@ class MixQLinear(torch.nn.Module):
         else:
             self.bias = None
         self._plugin = None
+        self._peer = None
+
+    def attach_peer_buffers(self, peer) -> "MixQLinear":
+        """Row-parallel only: fuse the all-reduce into the GEMM kernel (mixq_enqueue_allreduce) using the symmetric
+        buffers in ``peer`` (mixq_tensorrt_llm_b200.peer.PeerBuffers).  The returned tensor of forward() is then a
+        view of peer's Out buffer, valid until the next fused call that uses the same buffers."""
+        if self.parallel_mode != "row":
+            raise ValueError("peer buffers are used by row-parallel linears only")
+        self._peer = peer
+        return self
 
     @torch.no_grad()
     def load_packed(self, W8: torch.Tensor, scale_b: torch.Tensor, fp_weight: torch.Tensor, ind: torch.Tensor,
@@ -157,6 +167,18 @@ class MixQLinear(torch.nn.Module):
         return self
 
     def forward(self, A: torch.Tensor) -> torch.Tensor:
+        if self._peer is not None and self.tp_size > 1:
+            binding.require_device()
+            M = A.numel() // A.shape[-1]
+            A2 = A.reshape(M, A.shape[-1]).contiguous()
+            ws = _workspace(A.device, binding.workspace_size(max(M, 1), self.out_features, self.in_features))
+            binding.enqueue_allreduce(A2, self.weight.view(torch.int8).view(self.out_features, self.in_features),
+                                      self.weights_scaling_factor, self.fp_weight, self.fp_ind.view(torch.int32), ws,
+                                      self._peer.peer_group(M, self.out_features))
+            x = self._peer.out(M, self.out_features).view(*A.shape[:-1], self.out_features)
+            if self.bias is not None:
+                x = x + self.bias.to(x.dtype)
+            return x
         if self._plugin is None:
             self._plugin = _PluginHandle(A.shape[0], self.out_features, self.in_features)
         x = mixgemm(A.shape[0], self.out_features, self.in_features,

@@ -156,3 +156,22 @@ def test_product_does_not_touch_oracle():
     if so.exists():
         ldd = subprocess.run(["ldd", str(so)], capture_output=True, text=True).stdout
         assert "oracle" not in ldd and "ref_" not in ldd
+
+
+def test_allreduce_entry_points_validate_arguments(lib):
+    """mixq_enqueue_allreduce / mixq_gemm_dequant_allreduce reject bad groups before touching the GPU."""
+    from mixq_tensorrt_llm_b200 import binding
+    assert lib.mixq_allreduce_counter_size(512, 8192, 8) >= 16
+    # one 256x256 tile slot per tile, rounded up to a multiple of world
+    assert lib.mixq_allreduce_staging_size(512, 8192, 8) == 512 * 8192 * 2
+    assert lib.mixq_allreduce_staging_size(300, 1000, 2) == 2 * 4 * 256 * 256 * 2
+    assert lib.mixq_allreduce_staging_size(0, 8, 2) == 0
+    g = binding.PeerGroup()
+    g.world, g.rank = 9, 0
+    assert lib.mixq_gemm_dequant_allreduce(16, 16, 16, 16, None, None, 8, 8, 16, ctypes.byref(g), None) == -1   # world > 8
+    g.world, g.rank = 2, 2
+    assert lib.mixq_gemm_dequant_allreduce(16, 16, 16, 16, None, None, 8, 8, 16, ctypes.byref(g), None) == -1   # rank >= world
+    assert lib.mixq_gemm_dequant_allreduce(16, 16, 16, 16, None, None, 8, 8, 16, None, None) == -1              # no group
+    t = binding.Tensors()
+    assert lib.mixq_enqueue_allreduce(ctypes.byref(t), 8, 8, 16, None, 0, ctypes.byref(g), 0, None) == -1       # null tensors
+    assert lib.mixq_enqueue_allreduce(ctypes.byref(t), 0, 8, 16, None, 0, ctypes.byref(g), 0, None) == 0        # M == 0: no-op

@@ -400,3 +400,19 @@ def test_full_size_properties(B, oracle):
     B.enqueue(tA, tW, tsb, tfw, tind, out_r, ws)
     torch.cuda.synchronize()
     assert torch.equal(out_r.view(torch.int16), out.view(torch.int16))
+
+
+# ------------------------------------------------------------------ fused row-parallel GEMM + all-reduce
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_fused_allreduce_virtual_ranks(world):
+    """mixq_gemm_dequant_allreduce, protocol + arithmetic on one GPU: `world` concurrent launches (virtual ranks, each
+    confined to 148/world SMs, peer pointers = local pointers).  Every rank's Out must equal
+    fp16(sum_r fp32(partial_r)) in rank order BIT FOR BIT, across repeated launches (counter re-arming, epoch parity)
+    and shapes with M/N edges.  Runs in a subprocess: a protocol bug traps that context instead of hanging pytest."""
+    import subprocess
+    import sys as _sys
+    r = subprocess.run([_sys.executable, str(ROOT / "tests" / "gpu_ar_virtual.py"), str(world),
+                        "512x4096x1024", "300x1000x512", "2048x4096x2048", "40x256x256"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
