@@ -47,7 +47,7 @@ enum {
      * commented out (kernel/i8gemm.cu:218). */
     MIXQ_FLAG_MASK_OUTLIERS = 1u << 0,
     /* Skip the M<=4 weight-only branch (TsinghuaMixQPlugin.cpp:472,641-647) and
-     * run the mixed W8A8O16 path for every M. */
+     * run the mixed W8A8O16 path for every M (also what happens when q_weight is NULL). */
     MIXQ_FLAG_FORCE_MIXED = 1u << 1
 };
 
@@ -90,8 +90,10 @@ size_t mixq_workspace_size(int64_t M, int64_t N, int64_t K);
  * Requirements: K % 16 == 0, N % 8 == 0, all pointers 16-byte aligned, `ind`
  * values in [0, K). M may be any positive value (M == 0 is a no-op).
  * For M <= 4 the reference switches to a weight-only GEMV over q_weight
- * (TsinghuaMixQPlugin.cpp:641-647); this build runs the mixed path for every M
- * (see DESIGN.md "M<=4").  */
+ * (TsinghuaMixQPlugin.cpp:472,641-647).  So does this call when t->q_weight is given
+ * (then only A, q_weight, scaling_factors and Out are read, N % 4 == 0 and K % 64 == 0
+ * are required and the workspace is not used): see mixq_gemv_w8a16.  With q_weight ==
+ * NULL or MIXQ_FLAG_FORCE_MIXED the mixed path runs for every M.  */
 int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace,
                  size_t workspace_bytes, unsigned flags, void* stream);
 
@@ -120,6 +122,15 @@ int mixq_rmsnorm_quant_extract(const void* X, const void* gamma, float eps, int6
 int mixq_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b,
                       const void* fp_A, const void* fp_weight, void* Out, int64_t M, int64_t N,
                       int64_t K, void* stream);
+
+/* The M <= 4 branch alone.  Replaces w8_a16_gemm_forward_cuda -> weight_only_batched_gemv
+ * (weightonlykernel/fpA_intB_gemm_wrapper.cu:29-57; weightOnlyBatchedGemv/kernel.h:285-438):
+ *   Out[m,n] = sum_k A[m,k] * fp16((code[k,n] - 128) * scales[n]),  1 <= M <= 4,
+ * fp16 accumulation per thread and fp32 across threads in the reference kernel's order (bit-identical to it).
+ * q_weight is the processed int8 tensor EETQ.quant_weights returns for W^T [K,N]
+ * (cutlass_preprocessors.cc:497-533, Sm80 layout); scales is its fp16 [N] companion. */
+int mixq_gemv_w8a16(const void* A, const void* q_weight, const void* scales, void* Out, int64_t M,
+                    int64_t N, int64_t K, void* stream);
 
 /* Stage 2 with scratch for the stream-K schedule the library prefers for decode-sized M (tiles that do
  * not fill the GPU evenly are cut along K; int32 partial sums meet in `workspace`).  Results are

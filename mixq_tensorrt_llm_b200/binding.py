@@ -19,7 +19,7 @@ FLAG_FORCE_MIXED = 2
 # every symbol include/mixq_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_enqueue",
-    "mixq_quant_extract", "mixq_rmsnorm_quant_extract", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
+    "mixq_quant_extract", "mixq_rmsnorm_quant_extract", "mixq_gemv_w8a16", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
     "mixq_host_scratch_size", "mixq_linear_host",
     "mixq_allreduce_staging_size", "mixq_allreduce_counter_size", "mixq_enqueue_allreduce", "mixq_gemm_dequant_allreduce",
     "mixq_launch_count", "mixq_set_gemm_config", "mixq_set_sm_limit", "mixq_debug_set_trace", "initOpenAiTritonPlugins", "mixq_plugin_create",
@@ -77,6 +77,8 @@ def load() -> ctypes.CDLL:
     L.mixq_rmsnorm_quant_extract.argtypes = [vp, vp, ctypes.c_float, i64, i64, vp, ci, vp, vp, vp, vp, u32, vp]
     L.mixq_gemm_dequant.restype = ci
     L.mixq_gemm_dequant.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
+    L.mixq_gemv_w8a16.restype = ci
+    L.mixq_gemv_w8a16.argtypes = [vp, vp, vp, vp, i64, i64, i64, vp]
     L.mixq_gemm_workspace_size.restype = sz
     L.mixq_gemm_workspace_size.argtypes = []
     L.mixq_gemm_dequant_ws.restype = ci
@@ -165,11 +167,13 @@ def make_tensors(A, W8, scale_b, fp_weight, ind, Out, q_weight=None, scaling_fac
     return t
 
 
-def enqueue(A, W8, scale_b, fp_weight, ind, Out, workspace, flags: int = 0, stream=None) -> None:
-    """mixq_enqueue on torch CUDA tensors (A [M,K] fp16 contiguous, Out [M,N] fp16)."""
+def enqueue(A, W8, scale_b, fp_weight, ind, Out, workspace, flags: int = 0, stream=None, q_weight=None,
+            scaling_factors=None) -> None:
+    """mixq_enqueue on torch CUDA tensors (A [M,K] fp16 contiguous, Out [M,N] fp16).  With q_weight / scaling_factors
+    (the EETQ pair) a call with M <= 4 takes the weight-only branch, as the reference plugin does."""
     M, K = A.shape
     N = Out.shape[-1]
-    t = make_tensors(A, W8, scale_b, fp_weight, ind, Out)
+    t = make_tensors(A, W8, scale_b, fp_weight, ind, Out, q_weight, scaling_factors)
     check(load().mixq_enqueue(ctypes.byref(t), M, N, K, _ptr(workspace), workspace.numel() * workspace.element_size(),
                               flags, _stream(stream)), "mixq_enqueue")
 
@@ -226,3 +230,10 @@ def gemm_dequant_allreduce(A8, W8, scale_a, scale_b, fp_A, fp_weight, group: Pee
     N = W8.shape[0]
     check(load().mixq_gemm_dequant_allreduce(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A), _ptr(fp_weight),
                                              M, N, K, ctypes.byref(group), _stream(stream)), "mixq_gemm_dequant_allreduce")
+
+
+def gemv_w8a16(A, q_weight, scales, Out, stream=None) -> None:
+    """mixq_gemv_w8a16: the M <= 4 weight-only branch alone."""
+    M, K = A.shape
+    N = Out.shape[-1]
+    check(load().mixq_gemv_w8a16(_ptr(A), _ptr(q_weight), _ptr(scales), _ptr(Out), M, N, K, _stream(stream)), "mixq_gemv_w8a16")

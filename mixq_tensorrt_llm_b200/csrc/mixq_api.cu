@@ -121,6 +121,11 @@ int mixq_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const
                                static_cast<cudaStream_t>(stream), /*pdl=*/false);
 }
 
+int mixq_gemv_w8a16(const void* A, const void* q_weight, const void* scales, void* Out, int64_t M, int64_t N, int64_t K,
+                    void* stream) {
+    return launch_gemv_w8a16(A, q_weight, scales, Out, M, N, K, static_cast<cudaStream_t>(stream));
+}
+
 int mixq_debug_set_trace(void* dev_buf) { return set_trace_buffer(dev_buf); }
 
 size_t mixq_gemm_workspace_size(void) { return streamk_workspace_bytes(); }
@@ -137,6 +142,13 @@ int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* w
     if (!t) return set_error(MIXQ_ERR_BAD_ARG, "enqueue: null tensor table");
     if (M < 0 || N <= 0 || K <= 0) return set_error(MIXQ_ERR_BAD_ARG, "enqueue: bad dimensions");
     if (M == 0) return MIXQ_OK;
+    // decode with at most 4 tokens: the reference switches to the weight-only GEMV over q_weight
+    // (TsinghuaMixQPlugin.cpp:472, 641-647).  Taken when the caller provides that second weight copy.
+    if (M <= 4 && t->q_weight && !(flags & MIXQ_FLAG_FORCE_MIXED)) {
+        if (!t->A || !t->scaling_factors || !t->Out)
+            return set_error(MIXQ_ERR_BAD_ARG, "enqueue: null tensor (A, q_weight, scaling_factors and Out are required for M <= 4)");
+        return launch_gemv_w8a16(t->A, t->q_weight, t->scaling_factors, t->Out, M, N, K, static_cast<cudaStream_t>(stream));
+    }
     if (!t->A || !t->W8 || !t->scale_b || !t->fp_weight || !t->ind || !t->Out)
         return set_error(MIXQ_ERR_BAD_ARG, "enqueue: null tensor (A, W8, scale_b, fp_weight, ind and Out are required)");
     if (!workspace) return set_error(MIXQ_ERR_WORKSPACE, "enqueue: null workspace");

@@ -46,6 +46,10 @@ size_t allreduce_staging_bytes(int64_t M, int64_t N, int world);
 size_t allreduce_counter_bytes(int64_t M, int64_t N, int world);
 int set_trace_buffer(void* dev_buf);
 
+// M <= 4 branch (gemv_w8a16.cu): weight-only GEMV over the EETQ-interleaved q_weight
+int launch_gemv_w8a16(const void* A, const void* q_weight, const void* scales, void* Out, int64_t M, int64_t N, int64_t K,
+                      cudaStream_t stream);
+
 // GEMM tile configuration ids (mixq_set_gemm_config); 0 = pick automatically.
 enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfg2CtaN256Tma = 9, kCfg2CtaN192Tma = 10, kCfgCount };
 int current_gemm_config();

@@ -229,6 +229,108 @@ void mixq_oracle_forward(const uint16_t* A, const int8_t* W8, const uint16_t* sc
 }
 
 /* torchrun exports OMP_NUM_THREADS=1; the timing legs ask for all host cores explicitly. */
+/* ------------------------------------------------------------------------------------------------
+ * M <= 4 branch: W8A16 weight-only GEMV (reference TsinghuaMixQPlugin.cpp:472,641-647 ->
+ * weightonlykernel/fpA_intB_gemm_wrapper.cu:29-57 -> weightOnlyBatchedGemv/kernelLauncher.cu:179-206
+ * (Int8b, PerChannel: NPerBlock = 2, Batch = M, BlockSize = 256) -> weightOnlyBatchedGemv/kernel.h:285-438).
+ *
+ * The kernel's arithmetic is restated slot by slot, because its rounding sequence IS the specification:
+ *   - a block of 256 thread slots owns 4 consecutive output channels n0..n0+3 (two interleaved row pairs);
+ *   - slot t reads 16 codes of channel n0 + 2*idx + r, r = (t / 4) % 2, idx in {0, 1}, at
+ *       k = (t / 8 + 32 * it) * 64 + (t % 4) * 16 + y,  y = 0..15,   while t * 16 + it * 4096 < 2 * K   (kernel.h:322-323);
+ *   - w = fp16( (code - 128) * scale[n] )   (__hfma2(v, scale, 0), kernel.h:355-356);
+ *   - per slot and token, an fp16 chain  acc = fp16_fma(w, in[m, k], acc)  over y ascending, over `it` ascending
+ *     (__hfma2 with single rounding, kernel.h:401-411);
+ *   - the slot sums are converted to fp32 and combined with the butterfly xor 16, 8, 2, 1 inside each warp
+ *     (kernel.h:155-161), the 8 warp results are added in warp order starting from 0.f (kernel.h:420-425),
+ *     and the fp32 sum is rounded to fp16 (kernel.h:432).
+ * `qweight` is the processed (permuted / transposed / 2-column interleaved / +128 biased / byte-swizzled) tensor
+ * EETQ.quant_weights produces (cutlass_preprocessors.cc:497-533); the byte fetched for (channel, k) follows from
+ * undoing those steps exactly as the kernel does (kernel.h:336-368):
+ *   byte address = (n / 2) * 2K + (k / 64) * 128 + (n % 2) * 64 + (k % 64) / 16 * 16 + pos(k % 16)
+ *   pos(y): p = (y / 8) * 2 + ((y % 8) / 2) * 4 + y % 2  (position after permute_B_rows),  then bytes 1 and 2 of each
+ *           aligned group of four are swapped (add_bias_and_interleave_int8s_inplace).
+ */
+static inline f16 dev_hfma(f16 a, f16 b, f16 c) {
+    /* exact product (22 significant bits), one rounding to fp16 of product + c: the double sum is made
+       round-to-odd when it is inexact, so the final rounding sees the sticky information */
+    const double p = (double)a * (double)b;
+    const double cc = (double)c;
+    double s = p + cc;
+    if (isfinite(s)) {
+        const double bb = s - p;
+        const double err = (p - (s - bb)) + (cc - bb);
+        if (err != 0.0) {
+            uint64_t u;
+            memcpy(&u, &s, 8);
+            if ((u & 1) == 0) {
+                if ((err > 0) == (s > 0)) u += 1; else u -= 1;
+                memcpy(&s, &u, 8);
+            }
+        }
+    }
+    return (f16)s;
+}
+
+static inline int gemv_byte_pos(int y) {
+    const int p = (y / 8) * 2 + ((y % 8) / 2) * 4 + (y % 2);
+    const int q = p & 3;
+    return (p & ~3) | (q == 1 ? 2 : q == 2 ? 1 : q);
+}
+
+void mixq_oracle_gemv_w8a16(const uint16_t* in, const uint8_t* qweight, const uint16_t* scales, int64_t M,
+                            int64_t N, int64_t K, uint16_t* out) {
+    int pos[16];
+    for (int y = 0; y < 16; ++y) pos[y] = gemv_byte_pos(y);
+#pragma omp parallel for schedule(static)
+    for (int64_t blk = 0; blk < N / 4; ++blk) {
+        const int64_t n0 = blk * 4;
+        float slot[256][8];                       /* [slot][m * 2 + idx] as fp32 */
+        for (int t = 0; t < 256; ++t) {
+            const int r = (t / 4) % 2;
+            f16 acc[8];
+            for (int i = 0; i < 8; ++i) acc[i] = (f16)0.0f;
+            for (int64_t it = 0; (int64_t)t * 16 + it * 4096 < 2 * K; ++it) {
+                const int64_t kb = ((int64_t)(t / 8) + 32 * it) * 64 + (t % 4) * 16;
+                f16 w[2][16];
+                for (int idx = 0; idx < 2; ++idx) {
+                    const int64_t n = n0 + 2 * idx + r;
+                    const f16 sc = bits_to_f16(scales[n]);
+                    const uint8_t* src = qweight + (n / 2) * 2 * K + (kb / 64) * 128 + (n % 2) * 64 + (kb % 64);
+                    for (int y = 0; y < 16; ++y) {
+                        const f16 code = (f16)(float)((int)src[pos[y]] - 128);
+                        w[idx][y] = (f16)((float)code * (float)sc + 0.0f);   /* __hfma2(v, scale, 0): product exact in fp32 */
+                    }
+                }
+                for (int64_t m = 0; m < M; ++m)
+                    for (int y = 0; y < 16; ++y) {
+                        const f16 x = bits_to_f16(in[m * K + kb + y]);
+                        acc[m * 2 + 0] = dev_hfma(w[0][y], x, acc[m * 2 + 0]);
+                        acc[m * 2 + 1] = dev_hfma(w[1][y], x, acc[m * 2 + 1]);
+                    }
+            }
+            for (int i = 0; i < 8; ++i) slot[t][i] = (float)acc[i];
+        }
+        for (int64_t m = 0; m < M; ++m)
+            for (int idx = 0; idx < 2; ++idx)
+                for (int r = 0; r < 2; ++r) {
+                    float v = 0.0f;
+                    for (int wp = 0; wp < 8; ++wp) {
+                        float lane[32];
+                        for (int l = 0; l < 32; ++l) lane[l] = slot[wp * 32 + l][m * 2 + idx];
+                        static const int steps[4] = {16, 8, 2, 1};
+                        for (int st = 0; st < 4; ++st) {
+                            float nx[32];
+                            for (int l = 0; l < 32; ++l) nx[l] = lane[l] + lane[l ^ steps[st]];
+                            memcpy(lane, nx, sizeof(lane));
+                        }
+                        v += lane[r * 4];              /* lanes 0 and 4 publish rows r = 0 and 1 */
+                    }
+                    out[m * N + n0 + 2 * idx + r] = f16_to_bits((f16)v);
+                }
+    }
+}
+
 void mixq_oracle_set_threads(int n) {
 #ifdef _OPENMP
     if (n > 0) omp_set_num_threads(n);

@@ -61,6 +61,8 @@ def lib():
                                           u16p, u16p, i8p, u16p, i32p, u16p]
         L.mixq_oracle_rmsnorm.argtypes = [u16p, u16p, ctypes.c_float, i64, i64, u16p]
         L.mixq_oracle_rmsnorm.restype = None
+        L.mixq_oracle_gemv_w8a16.argtypes = [u16p, ctypes.POINTER(ctypes.c_uint8), u16p, i64, i64, i64, u16p]
+        L.mixq_oracle_gemv_w8a16.restype = None
         L.mixq_oracle_num_threads.restype = i32
         L.mixq_oracle_set_threads.argtypes = [i32]
         L.mixq_oracle_set_threads.restype = None
@@ -236,6 +238,71 @@ def pack_linear_weights(W: np.ndarray, act_scale: np.ndarray, fp_features: int =
     W8 = np.clip(np.rint(quot.astype(np.float32)), -128, 127)
     W8 = np.nan_to_num(W8, nan=0.0).astype(np.int8)
     return dict(W8=W8, scale_b=sb, fp_weight=fp_weight, ind=ind)
+
+
+# ----------------------------------------------------------------------------- M <= 4 branch (weight-only)
+_PERM16 = np.array([0, 1, 8, 9, 2, 3, 10, 11, 4, 5, 12, 13, 6, 7, 14, 15])   # cutlass_preprocessors.cc:133-134,174-175
+
+
+def eetq_preprocess(q_kn: np.ndarray) -> np.ndarray:
+    """numpy restatement of preprocess_weights_for_mixed_gemm for int8 on the Sm80 layout
+    (weightonlykernel/cutlass_kernels/cutlass_preprocessors.cc:497-533; arch 80..90 -> :121-122,
+    ColumnMajorTileInterleave<64, 2> + OpMultiplyAddDequantizeInterleavedBToA):
+      1. permute_B_rows_for_mixed_gemm   (:137-199)  rows (K) permuted inside groups of 16
+      2. subbyte_transpose               (:322-335)  [K, N] row-major -> [N, K]
+      3. interleave_column_major_tensor  (:432-495)  two output channels interleaved in runs of 64 codes
+      4. add_bias_and_interleave_int8s   (:337-358)  +128, then bytes 1 and 2 of every four swapped
+    `q_kn` is the row-major int8 [K, N] matrix (the TRANSPOSED weight, as model_config_utils.py:437 passes it);
+    returns the processed bytes with the same nominal shape [K, N] (int8 view, as EETQ returns it)."""
+    q = np.ascontiguousarray(q_kn, dtype=np.int8)
+    K, N = q.shape
+    assert K % 64 == 0 and N % 2 == 0, "EETQ layout: K multiple of 64 (rows_per_column_tile), N even"
+    q = q.reshape(K // 16, 16, N)[:, _PERM16, :].reshape(K, N)
+    t = np.ascontiguousarray(q.T)                                                    # [N, K]
+    t = t.reshape(N // 2, 2, K // 64, 64).transpose(0, 2, 1, 3).reshape(N // 2, 2 * K)
+    u = (t.astype(np.int16) + 128).astype(np.uint8).reshape(-1, 4)[:, [0, 2, 1, 3]]
+    return np.ascontiguousarray(u).reshape(K, N).view(np.int8)
+
+
+def eetq_unprocess(processed: np.ndarray) -> np.ndarray:
+    """Inverse of eetq_preprocess: the plain int8 [K, N] codes."""
+    K, N = processed.shape
+    u = processed.view(np.uint8).reshape(-1, 4)[:, [0, 2, 1, 3]]
+    t = (u.astype(np.int16) - 128).astype(np.int8).reshape(N // 2, K // 64, 2, 64).transpose(0, 2, 1, 3).reshape(N, K)
+    q = np.ascontiguousarray(t.T)
+    inv = np.argsort(_PERM16)
+    return q.reshape(K // 16, 16, N)[:, inv, :].reshape(K, N)
+
+
+def eetq_quant_weights(W_t: np.ndarray):
+    """numpy restatement of EETQ.quant_weights(W.T, torch.int8, False) = symmetric_quantize<half, half>
+    (EETQ/csrc/cutlass_kernels/fpA_intB_gemm_wrapper.cu:28-110 -> cutlass_preprocessors.cc:581-678), as called at
+    model_config_utils.py:437-438 on the UN-zeroed weight:
+      per output channel n:  s = max_k |W_t[k, n]| * (1/128)  in fp32; scales[n] = fp16(s)          (:626-629)
+      code = clamp(round_half_away(W_t[k, n] / s), -128, 127)   with the fp32 s, not its fp16 image   (:637-641)
+    Returns (processed int8 [K, N], scales fp16 [N])."""
+    W_t = np.ascontiguousarray(W_t, dtype=np.float16)
+    s = np.abs(W_t.astype(np.float32)).max(axis=0) * np.float32(1.0 / 128.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        x = W_t.astype(np.float32) / s[None, :]
+    r = np.where(x >= 0, np.floor(x + np.float32(0.5)), np.ceil(x - np.float32(0.5)))   # C round(): half away from zero
+    # int8_t(std::max(-128.f, std::min(127.f, r))): std::min(127.f, NaN) keeps 127.f, so an all-zero channel (0/0) codes 127
+    q = np.nan_to_num(np.clip(r, -128, 127), nan=127.0).astype(np.int8)
+    return eetq_preprocess(q), s.astype(np.float16)
+
+
+def gemv_w8a16(A: np.ndarray, qweight: np.ndarray, scales: np.ndarray) -> np.ndarray:
+    """The M <= 4 branch: Out = A . dequant(qweight) with the reference kernel's exact rounding sequence
+    (oracle/mixq_oracle.c: mixq_oracle_gemv_w8a16).  A fp16 [M, K], qweight processed int8 [K, N], scales fp16 [N]."""
+    A = np.ascontiguousarray(A, dtype=np.float16)
+    M, K = A.shape
+    N = scales.shape[0]
+    assert qweight.size == K * N and 1 <= M <= 4 and N % 4 == 0 and K % 64 == 0
+    qw = np.ascontiguousarray(qweight).view(np.uint8).reshape(-1)
+    out = np.empty((M, N), dtype=np.float16)
+    lib().mixq_oracle_gemv_w8a16(_P(_u16(A), ctypes.c_uint16), _P(qw, ctypes.c_uint8), _P(_u16(scales), ctypes.c_uint16),
+                                 M, N, K, _P(out.view(np.uint16), ctypes.c_uint16))
+    return out
 
 
 def as_plugin_tensors(packed: dict):

@@ -89,3 +89,64 @@ def hdiv(a, b):
     qi = torch.empty(a.numel(), dtype=torch.int32, device=a.device)
     assert load().ref_hdiv(_p(a), _p(b), _p(q), _p(qi), a.numel(), _s()) == 0
     return q, qi
+
+
+# ---- M <= 4 branch: the reference's weight-only GEMV kernels (oracle/_ref/libref_gemv.so) and its CPU packer
+_gemv = None
+_pre = None
+
+
+def gemv_available() -> bool:
+    return (REF_DIR / "libref_gemv.so").exists()
+
+
+def preprocess_available() -> bool:
+    return (REF_DIR / "libref_preprocess.so").exists()
+
+
+def gemv(A, qweight, scales):
+    """reference weight_only_batched_gemv (Int8b, PerChannel, fp16) on torch CUDA tensors."""
+    import torch
+    global _gemv
+    if _gemv is None:
+        _gemv = ctypes.CDLL(str(REF_DIR / "libref_gemv.so"))
+        _gemv.ref_w8a16_gemv.restype = ctypes.c_int
+        _gemv.ref_w8a16_gemv.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 3 + [ctypes.c_void_p]
+    M, K = A.shape
+    N = scales.numel()
+    out = torch.empty(M, N, dtype=torch.float16, device=A.device)
+    rc = _gemv.ref_w8a16_gemv(_p(A), _p(qweight), _p(scales), _p(out), M, N, K, _s())
+    assert rc == 0, rc
+    return out
+
+
+def _prelib():
+    global _pre
+    if _pre is None:
+        _pre = ctypes.CDLL(str(REF_DIR / "libref_preprocess.so"))
+        _pre.ref_preprocess_int8.restype = ctypes.c_int
+        _pre.ref_preprocess_int8.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]
+        _pre.ref_symmetric_quantize_half.restype = ctypes.c_int
+        _pre.ref_symmetric_quantize_half.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_size_t] * 2
+    return _pre
+
+
+def preprocess_int8(q_kn, arch: int = 80):
+    """reference preprocess_weights(int8 [K,N] row-major) -> processed bytes (numpy, CPU)."""
+    import numpy as np
+    q = np.ascontiguousarray(q_kn, dtype=np.int8)
+    out = np.empty_like(q)
+    assert _prelib().ref_preprocess_int8(out.ctypes.data, q.ctypes.data, q.shape[0], q.shape[1], arch) == 0
+    return out
+
+
+def symmetric_quantize_half(W_t):
+    """reference symmetric_quantize<half, half> on W^T fp16 [K,N]: (plain int8 codes [K,N], scales fp16 [N])."""
+    import numpy as np
+    W = np.ascontiguousarray(W_t, dtype=np.float16)
+    K, N = W.shape
+    proc = np.zeros((K, N), dtype=np.int8)
+    unproc = np.zeros((K, N), dtype=np.int8)
+    scales = np.zeros(N, dtype=np.float16)
+    _prelib().ref_symmetric_quantize_half(proc.ctypes.data, unproc.ctypes.data, scales.ctypes.data, W.ctypes.data, K, N)
+    return unproc, scales

@@ -12,6 +12,7 @@ Tolerances:
     dot product inside cuBLAS / the tensor core).
 """
 import ctypes
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -23,6 +24,7 @@ import refgpu
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
 DEV = "cuda"
+ROOT = Path(__file__).resolve().parent.parent
 
 
 @pytest.fixture(scope="module")
@@ -416,3 +418,78 @@ def test_fused_allreduce_virtual_ranks(world):
                         "512x4096x1024", "300x1000x512", "2048x4096x2048", "40x256x256"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------ M <= 4 branch: weight-only GEMV
+def _gemv_cases():
+    import sys
+    sys.path.insert(0, str(GOLD))
+    import make_gemv_golden as G
+    return G, list(G.GEMV_CASES) + [(4, 4096, 4096, 21), (1, 12288, 4096, 22), (3, 4096, 11008, 23)]
+
+
+@pytest.mark.parametrize("case", range(10))
+def test_gemv_w8a16_bit_exact(B, oracle, case):
+    """mixq_gemv_w8a16 vs the CPU oracle (which is pinned to the reference kernel's outputs, tests/golden/
+    ref_gemv_b200.npz) and, when oracle/_ref/libref_gemv.so is on the box, vs the reference kernel itself:
+    fp16 output BIT-EXACT (the kernel keeps the reference's fp16 chains and fp32 reduction tree)."""
+    G, cases = _gemv_cases()
+    M, N, K, seed = cases[case]
+    A, W_t = G.gemv_case(M, N, K, seed)
+    qw, sc = oracle.eetq_quant_weights(W_t)
+    dA, dq, ds = _t(A), _t(qw), _t(sc)
+    out = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
+    B.gemv_w8a16(dA, dq, ds, out)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    if N * K <= 4096 * 4096:                    # the scalar oracle takes seconds beyond that
+        want = oracle.gemv_w8a16(A, qw, sc)
+        assert np.array_equal(got.view(np.uint16), want.view(np.uint16)), (M, N, K)
+    if refgpu.gemv_available():
+        ref = refgpu.gemv(dA, dq, ds).cpu().numpy()
+        assert np.array_equal(got.view(np.uint16), ref.view(np.uint16)), (M, N, K)
+    # sanity against float64 on the dequantised weights
+    f64 = A.astype(np.float64) @ (oracle.eetq_unprocess(qw).astype(np.float64) * sc.astype(np.float64)[None, :])
+    assert np.abs(got.astype(np.float64) - f64).max() <= 4e-3 * np.abs(f64).max() + 2e-3
+
+
+def test_enqueue_takes_weight_only_branch_for_small_M(B, oracle):
+    """TsinghuaMixQPlugin.cpp:472: M <= 4 -> weight-only GEMV over q_weight with input 6 as the scales; M > 4, a NULL
+    q_weight or MIXQ_FLAG_FORCE_MIXED -> the mixed path."""
+    N, K = 512, 4096
+    lin = oracle.synth_linear(N, K, oracle.load_act_scales("Llama-2-7b/self_attn.q_proj"))
+    rng = np.random.default_rng(9)
+    W_t = (rng.standard_normal((K, N)) * 0.02).astype(np.float16)
+    qw, sc = oracle.eetq_quant_weights(W_t)
+    dq, ds = _t(qw), _t(sc)
+    W8, sb, fw, ind = (_t(lin[k]) for k in ("W8", "scale_b", "fp_weight", "ind"))
+    for M in (1, 4, 5):
+        A = oracle.synth_activations(M, lin["act_scale"], seed=30 + M)
+        dA = _t(A)
+        ws = torch.empty(B.workspace_size(M, N, K), dtype=torch.uint8, device=DEV)
+        mixed = torch.empty(M, N, dtype=torch.float16, device=DEV)
+        B.enqueue(dA, W8, sb, fw, ind, mixed, ws)                                   # q_weight NULL -> mixed
+        out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+        B.enqueue(dA, W8, sb, fw, ind, out, ws, q_weight=dq, scaling_factors=ds)
+        forced = torch.empty(M, N, dtype=torch.float16, device=DEV)
+        B.enqueue(dA, W8, sb, fw, ind, forced, ws, flags=B.FLAG_FORCE_MIXED, q_weight=dq, scaling_factors=ds)
+        torch.cuda.synchronize()
+        assert torch.equal(forced.view(torch.int16), mixed.view(torch.int16))
+        if M <= 4:
+            want = oracle.gemv_w8a16(A, qw, sc)
+            assert np.array_equal(out.cpu().numpy().view(np.uint16), want.view(np.uint16))
+        else:
+            assert torch.equal(out.view(torch.int16), mixed.view(torch.int16))
+
+
+def test_gemv_w8a16_rejects_bad_shapes(B, lib):
+    a = torch.zeros(5, 64, dtype=torch.float16, device=DEV)
+    q = torch.zeros(64, 8, dtype=torch.int8, device=DEV)
+    s = torch.zeros(8, dtype=torch.float16, device=DEV)
+    o = torch.zeros(5, 8, dtype=torch.float16, device=DEV)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.mixq_gemv_w8a16(p(a), p(q), p(s), p(o), 5, 8, 64, None) == -4     # M > 4
+    assert lib.mixq_gemv_w8a16(p(a), p(q), p(s), p(o), 2, 6, 64, None) == -4     # N % 4
+    assert lib.mixq_gemv_w8a16(p(a), p(q), p(s), p(o), 2, 8, 32, None) == -4     # K % 64
+    assert lib.mixq_gemv_w8a16(None, p(q), p(s), p(o), 2, 8, 64, None) == -1
+    assert lib.mixq_gemv_w8a16(p(a), p(q), p(s), p(o), 0, 8, 64, None) == 0

@@ -194,3 +194,46 @@ def test_oracle_matches_reference_kernels_fixture(oracle):
     ulp = np.spacing(np.abs(ref).astype(np.float16)).astype(np.float32)[ok]
     assert (d <= ulp).all()
     assert (out.view(np.uint16) != ref.view(np.uint16))[ok].mean() < 0.02
+
+
+# ------------------------------------------------------------------ M <= 4 branch (weight-only GEMV)
+def test_eetq_layout_matches_reference_packer(oracle):
+    """eetq_preprocess / eetq_quant_weights vs the reference's own cutlass_preprocessors.cc (compiled unmodified,
+    tests/golden/make_gemv_golden.py cpu): processed bytes, plain codes and scales bit-exact, incl. an all-zero
+    channel (0/0 -> code 127 through std::min/std::max) and an exact zero."""
+    g = np.load(GOLD / "eetq_layout.npz")
+    assert np.array_equal(oracle.eetq_preprocess(g["q_kn"]), g["processed"])
+    assert np.array_equal(oracle.eetq_unprocess(g["processed"]), g["q_kn"])
+    qw, sc = oracle.eetq_quant_weights(g["W_t"])
+    assert np.array_equal(sc.view(np.uint16), g["scales"].view(np.uint16))
+    assert np.array_equal(oracle.eetq_unprocess(qw), g["codes"])
+    assert np.array_equal(qw, g["processed_codes"])
+
+
+def test_gemv_oracle_matches_reference_kernel_fixture(oracle):
+    """mixq_oracle_gemv_w8a16 vs outputs of the reference's weight_only_batched_gemv kernels run on a B200
+    (tests/golden/ref_gemv_b200.npz, make_gemv_golden.py gpu): bit-exact (fp16 chains + fp32 tree restated)."""
+    import sys
+    sys.path.insert(0, str(GOLD))
+    import make_gemv_golden as G
+    p = GOLD / "ref_gemv_b200.npz"
+    if not p.exists():
+        pytest.skip("ref_gemv_b200.npz not captured yet")
+    g = np.load(p)
+    for i, (M, N, K, seed) in enumerate(G.GEMV_CASES):
+        A, W_t = G.gemv_case(M, N, K, seed)
+        qw, sc = oracle.eetq_quant_weights(W_t)
+        assert G.crc(A, qw, sc) == g[f"crc{i}"], "inputs regenerated from the seed differ from the captured ones"
+        out = oracle.gemv_w8a16(A, qw, sc)
+        assert np.array_equal(out.view(np.uint16), g[f"out{i}"].view(np.uint16)), (i, M, N, K)
+
+
+def test_gemv_oracle_close_to_float64(oracle):
+    rng = np.random.default_rng(3)
+    K, N, M = 2048, 32, 4
+    W_t = (rng.standard_normal((K, N)) * 0.02).astype(np.float16)
+    A = rng.standard_normal((M, K)).astype(np.float16)
+    qw, sc = oracle.eetq_quant_weights(W_t)
+    out = oracle.gemv_w8a16(A, qw, sc).astype(np.float64)
+    ref = A.astype(np.float64) @ (oracle.eetq_unprocess(qw).astype(np.float64) * sc.astype(np.float64)[None, :])
+    assert np.abs(out - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-3
