@@ -11,7 +11,10 @@ SURVEY.md 8f "next #3".  The reference produces the layout in
     weights_scaling_factor  [N]        max_k |W[n,k]| / 127, taken BEFORE the outlier columns are zeroed
     fp_weight               [N, 128]   the outlier columns of W
     fp_ind                  [256]      128 int32 column indices as raw bytes
-    qweight, scales                    EETQ weight-only copy for the M <= 4 branch (not produced here)
+    qweight                 [K, N/2]   EETQ weight-only copy of the UN-zeroed weight for the M <= 4 branch: int8 codes
+                                       of W^T in the interleaved layout of cutlass_preprocessors.cc:497-533 (:437-440)
+    scales                  [N]        its scales, max_k |W[n,k]| / 128 (:441; the plugin is fed weights_scaling_factor
+                                       instead, plugin.py:149 -- kept as the reference has it)
 
 This module needs neither mixlib nor EETQ: their ``int8_matrix_to_half`` / ``int_to_half`` helpers are
 byte reinterpretations (``Tensor.view(torch.float16)``).  The reference hard-codes its activation
@@ -31,38 +34,83 @@ MIXQ_LINEARS = ("attention.qkv", "mlp.gate", "mlp.proj")          # model_config
 ACT_SCALE_KEY = {"attention.qkv": "self_attn.q_proj", "mlp.gate": "mlp.gate_proj", "mlp.proj": "mlp.up_proj"}
 
 
+_PERM16 = (0, 1, 8, 9, 2, 3, 10, 11, 4, 5, 12, 13, 6, 7, 14, 15)     # permute_B_rows_for_mixed_gemm, int8
+
+
 @torch.no_grad()
-def pack_linear_weights(weight: torch.Tensor, act_scale: torch.Tensor, fp_features: int = NUM_OUTLIERS) -> Dict[str, torch.Tensor]:
+def eetq_preprocess(q_kn: torch.Tensor) -> torch.Tensor:
+    """int8 codes of W^T, row-major [K, N] -> the processed tensor EETQ hands to its kernels (same nominal shape):
+    preprocess_weights_for_mixed_gemm with the Sm80 int8 layout (cutlass_preprocessors.cc:497-533): K permuted in
+    groups of 16 (:137-199), transposed (:322-335), channel pairs interleaved in runs of 64 codes (:432-495), +128
+    bias and bytes 1 / 2 of every four swapped (:337-358)."""
+    K, N = q_kn.shape
+    if K % 64 or N % 64:
+        raise ValueError("EETQ layout needs K % 64 == 0 and N % 64 == 0 (cutlass_preprocessors.cc:230,455)")
+    q = q_kn.to(torch.int8).cpu().reshape(K // 16, 16, N)[:, list(_PERM16), :].reshape(K, N)
+    t = q.t().contiguous().reshape(N // 2, 2, K // 64, 64).permute(0, 2, 1, 3).reshape(N // 2, 2 * K)
+    u = (t.to(torch.int16) + 128).to(torch.uint8).reshape(-1, 4)[:, [0, 2, 1, 3]]
+    return u.contiguous().reshape(K, N).view(torch.int8)
+
+
+@torch.no_grad()
+def eetq_quant_weights(weight_t: torch.Tensor):
+    """EETQ.quant_weights(W^T, torch.int8, False) (symmetric_quantize<half, half>, cutlass_preprocessors.cc:581-678):
+    per output channel s = max|w| / 128 in fp32, code = clamp(round_half_away(w / s), -128, 127), then the layout
+    transform.  Returns (processed int8 [K, N], scales fp16 [N])."""
+    w = weight_t.detach().to(torch.float16).cpu().float()
+    s = w.abs().amax(dim=0) * (1.0 / 128.0)
+    x = w / s[None, :]
+    r = torch.where(x >= 0, torch.floor(x + 0.5), torch.ceil(x - 0.5))
+    q = torch.nan_to_num(r.clamp(-128, 127), nan=127.0).to(torch.int8)     # std::min(127.f, NaN) keeps 127.f (:639-640)
+    return eetq_preprocess(q), s.to(torch.float16)
+
+
+@torch.no_grad()
+def pack_linear_weights(weight: torch.Tensor, act_scale: torch.Tensor, fp_features: int = NUM_OUTLIERS,
+                        with_qweight: bool = False) -> Dict[str, torch.Tensor]:
     """One linear, reference order of operations (weight is fp16 [N, K]); returns typed tensors
-    (W8 int8 [N,K], scale_b fp16 [N], fp_weight fp16 [N,128], ind int32 [128])."""
+    (W8 int8 [N,K], scale_b fp16 [N], fp_weight fp16 [N,128], ind int32 [128]) and, with_qweight, the weight-only
+    pair (qweight int8 [K,N] processed, scales fp16 [N]) taken from the un-zeroed weight (:437-441 run before :453)."""
     w = weight.detach().to(torch.float16).cpu().clone()
     scale_b = (torch.max(torch.abs(w), dim=1)[0].unsqueeze(1) / 127).to(torch.float16).reshape(w.shape[0])
+    extra = {}
+    if with_qweight:
+        extra["qweight"], extra["scales"] = eetq_quant_weights(w.t().contiguous())
     ind = torch.sort(act_scale.detach().float().cpu(), stable=True)[1][-fp_features:]
     fp_weight = w[:, ind].contiguous()
     w[:, ind] = 0
     # CPU fp16 divide (computed in fp32, rounded to fp16), round-half-even, clamp: to_quantized_weight :303-308
     W8 = (w / scale_b[:, None]).round().clamp(-128, 127).nan_to_num(0).to(torch.int8)
-    return {"W8": W8, "scale_b": scale_b, "fp_weight": fp_weight, "ind": ind.to(torch.int32)}
+    return {"W8": W8, "scale_b": scale_b, "fp_weight": fp_weight, "ind": ind.to(torch.int32), **extra}
 
 
 def to_checkpoint_tensors(packed: Mapping[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """Typed tensors -> the fp16-typed containers the reference stores (plugin.py:99-111)."""
-    return {
+    out = {
         "weight": packed["W8"].contiguous().view(torch.float16),
         "weights_scaling_factor": packed["scale_b"].contiguous(),
         "fp_weight": packed["fp_weight"].contiguous(),
         "fp_ind": packed["ind"].to(torch.int32).contiguous().view(torch.float16),
     }
+    if "qweight" in packed:
+        out["qweight"] = packed["qweight"].contiguous().view(torch.float16)      # [K, N/2], mixlib.int8_matrix_to_half
+        out["scales"] = packed["scales"].contiguous()
+    return out
 
 
 def from_checkpoint_tensors(t: Mapping[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """fp16-typed containers -> typed tensors."""
-    return {
+    out = {
         "W8": t["weight"].contiguous().view(torch.int8),
         "scale_b": t["weights_scaling_factor"].reshape(-1),
         "fp_weight": t["fp_weight"],
         "ind": t["fp_ind"].contiguous().view(torch.int32),
     }
+    if "qweight" in t:
+        out["qweight"] = t["qweight"].contiguous().view(torch.int8)
+        if "scales" in t:
+            out["scales"] = t["scales"].reshape(-1)
+    return out
 
 
 def save_checkpoint(path, layers: Iterable[Mapping[str, Mapping[str, torch.Tensor]]], config: Optional[dict] = None,
@@ -96,10 +144,10 @@ def load_checkpoint(path, rank: int = 0) -> Dict[int, Dict[str, Dict[str, torch.
             if len(parts) < 6 or parts[0] != "transformer" or parts[1] != "layers":
                 continue
             lin, name = ".".join(parts[3:5]), parts[5]
-            if lin in MIXQ_LINEARS and name in ("weight", "weights_scaling_factor", "fp_weight", "fp_ind"):
+            if lin in MIXQ_LINEARS and name in ("weight", "weights_scaling_factor", "fp_weight", "fp_ind", "qweight", "scales"):
                 raw.setdefault((int(parts[2]), lin), {})[name] = f.get_tensor(key)
     for (i, lin), t in raw.items():
-        if len(t) == 4:
+        if all(k in t for k in ("weight", "weights_scaling_factor", "fp_weight", "fp_ind")):
             layers.setdefault(i, {})[lin] = from_checkpoint_tensors(t)
     return layers
 
@@ -107,5 +155,6 @@ def load_checkpoint(path, rank: int = 0) -> Dict[int, Dict[str, Dict[str, torch.
 def load_into(module, packed: Mapping[str, torch.Tensor]):
     """Fill a ``MixQLinear`` from a typed packed dict."""
     dev = module.weight.device
+    qw = packed.get("qweight")
     return module.load_packed(packed["W8"].to(dev), packed["scale_b"].to(dev), packed["fp_weight"].to(dev),
-                              packed["ind"].to(dev))
+                              packed["ind"].to(dev), qweight=qw.to(dev) if qw is not None else None)

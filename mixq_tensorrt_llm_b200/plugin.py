@@ -14,8 +14,8 @@ Differences from the reference, on purpose:
     row-parallel (quantization/quantize.py:342).  Here ``parallel_mode="column"`` needs no
     collective (optionally all-gathers when gather_output) and ``parallel_mode="row"`` does the
     single all-reduce of the partial sums.
-  * the M<=4 weight-only branch is not taken; ``qweight`` is accepted and
-    ignored.
+  * the M<=4 weight-only branch (TsinghuaMixQPlugin.cpp:472) is taken when ``qweight`` has been loaded; an empty
+    ``qweight`` (a NULL plugin input 5) keeps the mixed path for every M.
 """
 from __future__ import annotations
 
@@ -112,7 +112,7 @@ class MixQLinear(torch.nn.Module):
       weight [N/tp, K/2]      int8 codes, two per fp16 slot  (model_config_utils.py:460-466)
       fp_weight [N/tp, 128]   outlier weight columns          (:452)
       fp_ind [256]            128 int32 indices as raw bytes  (:455-457)
-      qweight [K, N/tp/2]     weight-only layout for M<=4     (:437-441; unused here)
+      qweight [K, N/tp/2]     weight-only layout for M<=4     (:437-441; optional, see load_packed)
       weights_scaling_factor [N/tp]                            (:429-430)
     """
 
@@ -136,7 +136,7 @@ class MixQLinear(torch.nn.Module):
         self.register_buffer("weight", torch.zeros(N, K // 2, **h))
         self.register_buffer("fp_weight", torch.zeros(N, NUM_OUTLIERS, **h))
         self.register_buffer("fp_ind", torch.zeros(NUM_OUTLIERS * 2, **h))
-        self.register_buffer("qweight", torch.zeros(0, **h))  # kept for layout parity; M<=4 branch not built
+        self.register_buffer("qweight", torch.zeros(0, **h))  # empty = NULL plugin input 5: mixed path for every M
         self.register_buffer("weights_scaling_factor", torch.zeros(N, **h))
         if bias:
             self.register_buffer("bias", torch.zeros(N, dtype=dtype or torch.float16, device=device))
@@ -156,8 +156,12 @@ class MixQLinear(torch.nn.Module):
 
     @torch.no_grad()
     def load_packed(self, W8: torch.Tensor, scale_b: torch.Tensor, fp_weight: torch.Tensor, ind: torch.Tensor,
-                    bias: Optional[torch.Tensor] = None) -> "MixQLinear":
-        """Fill the buffers from typed tensors (int8 [N,K], fp16 [N], fp16 [N,128], int32 [128])."""
+                    bias: Optional[torch.Tensor] = None, qweight: Optional[torch.Tensor] = None) -> "MixQLinear":
+        """Fill the buffers from typed tensors (int8 [N,K], fp16 [N], fp16 [N,128], int32 [128]); ``qweight`` is the
+        processed EETQ tensor (int8 [K,N]): with it, calls with M <= 4 take the weight-only branch like the reference
+        (TsinghuaMixQPlugin.cpp:472), scaled by weights_scaling_factor as plugin.py:149 wires it."""
+        if qweight is not None:
+            self.qweight = qweight.contiguous().view(torch.float16).reshape(self.in_features, self.out_features // 2).to(self.weight.device)
         self.weight.copy_(W8.contiguous().view(torch.float16))
         self.weights_scaling_factor.copy_(scale_b.reshape(-1))
         self.fp_weight.copy_(fp_weight)

@@ -74,3 +74,26 @@ def test_load_into_module():
     m = ck.load_into(MixQLinear(256, 24), p)
     assert torch.equal(m.weight.view(torch.int8).view(24, 256), p["W8"])
     assert torch.equal(m.fp_ind.view(torch.int32), p["ind"])
+
+
+def test_eetq_pair_matches_reference_packer_and_roundtrips(tmp_path, oracle):
+    """checkpoint.eetq_preprocess / eetq_quant_weights (torch, product side) vs the reference packer's golden vectors
+    (tests/golden/eetq_layout.npz) and vs the oracle's numpy restatement; qweight/scales survive save -> load."""
+    import numpy as np
+    from pathlib import Path
+    from mixq_tensorrt_llm_b200 import checkpoint as C
+    g = np.load(Path(__file__).resolve().parent / "golden" / "eetq_layout.npz")
+    assert np.array_equal(C.eetq_preprocess(torch.from_numpy(g["q_kn"])).numpy(), g["processed"])
+    qw, sc = C.eetq_quant_weights(torch.from_numpy(g["W_t"]))
+    assert np.array_equal(qw.numpy(), g["processed_codes"])
+    assert np.array_equal(sc.numpy().view(np.uint16), g["scales"].view(np.uint16))
+    torch.manual_seed(0)
+    W = (torch.randn(128, 256) * 0.02).half()
+    act = torch.rand(256)
+    p = C.pack_linear_weights(W, act, with_qweight=True)
+    oq, osc = oracle.eetq_quant_weights(W.t().contiguous().numpy())
+    assert np.array_equal(p["qweight"].numpy(), oq) and np.array_equal(p["scales"].numpy().view(np.uint16), osc.view(np.uint16))
+    C.save_checkpoint(tmp_path, [{"attention.qkv": p}])
+    back = C.load_checkpoint(tmp_path)[0]["attention.qkv"]
+    assert torch.equal(back["qweight"].reshape(-1), p["qweight"].reshape(-1)) and torch.equal(back["scales"], p["scales"])
+    assert torch.equal(back["W8"].reshape(-1), p["W8"].reshape(-1))

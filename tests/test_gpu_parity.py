@@ -493,3 +493,25 @@ def test_gemv_w8a16_rejects_bad_shapes(B, lib):
     assert lib.mixq_gemv_w8a16(p(a), p(q), p(s), p(o), 2, 8, 32, None) == -4     # K % 64
     assert lib.mixq_gemv_w8a16(None, p(q), p(s), p(o), 2, 8, 64, None) == -1
     assert lib.mixq_gemv_w8a16(p(a), p(q), p(s), p(o), 0, 8, 64, None) == 0
+
+
+def test_plugin_module_takes_weight_only_branch_with_qweight(B, oracle):
+    """MixQLinear -> C plugin handle -> MixQPlugin::enqueue: with qweight loaded a call with M <= 4 goes through the
+    weight-only GEMV (scaled by weights_scaling_factor = plugin input 6, as plugin.py:149 wires it); M = 5 is mixed."""
+    from mixq_tensorrt_llm_b200.plugin import MixQLinear
+    N, K = 512, 4096
+    lin = oracle.synth_linear(N, K, oracle.load_act_scales("Llama-2-7b/self_attn.q_proj"))
+    rng = np.random.default_rng(4)
+    W_t = (rng.standard_normal((K, N)) * 0.02).astype(np.float16)
+    qw, _ = oracle.eetq_quant_weights(W_t)
+    mod = MixQLinear(K, N, device=DEV)
+    mod.load_packed(*(_t(lin[k]) for k in ("W8", "scale_b", "fp_weight", "ind")), qweight=_t(qw))
+    A = oracle.synth_activations(2, lin["act_scale"], seed=77)
+    y = mod(_t(A))
+    torch.cuda.synchronize()
+    want = oracle.gemv_w8a16(A, qw, lin["scale_b"])
+    assert np.array_equal(y.cpu().numpy().view(np.uint16), want.view(np.uint16))
+    A5 = oracle.synth_activations(5, lin["act_scale"], seed=78)
+    y5 = mod(_t(A5)).cpu().numpy()
+    r = oracle.forward(A5, lin["W8"], lin["scale_b"], lin["fp_weight"], lin["ind"], return_parts=True)
+    _assert_mixed_close(y5, r["out"], r["out0"], "M=5 mixed")
