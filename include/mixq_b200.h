@@ -97,6 +97,24 @@ size_t mixq_workspace_size(int64_t M, int64_t N, int64_t K);
 int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace,
                  size_t workspace_bytes, unsigned flags, void* stream);
 
+/* The same call with a fused epilogue:
+ *   y   = fp16( act( fma(float(acc), sb*sa, float(out0)) ) )     act in fp32 BEFORE the rounding, as the reference's
+ *                                                                 LinearCombinationDequantSilu (linear_combination_dequant.h:167-272,
+ *                                                                 silu(x) = x / (1 + expf(-x)), fast-math build)
+ *   Out = bias ? fp16( float(y) + float(bias[n]) ) : y           the bias add the reference does after the plugin
+ *                                                                 (plugin.py:158-160; MixQ/src/mixquant/modules/linear.py:368-369)
+ * epi == NULL is mixq_enqueue.  Also applied on the M <= 4 weight-only branch. */
+enum { MIXQ_ACT_NONE = 0, MIXQ_ACT_SILU = 1 };
+typedef struct mixq_epilogue {
+    const void* bias; /* fp16 [N] device pointer, or NULL */
+    int activation;   /* MIXQ_ACT_*                        */
+} mixq_epilogue;
+int mixq_enqueue_ex(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace,
+                    size_t workspace_bytes, const mixq_epilogue* epi, unsigned flags, void* stream);
+int mixq_gemm_dequant_ex(const void* A8, const void* W8, const void* scale_a, const void* scale_b,
+                         const void* fp_A, const void* fp_weight, void* Out, int64_t M, int64_t N,
+                         int64_t K, const mixq_epilogue* epi, void* stream);
+
 /* Stage 1 alone. Replaces int8quant (kernel/i8gemm.cu:66-107,139-150) and
  * ExtractOutliersAndSetToZeros (kernel/i8gemm.cu:198-244) in one pass over A.
  *   sa[m]   = hdiv(max_k |A[m,k]|, 127)

@@ -18,7 +18,8 @@ FLAG_FORCE_MIXED = 2
 
 # every symbol include/mixq_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_enqueue",
+    "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_enqueue", "mixq_enqueue_ex",
+    "mixq_gemm_dequant_ex",
     "mixq_quant_extract", "mixq_rmsnorm_quant_extract", "mixq_gemv_w8a16", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
     "mixq_host_scratch_size", "mixq_linear_host",
     "mixq_allreduce_staging_size", "mixq_allreduce_counter_size", "mixq_enqueue_allreduce", "mixq_gemm_dequant_allreduce",
@@ -41,6 +42,13 @@ class Tensors(ctypes.Structure):
 
 
 MAX_RANKS = 8
+ACT_NONE, ACT_SILU = 0, 1
+
+
+class Epilogue(ctypes.Structure):
+    """struct mixq_epilogue"""
+    _fields_ = [("bias", ctypes.c_void_p), ("activation", ctypes.c_int)]
+
 
 
 class PeerGroup(ctypes.Structure):
@@ -71,6 +79,10 @@ def load() -> ctypes.CDLL:
     L.mixq_workspace_size.argtypes = [i64, i64, i64]
     L.mixq_enqueue.restype = ci
     L.mixq_enqueue.argtypes = [ctypes.POINTER(Tensors), i64, i64, i64, vp, sz, u32, vp]
+    L.mixq_enqueue_ex.restype = ci
+    L.mixq_enqueue_ex.argtypes = [ctypes.POINTER(Tensors), i64, i64, i64, vp, sz, ctypes.POINTER(Epilogue), u32, vp]
+    L.mixq_gemm_dequant_ex.restype = ci
+    L.mixq_gemm_dequant_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, ctypes.POINTER(Epilogue), vp]
     L.mixq_quant_extract.restype = ci
     L.mixq_quant_extract.argtypes = [vp, i64, i64, vp, ci, vp, vp, vp, u32, vp]
     L.mixq_rmsnorm_quant_extract.restype = ci
@@ -168,12 +180,17 @@ def make_tensors(A, W8, scale_b, fp_weight, ind, Out, q_weight=None, scaling_fac
 
 
 def enqueue(A, W8, scale_b, fp_weight, ind, Out, workspace, flags: int = 0, stream=None, q_weight=None,
-            scaling_factors=None) -> None:
+            scaling_factors=None, bias=None, activation: int = 0) -> None:
     """mixq_enqueue on torch CUDA tensors (A [M,K] fp16 contiguous, Out [M,N] fp16).  With q_weight / scaling_factors
     (the EETQ pair) a call with M <= 4 takes the weight-only branch, as the reference plugin does."""
     M, K = A.shape
     N = Out.shape[-1]
     t = make_tensors(A, W8, scale_b, fp_weight, ind, Out, q_weight, scaling_factors)
+    if bias is not None or activation:
+        e = Epilogue(bias.data_ptr() if bias is not None else None, int(activation))
+        check(load().mixq_enqueue_ex(ctypes.byref(t), M, N, K, _ptr(workspace), workspace.numel() * workspace.element_size(),
+                                     ctypes.byref(e), flags, _stream(stream)), "mixq_enqueue_ex")
+        return
     check(load().mixq_enqueue(ctypes.byref(t), M, N, K, _ptr(workspace), workspace.numel() * workspace.element_size(),
                               flags, _stream(stream)), "mixq_enqueue")
 
@@ -193,9 +210,15 @@ def rmsnorm_quant_extract(X, gamma, eps, ind, A8, scale_a, fp_A, Y=None, flags: 
           "mixq_rmsnorm_quant_extract")
 
 
-def gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, stream=None, workspace=None) -> None:
+def gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, stream=None, workspace=None, bias=None,
+                 activation: int = 0) -> None:
     M, K = A8.shape
     N = W8.shape[0]
+    if bias is not None or activation:
+        e = Epilogue(bias.data_ptr() if bias is not None else None, int(activation))
+        check(load().mixq_gemm_dequant_ex(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A), _ptr(fp_weight),
+                                          _ptr(Out), M, N, K, ctypes.byref(e), _stream(stream)), "mixq_gemm_dequant_ex")
+        return
     if workspace is None:
         check(load().mixq_gemm_dequant(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A), _ptr(fp_weight),
                                        _ptr(Out), M, N, K, _stream(stream)), "mixq_gemm_dequant")

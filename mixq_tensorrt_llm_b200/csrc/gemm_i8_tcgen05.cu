@@ -76,10 +76,10 @@ struct GemmTraits {
     static_assert(kTmemColsRaw <= 512, "TMEM has 512 columns");
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
     static_assert(kLoadN % 8 == 0 && kBBytes % 1024 == 0, "W tile must be whole 8-row swizzle groups");
-    // dynamic smem: ring | sb staging (2 x BLOCK_N floats) | barriers | tmem ptr  (+1024 alignment slack)
+    // dynamic smem: ring | sb and bias staging (2 x 2 x BLOCK_N floats) | barriers | tmem ptr  (+1024 alignment slack)
     static constexpr int kNumBarriers = 2 * STAGES + 2 * ACC_STAGES;
     static constexpr size_t kSmemBytes =
-        1024 + static_cast<size_t>(STAGES) * kStageBytes + 2 * BLOCK_N * sizeof(float) + kNumBarriers * 8 + 16;
+        1024 + static_cast<size_t>(STAGES) * kStageBytes + 4 * BLOCK_N * sizeof(float) + kNumBarriers * 8 + 16;
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
@@ -97,13 +97,36 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int m_tiles, int n_til
     return {first_m + r % gsz, r / gsz};
 }
 
+// Optional fused epilogue: activation in fp32 BEFORE the output rounding, as the reference's
+// LinearCombinationDequantSilu does (kernel/symmetric/epilogue/thread/linear_combination_dequant.h:167-272,
+// silu(x) = x / (1 + expf(-x)); the reference extension is built with --use_fast_math, hence the fast intrinsics),
+// then the bias added to the fp16 result with a second rounding, as the reference adds it outside the kernel
+// (plugin.py:158-160, MixQ/src/mixquant/modules/linear.py:368-369).
+struct EpiArgs {
+    const __half* bias;   // fp16 [N] or null
+    int act;              // MIXQ_ACT_NONE / MIXQ_ACT_SILU
+};
+__device__ __forceinline__ __half2 epi_finish(float r0, float r1, const float* bias_s, const EpiArgs& e) {
+    if (e.act == MIXQ_ACT_NONE && e.bias == nullptr) return __floats2half2_rn(r0, r1);   // the plugin's epilogue (uniform branch)
+    if (e.act == MIXQ_ACT_SILU) {
+        r0 = __fdividef(r0, 1.0f + __expf(-r0));
+        r1 = __fdividef(r1, 1.0f + __expf(-r1));
+    }
+    __half2 h = __floats2half2_rn(r0, r1);
+    if (e.bias) {
+        const float2 f = __half22float2(h);
+        h = __floats2half2_rn(f.x + bias_s[0], f.y + bias_s[1]);
+    }
+    return h;
+}
+
 template <class T>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_w8,
                          const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fw,
                          const __half* __restrict__ scale_a, const __half* __restrict__ scale_b,
                          __half* __restrict__ Out, int M, int N, int K, int has_outlier, int m_tiles, int n_tiles,
-                         int group_m) {
+                         int group_m, EpiArgs epi) {
     constexpr int BLOCK_N = T::kBlockN;
     constexpr int CTA = T::kCta;
     extern __shared__ uint8_t smem_raw[];
@@ -111,7 +134,8 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* ring = smem;
     float* sb_s = reinterpret_cast<float*>(ring + static_cast<size_t>(T::kStages) * T::kStageBytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sb_s + 2 * BLOCK_N);
+    float* bias_sm = sb_s + 2 * BLOCK_N;   // staged bias, double-buffered like sb_s
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sb_s + 4 * BLOCK_N);
     uint64_t* empty_bar = full_bar + T::kStages;
     uint64_t* tmem_full_bar = empty_bar + T::kStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + T::kAccStages;
@@ -270,8 +294,11 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
             const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
             const int n0 = tc.n_blk * BLOCK_N;
             float* sbt = sb_s + (local_tile & 1) * BLOCK_N;
-            for (int j = et; j < BLOCK_N; j += kNumEpilogueThreads)
+            float* bt = bias_sm + (local_tile & 1) * BLOCK_N;
+            for (int j = et; j < BLOCK_N; j += kNumEpilogueThreads) {
                 sbt[j] = (n0 + j < N) ? __half2float(scale_b[n0 + j]) : 0.0f;
+                bt[j] = (epi.bias && n0 + j < N) ? __half2float(epi.bias[n0 + j]) : 0.0f;
+            }
             const int gm = m0 + row;
             const bool row_ok = gm < M;
             const float sa_f = row_ok ? __half2float(scale_a[gm]) : 0.0f;
@@ -302,7 +329,7 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
                     const float2 of = __half22float2(o);
                     const float r0 = __fmaf_rn(__int2float_rn(static_cast<int>(vi[j])), p0, of.x);
                     const float r1 = __fmaf_rn(__int2float_rn(static_cast<int>(vi[j + 1])), p1, of.y);
-                    const __half2 r = __floats2half2_rn(r0, r1);
+                    const __half2 r = epi_finish(r0, r1, bt + c * 32 + j, epi);
                     packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&r);
                 }
                 if (row_ok) {
@@ -367,7 +394,7 @@ struct StashTraits {
     static constexpr int kStashBytes = kBlockM * kBlockN * 2;  // fp16 outlier product of this CTA's 128 rows
     static constexpr int kNumBarriers = 2 * STAGES + 8;
     static constexpr size_t kSmemBytes = 1024 + static_cast<size_t>(STAGES) * kStageBytes + kStashBytes +
-                                         2 * kBlockN * sizeof(float) + kNumBarriers * 8 + 16;
+                                         4 * kBlockN * sizeof(float) + kNumBarriers * 8 + 16;
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
@@ -377,7 +404,7 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
                                const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fw,
                                const __half* __restrict__ scale_a, const __half* __restrict__ scale_b,
                                __half* __restrict__ Out, int M, int N, int K, int has_outlier, int m_tiles,
-                               int n_tiles, int group_m) {
+                               int n_tiles, int group_m, EpiArgs epi) {
     constexpr int BLOCK_N = T::kBlockN;
     constexpr int CTA = T::kCta;
     extern __shared__ uint8_t smem_raw[];
@@ -385,7 +412,8 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
     uint8_t* ring = smem;
     uint4* stash = reinterpret_cast<uint4*>(ring + static_cast<size_t>(T::kStages) * T::kStageBytes);
     float* sb_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stash) + T::kStashBytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sb_s + 2 * BLOCK_N);
+    float* bias_sm = sb_s + 2 * BLOCK_N;   // staged bias, double-buffered like sb_s
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sb_s + 4 * BLOCK_N);
     uint64_t* empty_bar = full_bar + T::kStages;
     uint64_t* tmem_full_bar = empty_bar + T::kStages;  // [2] int32 accumulators of buffer b complete
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2] epilogue has read buffer b's int32 accumulators
@@ -565,7 +593,9 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
             const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
             const int n0 = tc.n_blk * BLOCK_N;
             float* sbt = sb_s + b * BLOCK_N;
+            float* bt = bias_sm + b * BLOCK_N;
             sbt[et] = (n0 + et < N) ? __half2float(scale_b[n0 + et]) : 0.0f;
+            bt[et] = (epi.bias && n0 + et < N) ? __half2float(epi.bias[n0 + et]) : 0.0f;
             const int gm = m0 + row;
             const bool row_ok = gm < M;
             const float sa_f = row_ok ? __half2float(scale_a[gm]) : 0.0f;
@@ -637,7 +667,7 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
                         const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&fw[q]));
                         const float r0 = __fmaf_rn(__int2float_rn(static_cast<int>(v[j])), p0, of.x);
                         const float r1 = __fmaf_rn(__int2float_rn(static_cast<int>(v[j + 1])), p1, of.y);
-                        const __half2 r = __floats2half2_rn(r0, r1);
+                        const __half2 r = epi_finish(r0, r1, bt + col0 + c * 32 + j, epi);
                         packed[q] = *reinterpret_cast<const uint32_t*>(&r);
                     }
                     if (row_ok && n0 + col0 + c * 32 + g * 8 + 8 <= N)
@@ -775,7 +805,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                                  __half* __restrict__ Out, int M, int N, int K, int has_outlier, int m_tiles,
                                  int n_tiles, int group_m, int stream_k, uint4* __restrict__ sk_slots,
                                  uint32_t* __restrict__ sk_flags,
-                                 const __grid_constant__ std::conditional_t<AR, ArParams, ArNone> ar) {
+                                 const __grid_constant__ std::conditional_t<AR, ArParams, ArNone> ar, EpiArgs epi) {
     constexpr int BLOCK_N = T::kBlockN;
     constexpr int CTA = T::kCta;
     extern __shared__ uint8_t smem_raw[];
@@ -783,7 +813,8 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
     uint8_t* ring = smem;
     uint4* stash = reinterpret_cast<uint4*>(ring + static_cast<size_t>(T::kStages) * T::kStageBytes);
     float* sb_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stash) + T::kStashBytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sb_s + 2 * BLOCK_N);
+    float* bias_sm = sb_s + 2 * BLOCK_N;   // staged bias, double-buffered like sb_s
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sb_s + 4 * BLOCK_N);
     uint64_t* empty_bar = full_bar + T::kStages;
     uint64_t* tmem_full_bar = empty_bar + T::kStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -1002,7 +1033,10 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
             float* sbt = sb_s + b * BLOCK_N;
             float sa_f = 0.0f;
             if (finisher) {
-                if (et < BLOCK_N) sbt[et] = (n0 + et < N) ? __half2float(scale_b[n0 + et]) : 0.0f;
+                if (et < BLOCK_N) {
+                    sbt[et] = (n0 + et < N) ? __half2float(scale_b[n0 + et]) : 0.0f;
+                    bias_sm[b * BLOCK_N + et] = (epi.bias && n0 + et < N) ? __half2float(epi.bias[n0 + et]) : 0.0f;
+                }
                 sa_f = gm < M ? __half2float(scale_a[gm]) : 0.0f;
                 // the previous tile's TMA stores must have finished READING this warp's tiles
                 if (lane == 0) ptx::tma_store_wait_read<0>();
@@ -1135,7 +1169,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                             const float2 of = __half22float2(*reinterpret_cast<const __half2*>(&fw[q]));
                             const float r0 = __fmaf_rn(__int2float_rn(static_cast<int>(v[j])), p0, of.x);
                             const float r1 = __fmaf_rn(__int2float_rn(static_cast<int>(v[j + 1])), p1, of.y);
-                            const __half2 r = __floats2half2_rn(r0, r1);
+                            const __half2 r = epi_finish(r0, r1, bias_sm + b * BLOCK_N + col0 + c * 32 + j, epi);
                             packed[q] = *reinterpret_cast<const uint32_t*>(&r);
                         }
                         *tp = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -1424,7 +1458,7 @@ struct IsStreamK<StreamKTraits<CTA, STAGES, BLOCK_N>> : std::true_type {};
 template <class T>
 int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl,
-               void* sk_ws = nullptr, int stream_k = 0, const mixq_peer_group* pg = nullptr) {
+               void* sk_ws = nullptr, int stream_k = 0, const mixq_peer_group* pg = nullptr, EpiArgs epi = EpiArgs{nullptr, 0}) {
     const DeviceInfo& dev = device_info();
     CUtensorMap tm_a8, tm_w8, tm_fa, tm_fw;
     int rc;
@@ -1520,7 +1554,7 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
                                    static_cast<const __half*>(scale_a), static_cast<const __half*>(scale_b),
                                    static_cast<__half*>(Out), static_cast<int>(M), static_cast<int>(N),
                                    static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m, 0,
-                                   static_cast<uint4*>(nullptr), static_cast<uint32_t*>(nullptr), ar);
+                                   static_cast<uint4*>(nullptr), static_cast<uint32_t*>(nullptr), ar, EpiArgs{nullptr, 0});
             if (e != cudaSuccess) return set_cuda_error(e, "launch gemm_dequant_allreduce");
             count_launch();
             return MIXQ_OK;
@@ -1533,11 +1567,11 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
         e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, tm_out, static_cast<const __half*>(scale_a),
                                static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M),
                                static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m,
-                               (sk_ws && stream_k) ? 1 : 0, slots, flags, ArNone{0});
+                               (sk_ws && stream_k) ? 1 : 0, slots, flags, ArNone{0}, epi);
     } else {
         e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, static_cast<const __half*>(scale_a),
                                static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M),
-                               static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m);
+                               static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m, epi);
     }
     if (e != cudaSuccess) return set_cuda_error(e, "launch gemm_dequant");
     count_launch();
@@ -1556,8 +1590,10 @@ size_t streamk_workspace_bytes() { return kStreamKFlagBytes + static_cast<size_t
 
 int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                         const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
-                        bool pdl, void* sk_ws, size_t sk_ws_bytes, bool sk_flags_clean) {
+                        bool pdl, void* sk_ws, size_t sk_ws_bytes, bool sk_flags_clean, const void* bias, int act) {
     if (M == 0 || N == 0) return MIXQ_OK;
+    if (act != MIXQ_ACT_NONE && act != MIXQ_ACT_SILU) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: unknown activation");
+    const EpiArgs epi{static_cast<const __half*>(bias), act};
     if (!A8 || !W8 || !scale_a || !scale_b || !Out) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: null pointer");
     if ((fp_A == nullptr) != (fp_weight == nullptr))
         return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: fp_A and fp_weight must both be given or both be null");
@@ -1601,32 +1637,32 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
         }
     }
     if (cfg == kCfg2CtaN192Tma)  // 256x192 pair tiles: more tiles per wave for decode-sized M
-        return launch_cfg<StreamKTraits<2, 5, 192>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0);
+        return launch_cfg<StreamKTraits<2, 5, 192>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
     if (cfg == kCfg2CtaN256Tma)  // the stream-K kernel with whole tiles: TMA-store epilogue, no scratch needed
-        return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0);
+        return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
     if (cfg == kCfg2CtaN256StreamK) {
         if (!sk_ok) return set_error(MIXQ_ERR_WORKSPACE, "gemm_dequant: stream-K needs mixq_gemm_workspace_size() bytes of workspace");
         if (!sk_flags_clean) {
             cudaError_t e = cudaMemsetAsync(sk_ws, 0, kStreamKFlagBytes, stream);
             if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(stream-K flags)");
         }
-        return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, sk_ws, 1);
+        return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, sk_ws, 1, nullptr, epi);
     }
     switch (cfg) {
         case kCfgN128x2:
-            return launch_cfg<GemmTraits<1, 128, 2, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+            return launch_cfg<GemmTraits<1, 128, 2, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
         case kCfgN256x1:
-            return launch_cfg<GemmTraits<1, 256, 1, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+            return launch_cfg<GemmTraits<1, 256, 1, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
         case kCfgN64x2:
-            return launch_cfg<GemmTraits<1, 64, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+            return launch_cfg<GemmTraits<1, 64, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
         case kCfg2CtaN256x1:
-            return launch_cfg<GemmTraits<2, 256, 1, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+            return launch_cfg<GemmTraits<2, 256, 1, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
         case kCfg2CtaN128x2:
-            return launch_cfg<GemmTraits<2, 128, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+            return launch_cfg<GemmTraits<2, 128, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
         case kCfg2CtaN256Stash:
-            return launch_cfg<StashTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+            return launch_cfg<StashTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
         case kCfgN256Stash:
-            return launch_cfg<StashTraits<1, 3>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl);
+            return launch_cfg<StashTraits<1, 3>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
         default:
             return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: unknown config id");
     }

@@ -45,7 +45,8 @@ __device__ __forceinline__ void cvt4(uint32_t w, __half2& lo, __half2& hi) {
 template <int M>
 __global__ void __launch_bounds__(kGemvThreads, (M == 1 ? 4 : 3))
 mixq_gemv_w8a16_kernel(const __half* __restrict__ in, const uint8_t* __restrict__ qweight,
-                       const __half* __restrict__ scales, __half* __restrict__ out, int N, int K, int groups) {
+                       const __half* __restrict__ scales, __half* __restrict__ out, int N, int K, int groups,
+                       const __half* __restrict__ bias, int act) {
     // Persistent CTAs stride over the groups of four output channels.  The weights of step s+1 (two 4 KB passes over
     // the group's two interleaved rows, possibly of the NEXT group) are in flight while step s is being multiplied.
     __shared__ float sm[2][kGemvThreads / 32][M * 4];
@@ -153,7 +154,12 @@ mixq_gemv_w8a16_kernel(const __half* __restrict__ in, const uint8_t* __restrict_
             float v = 0.0f;
 #pragma unroll
             for (int j = 0; j < kGemvThreads / 32; ++j) v += sm[par][j][t];
-            out[static_cast<size_t>(t >> 2) * N + n0 + (t & 3)] = __float2half_rn(v);
+            // optional fused epilogue, same convention as the GEMM kernels: activation in fp32 before the rounding,
+            // bias added to the fp16 result
+            if (act == MIXQ_ACT_SILU) v = __fdividef(v, 1.0f + __expf(-v));
+            __half h = __float2half_rn(v);
+            if (bias) h = __float2half_rn(__half2float(h) + __half2float(bias[n0 + (t & 3)]));
+            out[static_cast<size_t>(t >> 2) * N + n0 + (t & 3)] = h;
         }
     }
 }
@@ -161,7 +167,7 @@ mixq_gemv_w8a16_kernel(const __half* __restrict__ in, const uint8_t* __restrict_
 }  // namespace
 
 int launch_gemv_w8a16(const void* A, const void* q_weight, const void* scales, void* Out, int64_t M, int64_t N,
-                      int64_t K, cudaStream_t stream) {
+                      int64_t K, cudaStream_t stream, const void* bias, int act) {
     if (M == 0 || N == 0) return MIXQ_OK;
     if (!A || !q_weight || !scales || !Out) return set_error(MIXQ_ERR_BAD_ARG, "gemv_w8a16: null pointer");
     if (M < 0 || M > 4) return set_error(MIXQ_ERR_UNSUPPORTED, "gemv_w8a16: the weight-only branch serves 1 <= M <= 4");
@@ -181,10 +187,10 @@ int launch_gemv_w8a16(const void* A, const void* q_weight, const void* scales, v
     __half* o = static_cast<__half*>(Out);
     const int n = static_cast<int>(N), k = static_cast<int>(K);
     switch (M) {
-        case 1: mixq_gemv_w8a16_kernel<1><<<grid, block, 0, stream>>>(a, q, s, o, n, k, groups); break;
-        case 2: mixq_gemv_w8a16_kernel<2><<<grid, block, 0, stream>>>(a, q, s, o, n, k, groups); break;
-        case 3: mixq_gemv_w8a16_kernel<3><<<grid, block, 0, stream>>>(a, q, s, o, n, k, groups); break;
-        default: mixq_gemv_w8a16_kernel<4><<<grid, block, 0, stream>>>(a, q, s, o, n, k, groups); break;
+        case 1: mixq_gemv_w8a16_kernel<1><<<grid, block, 0, stream>>>(a, q, s, o, n, k, groups, static_cast<const __half*>(bias), act); break;
+        case 2: mixq_gemv_w8a16_kernel<2><<<grid, block, 0, stream>>>(a, q, s, o, n, k, groups, static_cast<const __half*>(bias), act); break;
+        case 3: mixq_gemv_w8a16_kernel<3><<<grid, block, 0, stream>>>(a, q, s, o, n, k, groups, static_cast<const __half*>(bias), act); break;
+        default: mixq_gemv_w8a16_kernel<4><<<grid, block, 0, stream>>>(a, q, s, o, n, k, groups, static_cast<const __half*>(bias), act); break;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "launch gemv_w8a16");

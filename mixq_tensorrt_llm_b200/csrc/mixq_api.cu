@@ -139,6 +139,21 @@ int mixq_gemm_dequant_ws(const void* A8, const void* W8, const void* scale_a, co
 
 int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes,
                  unsigned flags, void* stream) {
+    return mixq_enqueue_ex(t, M, N, K, workspace, workspace_bytes, nullptr, flags, stream);
+}
+
+int mixq_gemm_dequant_ex(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
+                         const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, const mixq_epilogue* epi,
+                         void* stream) {
+    return launch_gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, static_cast<cudaStream_t>(stream),
+                               /*pdl=*/false, nullptr, 0, false, epi ? epi->bias : nullptr, epi ? epi->activation : 0);
+}
+
+int mixq_enqueue_ex(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes,
+                    const mixq_epilogue* epi, unsigned flags, void* stream) {
+    const void* bias = epi ? epi->bias : nullptr;
+    const int act = epi ? epi->activation : 0;
+    if (act != MIXQ_ACT_NONE && act != MIXQ_ACT_SILU) return set_error(MIXQ_ERR_BAD_ARG, "enqueue: unknown activation");
     if (!t) return set_error(MIXQ_ERR_BAD_ARG, "enqueue: null tensor table");
     if (M < 0 || N <= 0 || K <= 0) return set_error(MIXQ_ERR_BAD_ARG, "enqueue: bad dimensions");
     if (M == 0) return MIXQ_OK;
@@ -147,7 +162,7 @@ int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* w
     if (M <= 4 && t->q_weight && !(flags & MIXQ_FLAG_FORCE_MIXED)) {
         if (!t->A || !t->scaling_factors || !t->Out)
             return set_error(MIXQ_ERR_BAD_ARG, "enqueue: null tensor (A, q_weight, scaling_factors and Out are required for M <= 4)");
-        return launch_gemv_w8a16(t->A, t->q_weight, t->scaling_factors, t->Out, M, N, K, static_cast<cudaStream_t>(stream));
+        return launch_gemv_w8a16(t->A, t->q_weight, t->scaling_factors, t->Out, M, N, K, static_cast<cudaStream_t>(stream), bias, act);
     }
     if (!t->A || !t->W8 || !t->scale_b || !t->fp_weight || !t->ind || !t->Out)
         return set_error(MIXQ_ERR_BAD_ARG, "enqueue: null tensor (A, W8, scale_b, fp_weight, ind and Out are required)");
@@ -166,7 +181,7 @@ int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* w
     int rc = launch_quant_extract(t->A, M, K, t->ind, MIXQ_NUM_OUTLIERS, A8, sa, fpA, flags, s, /*pdl=*/true, sk, 1024);
     if (rc) return rc;
     return launch_gemm_dequant(A8, t->W8, sa, t->scale_b, fpA, t->fp_weight, t->Out, M, N, K, s, /*pdl=*/true, sk,
-                               streamk_workspace_bytes(), /*sk_flags_clean=*/true);
+                               streamk_workspace_bytes(), /*sk_flags_clean=*/true, bias, act);
 }
 
 size_t mixq_allreduce_staging_size(int64_t M, int64_t N, int world) { return allreduce_staging_bytes(M, N, world); }

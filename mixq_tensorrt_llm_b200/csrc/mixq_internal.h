@@ -36,7 +36,8 @@ int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, i
 // sk_flags_clean: the flags are already zero (mixq_enqueue lets kernel 1 clear them).
 int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                         const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
-                        bool pdl, void* sk_ws = nullptr, size_t sk_ws_bytes = 0, bool sk_flags_clean = false);
+                        bool pdl, void* sk_ws = nullptr, size_t sk_ws_bytes = 0, bool sk_flags_clean = false,
+                        const void* bias = nullptr, int act = 0);   // fused epilogue: see mixq_epilogue
 size_t streamk_workspace_bytes();
 // stage 2 with the row-parallel all-reduce fused in (peer memory; see ArParams in gemm_i8_tcgen05.cu)
 int launch_gemm_dequant_allreduce(const void* A8, const void* W8, const void* scale_a, const void* scale_b,
@@ -48,7 +49,7 @@ int set_trace_buffer(void* dev_buf);
 
 // M <= 4 branch (gemv_w8a16.cu): weight-only GEMV over the EETQ-interleaved q_weight
 int launch_gemv_w8a16(const void* A, const void* q_weight, const void* scales, void* Out, int64_t M, int64_t N, int64_t K,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const void* bias = nullptr, int act = 0);
 
 // GEMM tile configuration ids (mixq_set_gemm_config); 0 = pick automatically.
 enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfg2CtaN256Tma = 9, kCfg2CtaN192Tma = 10, kCfgCount };

@@ -170,7 +170,30 @@ class MixQLinear(torch.nn.Module):
             self.bias.copy_(bias)
         return self
 
-    def forward(self, A: torch.Tensor) -> torch.Tensor:
+    def forward(self, A: torch.Tensor, activation: Optional[str] = None, fuse_bias: bool = False) -> torch.Tensor:
+        """``activation="silu"`` and/or ``fuse_bias=True`` run the fused epilogue (mixq_enqueue_ex: SiLU in fp32 before the
+        output rounding, bias added to the fp16 result) instead of separate elementwise passes; not for tensor-parallel
+        shards, whose partial results must be reduced first."""
+        if activation is not None or fuse_bias:
+            if activation not in (None, "silu"):
+                raise ValueError("activation must be None or 'silu'")
+            if self.tp_size > 1 and self.parallel_mode == "row":
+                raise ValueError("the fused epilogue cannot run on row-parallel partial sums")
+            binding.require_device()
+            M = A.numel() // A.shape[-1]
+            A2 = A.reshape(M, A.shape[-1]).contiguous()
+            out = torch.empty(M, self.out_features, dtype=torch.float16, device=A.device)
+            ws = _workspace(A.device, binding.workspace_size(max(M, 1), self.out_features, self.in_features))
+            binding.enqueue(A2, self.weight.view(torch.int8).view(self.out_features, self.in_features),
+                            self.weights_scaling_factor, self.fp_weight, self.fp_ind.view(torch.int32), out, ws,
+                            q_weight=self.qweight if self.qweight.numel() else None,
+                            scaling_factors=self.weights_scaling_factor,
+                            bias=self.bias.to(torch.float16) if (fuse_bias and self.bias is not None) else None,
+                            activation=binding.ACT_SILU if activation == "silu" else binding.ACT_NONE)
+            x = out.view(*A.shape[:-1], self.out_features)
+            if self.bias is not None and not fuse_bias:
+                x = x + self.bias.to(x.dtype)
+            return x
         if self._peer is not None and self.tp_size > 1:
             binding.require_device()
             M = A.numel() // A.shape[-1]

@@ -178,6 +178,29 @@ def epilogue(acc: np.ndarray, sa: np.ndarray, sb: np.ndarray, out0: np.ndarray |
     return out
 
 
+def epilogue_ex(acc: np.ndarray, sa: np.ndarray, sb: np.ndarray, out0: np.ndarray | None, bias: np.ndarray | None = None,
+                silu: bool = False) -> np.ndarray:
+    """The fused epilogue of SURVEY.md 8f #4:
+        y   = fp16( act( fma(float(acc), sb*sa, float(out0)) ) )   act = silu(x) = x / (1 + exp(-x)) in fp32 before the rounding
+                                                                    (linear_combination_dequant.h:167-272)
+        out = fp16( float(y) + float(bias[n]) )                     the bias add the reference does outside the kernel
+                                                                    (plugin.py:158-160)
+    The FMA is evaluated in float64 and rounded to fp32 (exact except for astronomically rare double-rounding ties);
+    silu uses the exact exp (the reference extension is built with --use_fast_math: ~2 fp32 ulp away)."""
+    p = (sb.astype(np.float32)[None, :] * sa.astype(np.float32)[:, None]).astype(np.float64)
+    r = np.ascontiguousarray(acc, dtype=np.int32).astype(np.float32).astype(np.float64) * p
+    if out0 is not None:
+        r = r + out0.astype(np.float64)
+    r = r.astype(np.float32)
+    if silu:
+        with np.errstate(over="ignore"):
+            r = (r.astype(np.float64) / (1.0 + np.exp(-r.astype(np.float64)))).astype(np.float32)
+    y = r.astype(np.float16)
+    if bias is not None:
+        y = (y.astype(np.float32) + bias.astype(np.float32)[None, :]).astype(np.float16)
+    return y
+
+
 def forward(A, W8, sb, fp_weight, ind, mask: bool = False, use_table: bool = True, return_parts: bool = False):
     """MixQPlugin::enqueueImpl, M>4 branch (TsinghuaMixQPlugin.cpp:518-532), whole path."""
     M, K = A.shape

@@ -7,6 +7,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from mixq_tensorrt_llm_b200 import binding as B  # noqa: E402
 M, N, K = (int(x) for x in sys.argv[1:4])
+cfg = int(sys.argv[4]) if len(sys.argv) > 4 else 8
 dev = "cuda"
 lib = B.load()
 A8 = torch.randint(-127, 128, (M, K), dtype=torch.int8, device=dev)
@@ -18,7 +19,7 @@ fw = (torch.randn(N, 128, device=dev) * 0.02).half()
 out = torch.empty(M, N, dtype=torch.float16, device=dev)
 ws = torch.zeros(lib.mixq_gemm_workspace_size(), dtype=torch.uint8, device=dev)
 trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
-lib.mixq_set_gemm_config(8)
+lib.mixq_set_gemm_config(cfg)
 for it in range(4):
     B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws)
 torch.cuda.synchronize()
@@ -31,7 +32,7 @@ t0 = t[:, 0][t[:, 0] > 0].min()
 names = ["entry", "prologue", "firstTMA", "tile0issued", "mmaDone", "acc0ready", "accLast", "epiDone",
          "peersIn", "chunksDone", "loopExit", "storesDone"]
 rel = np.where(t > 0, (t - t0) / 1e3, np.nan)
-print("shape", M, N, K, "us relative to first CTA entry")
+print("shape", M, N, K, "cfg", cfg, "us relative to first CTA entry")
 for i, n in enumerate(names):
     col = rel[:, i]
     ok = ~np.isnan(col)

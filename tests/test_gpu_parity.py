@@ -515,3 +515,74 @@ def test_plugin_module_takes_weight_only_branch_with_qweight(B, oracle):
     y5 = mod(_t(A5)).cpu().numpy()
     r = oracle.forward(A5, lin["W8"], lin["scale_b"], lin["fp_weight"], lin["ind"], return_parts=True)
     _assert_mixed_close(y5, r["out"], r["out0"], "M=5 mixed")
+
+
+# ------------------------------------------------------------------ fused epilogue: bias / SiLU
+@pytest.mark.parametrize("cfg", [0, 1, 5, 6, 9, 10])
+def test_fused_bias_epilogue_bit_exact(B, lib, oracle, cfg):
+    """mixq_gemm_dequant_ex with a bias and no outlier slab: Out == fp16(float(fp16(fma)) + bias[n]) bit for bit
+    (int32 exact, one FMA, two roundings) for every kernel family."""
+    M, N, K = 300, 520, 1024
+    rng = np.random.default_rng(11)
+    q = rng.integers(-127, 128, (M, K), dtype=np.int8)
+    W8 = rng.integers(-127, 128, (N, K), dtype=np.int8)
+    sa = (rng.random(M) * 0.02 + 1e-3).astype(np.float16)
+    sb = (rng.random(N) * 2e-3 + 1e-4).astype(np.float16)
+    bias = rng.standard_normal(N).astype(np.float16)
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    lib.mixq_set_gemm_config(cfg)
+    try:
+        B.gemm_dequant(_t(q), _t(W8), _t(sa), _t(sb), None, None, out, bias=_t(bias))
+        torch.cuda.synchronize()
+    finally:
+        lib.mixq_set_gemm_config(0)
+    want = oracle.epilogue_ex(oracle.igemm(q, W8), sa, sb, None, bias=bias)
+    assert np.array_equal(out.cpu().numpy().view(np.uint16), want.view(np.uint16))
+
+
+@pytest.mark.parametrize("M", [3, 64, 700])
+def test_fused_silu_bias_epilogue(B, oracle, M):
+    """mixq_enqueue_ex (SiLU + bias) against the oracle: the activation runs in fp32 before the rounding with the
+    fast-math intrinsics the reference build uses, so the tolerance is 2 fp16 ulp of the result on top of the
+    mixed-path tolerance (1 ulp of the outlier product; silu' <= 1.1); M = 3 with q_weight also covers the GEMV."""
+    N, K = 512, 4096
+    lin = oracle.synth_linear(N, K, oracle.load_act_scales("Llama-2-7b/self_attn.q_proj"))
+    A = oracle.synth_activations(M, lin["act_scale"], seed=50 + M)
+    bias = np.random.default_rng(1).standard_normal(N).astype(np.float16)
+    ws = torch.empty(B.workspace_size(M, N, K), dtype=torch.uint8, device=DEV)
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    W8, sb, fw, ind = (_t(lin[k]) for k in ("W8", "scale_b", "fp_weight", "ind"))
+    B.enqueue(_t(A), W8, sb, fw, ind, out, ws, bias=_t(bias), activation=B.ACT_SILU)
+    torch.cuda.synchronize()
+    r = oracle.forward(A, lin["W8"], lin["scale_b"], lin["fp_weight"], lin["ind"], return_parts=True)
+    want = oracle.epilogue_ex(r["acc"], r["sa"], lin["scale_b"], r["out0"], bias=bias, silu=True)
+    got = out.cpu().numpy().astype(np.float32)
+    w32 = want.astype(np.float32)
+    ulp = lambda x: np.spacing(np.abs(x).astype(np.float16)).astype(np.float32)
+    bound = 2 * ulp(w32) + 1.2 * ulp(r["out0"].astype(np.float32)) + 2 * ulp((want.astype(np.float32) - bias.astype(np.float32)[None, :]))
+    assert (np.abs(got - w32) <= bound).all(), float((np.abs(got - w32) / bound).max())
+    if M <= 4:
+        Wt = (np.random.default_rng(6).standard_normal((K, N)) * 0.02).astype(np.float16)
+        qw, sc = oracle.eetq_quant_weights(Wt)
+        B.enqueue(_t(A), W8, sb, fw, ind, out, ws, q_weight=_t(qw), scaling_factors=_t(sc), bias=_t(bias), activation=B.ACT_SILU)
+        torch.cuda.synchronize()
+        plain = torch.empty(M, N, dtype=torch.float16, device=DEV)
+        B.enqueue(_t(A), W8, sb, fw, ind, plain, ws, q_weight=_t(qw), scaling_factors=_t(sc))
+        torch.cuda.synchronize()
+        x = plain.cpu().numpy().astype(np.float64)
+        ref = ((x / (1 + np.exp(-x))).astype(np.float16).astype(np.float32) + bias.astype(np.float32)[None, :])
+        assert np.abs(out.cpu().numpy().astype(np.float32) - ref).max() <= 3e-2
+
+
+def test_module_fused_bias_equals_unfused(B, oracle):
+    """MixQLinear(bias=True): forward(fuse_bias=True) == forward() (plugin, then x + bias as plugin.py:158-160) bit for bit."""
+    from mixq_tensorrt_llm_b200.plugin import MixQLinear
+    N, K, M = 512, 4096, 96
+    lin = oracle.synth_linear(N, K, oracle.load_act_scales("Llama-2-7b/self_attn.q_proj"))
+    bias = torch.randn(N, device=DEV).half()
+    mod = MixQLinear(K, N, bias=True, device=DEV)
+    mod.load_packed(*(_t(lin[k]) for k in ("W8", "scale_b", "fp_weight", "ind")), bias=bias)
+    A = _t(oracle.synth_activations(M, lin["act_scale"], seed=5))
+    a, b = mod(A), mod(A, fuse_bias=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.int16), b.view(torch.int16))

@@ -237,3 +237,21 @@ def test_gemv_oracle_close_to_float64(oracle):
     out = oracle.gemv_w8a16(A, qw, sc).astype(np.float64)
     ref = A.astype(np.float64) @ (oracle.eetq_unprocess(qw).astype(np.float64) * sc.astype(np.float64)[None, :])
     assert np.abs(out - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-3
+
+
+def test_epilogue_ex_reduces_to_epilogue(oracle):
+    """epilogue_ex without bias / activation is the reference epilogue (the C restatement) bit for bit."""
+    rng = np.random.default_rng(2)
+    acc = rng.integers(-3_000_000, 3_000_000, (16, 64), dtype=np.int32)
+    sa = (rng.random(16) * 0.02 + 1e-3).astype(np.float16)
+    sb = (rng.random(64) * 2e-3 + 1e-4).astype(np.float16)
+    out0 = rng.standard_normal((16, 64)).astype(np.float16)
+    a = oracle.epilogue(acc, sa, sb, out0)
+    b = oracle.epilogue_ex(acc, sa, sb, out0)
+    assert np.array_equal(a.view(np.uint16), b.view(np.uint16))
+    bias = rng.standard_normal(64).astype(np.float16)
+    c = oracle.epilogue_ex(acc, sa, sb, out0, bias=bias)
+    assert np.array_equal(c.view(np.uint16), (a.astype(np.float32) + bias.astype(np.float32)[None, :]).astype(np.float16).view(np.uint16))
+    d = oracle.epilogue_ex(acc, sa, sb, out0, silu=True).astype(np.float32)
+    x = a.astype(np.float32)
+    assert np.allclose(d, x / (1 + np.exp(-x)), rtol=2e-3, atol=2e-3)
