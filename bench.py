@@ -124,7 +124,7 @@ def traffic_from_profile():
     try:
         d = json.loads(p.read_text())["gemm"]
         return {"bytes": d["dram_read_bytes"] + d["dram_write_bytes"], "algorithmic_bytes": d["algorithmic_bytes"],
-                "shape": d["shape"], "source": "profiles/r1_ncu_summary.csv"}
+                "shape": d["shape"], "source": "profiles/r1s2_ncu_summary.csv"}
     except (OSError, KeyError, ValueError):
         return None
 
@@ -426,6 +426,50 @@ def run_ours(args, M, linears):
         except Exception as e:
             e2e = {"value": None, "unit": UNIT, "error": repr(e)[:200]}
 
+    # ---- the other batch size of the metric (decode, bs = 512 tokens per step) in the same run, N = 1: the same five
+    # linears through mixq_enqueue, the step replayed from a CUDA graph; weights (202 MB) exceed L2, activations do not
+    decode = None
+    if world == 1 and M != 512 and not args.no_decode:
+        try:
+            Md = 512
+            dacts = {k: acts[k][:Md].contiguous() for k in acts}
+            dout = torch.empty(Md * max_out, dtype=torch.float16, device=dev)
+
+            def dstep():
+                for name, mod, Ns, Ks, mode in mods:
+                    B.enqueue(dacts[Ks], mod.weight.view(torch.int8).view(Ns, Ks), mod.weights_scaling_factor, mod.fp_weight,
+                              mod.fp_ind.view(torch.int32), dout[: Md * Ns].view(Md, Ns), ws)
+            torch.cuda.synchronize()
+            gs2 = torch.cuda.Stream()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(gs2):
+                dstep()
+                gs2.synchronize()
+                with torch.cuda.graph(g2, stream=gs2):
+                    dstep()
+            torch.cuda.synchronize()
+            for _ in range(5):
+                g2.replay()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            d0.record()
+            nrep = 200
+            for _ in range(nrep):
+                g2.replay()
+            d1.record()
+            torch.cuda.synchronize()
+            dms = d0.elapsed_time(d1) / nrep
+            dfl = sum(2.0 * Md * N * K for _, N, K, _ in linears)
+            wbytes = sum(N * K for _, N, K, _ in linears)
+            decode = {"workload": args.workload.replace("bs32xseq2048", "decode-bs512"), "tokens_per_step": Md,
+                      "ms_per_step": dms, "value": dfl / (dms * 1e-3) / 1e12, "unit": UNIT, "tokens_per_s": Md / (dms * 1e-3),
+                      "launch": "cuda-graph replay of the step", "steps": nrep,
+                      "frac_of_int8_peak": round(dfl / (dms * 1e-3) / 1e12 / (2.0 * pk["bf16_sustained"]), 4),
+                      "weight_stream_gbs": round(wbytes / (dms * 1e-3) / 1e9, 1)}
+            del dout
+        except Exception as e:
+            decode = {"error": repr(e)[:200]}
+
     # ---- same-box GPU baseline: the reference's own kernels recompiled for sm_100a (oracle/_ref), N=1 only
     ref_gpu = None
     if rank == 0 and world == 1 and not args.no_ref_gpu:
@@ -486,7 +530,7 @@ def run_ours(args, M, linears):
                            "l2": "inputs larger than L2 (activations %.0f MB per linear), no flush" % (M * 4096 * 2 / 1e6)
                                  if M >= 16384 else "weights rotate through >126 MB per step; activations L2-resident"},
                 "tokens_per_s": M / (ms_step * 1e-3), "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "ref_gpu": ref_gpu,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "decode_bs512": decode, "ref_gpu": ref_gpu,
                 "int8_peak_note": "no INT8 figure in MEASURED_PEAKS.json; peak = 2 x measured bf16 (dense INT8 = 2 x dense BF16 on sm_100)"}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -511,6 +555,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="skip the bs=512 decode leg of the default run")
     args = ap.parse_args()
     M, linears = WORKLOADS[args.workload]
     if args.impl == "reference":

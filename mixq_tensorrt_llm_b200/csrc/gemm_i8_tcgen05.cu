@@ -1627,6 +1627,10 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
         int64_t best = INT64_MAX;
         for (const Cand& c : cands) {
             if (M <= 128 && c.cta == 2) continue;
+            // decode batches (weights streamed from HBM once, one or two tiles per CTA pair): the wide TMA-store tiles lose to
+            // the 128-wide ones, whose 8-stage ring keeps more loads in flight and whose exposed epilogue is shorter
+            // (measured at M = 512 on every Llama-2 / Qwen2 shape but one, where they are 5 % ahead)
+            if (M <= 512 && (c.id == kCfg2CtaN192Tma || c.id == kCfg2CtaN256Tma)) continue;
             const int64_t tiles = ((M + c.tile_m - 1) / c.tile_m) * ((N + c.tile_n - 1) / c.tile_n);
             const int64_t workers = usable_sms() / c.cta;
             const int64_t est = ((tiles + workers - 1) / workers) * c.kb_cycles * nkb + c.tail_cycles;
