@@ -261,9 +261,10 @@ extern "C" int mixq_linear_host(const mixq_tensors* t, const void* A_host, void*
     uint8_t* ws = dOut + align_up(static_cast<size_t>(M) * N * 2);
     const size_t ws_bytes = mixq_workspace_size(M, N, K);
 
-    // slabs of >= 2048 rows (a multiple of the 256-row tile), at most 64 of them
-    int64_t rows = (M + 7) / 8;
-    rows = rows < 2048 ? 2048 : (rows + 255) / 256 * 256;
+    // ~32 slabs of >= 1024 rows (a multiple of the 256-row tile), at most 64 of them: the call is PCIe-bound, so short
+    // slabs (small fill / drain bubbles of the three-stage pipeline) matter more than GEMM efficiency per slab
+    int64_t rows = (M + 31) / 32;
+    rows = rows < 1024 ? 1024 : (rows + 255) / 256 * 256;
     while ((M + rows - 1) / rows > 64) rows *= 2;
     const int n_slabs = static_cast<int>((M + rows - 1) / rows);
 

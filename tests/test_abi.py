@@ -175,3 +175,30 @@ def test_allreduce_entry_points_validate_arguments(lib):
     t = binding.Tensors()
     assert lib.mixq_enqueue_allreduce(ctypes.byref(t), 8, 8, 16, None, 0, ctypes.byref(g), 0, None) == -1       # null tensors
     assert lib.mixq_enqueue_allreduce(ctypes.byref(t), 0, 8, 16, None, 0, ctypes.byref(g), 0, None) == 0        # M == 0: no-op
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """binding.Tensors / PeerGroup / Epilogue must have the size and field offsets of the C structs in
+    include/mixq_b200.h (compiled here with gcc and printed)."""
+    from mixq_tensorrt_llm_b200 import binding
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "mixq_b200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu\n", sizeof(mixq_tensors), offsetof(mixq_tensors, q_weight), offsetof(mixq_tensors, Out), (size_t)MIXQ_MAX_RANKS);
+    printf("%zu %zu %zu %zu %zu %zu\n", sizeof(mixq_peer_group), offsetof(mixq_peer_group, out), offsetof(mixq_peer_group, staging),
+           offsetof(mixq_peer_group, counters), offsetof(mixq_peer_group, staging_bytes), offsetof(mixq_peer_group, counter_bytes));
+    printf("%zu %zu\n", sizeof(mixq_epilogue), offsetof(mixq_epilogue, activation));
+    return 0;
+}'''
+    c = tmp_path / "s.c"
+    c.write_text(src)
+    exe = tmp_path / "s"
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", str(ROOT / "include"), str(c), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a, b, e = (list(map(int, ln.split())) for ln in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    T, P, E = binding.Tensors, binding.PeerGroup, binding.Epilogue
+    assert a == [ctypes.sizeof(T), T.q_weight.offset, T.Out.offset, binding.MAX_RANKS]
+    assert b == [ctypes.sizeof(P), P.out.offset, P.staging.offset, P.counters.offset, P.staging_bytes.offset, P.counter_bytes.offset]
+    assert e == [ctypes.sizeof(E), E.activation.offset]
