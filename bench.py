@@ -429,7 +429,7 @@ def run_ours(args, M, linears):
     # ---- the other batch size of the metric (decode, bs = 512 tokens per step) in the same run, N = 1: the same five
     # linears through mixq_enqueue, the step replayed from a CUDA graph; weights (202 MB) exceed L2, activations do not
     decode = None
-    if world == 1 and M != 512 and not args.no_decode:
+    if world == 1 and M > 512 and not args.no_decode:
         try:
             Md = 512
             dacts = {k: acts[k][:Md].contiguous() for k in acts}
