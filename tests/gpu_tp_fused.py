@@ -120,8 +120,44 @@ for (M, N, K) in shapes:
     if rank == 0:
         print(json.dumps(res), flush=True)
     results.append(res)
+# ---- the module path: MixQLinear(parallel_mode="row").attach_peer_buffers(...) == plugin + NCCL all-reduce up to the
+# summation order (fp32 rank-order sum vs NCCL's fp16 ring), and a CUDA-graph replay of the fused call
+from mixq_tensorrt_llm_b200.plugin import MixQLinear  # noqa: E402
+M, N, K = shapes[0]
+Kr = K // world
+g = torch.Generator(device=dev).manual_seed(500 + rank)
+mod = MixQLinear(K, N, tp_size=world, tp_group=dist.group.WORLD, parallel_mode="row", device=dev)
+W8 = torch.randint(-127, 128, (N, Kr), dtype=torch.int8, device=dev, generator=g)
+ind = torch.randperm(Kr, device=dev, generator=g)[:128].int()
+mod.load_packed(W8, (torch.rand(N, device=dev, generator=g) * 2e-4 + 1e-4).half(),
+                (torch.randn(N, 128, device=dev, generator=g) * 0.02).half(), ind)
+A = torch.randn(M, Kr, device=dev, generator=g).half()
+y_nccl = mod(A).clone()
+mod.attach_peer_buffers(pb)
+y_fused = mod(A).clone()
+torch.cuda.synchronize()
+rel = float((y_fused.float() - y_nccl.float()).norm() / y_nccl.float().norm())
+gs = torch.cuda.Stream()
+graph = torch.cuda.CUDAGraph()
+dist.barrier()
+torch.cuda.synchronize()
+with torch.cuda.stream(gs):
+    mod(A)
+    gs.synchronize()
+    with torch.cuda.graph(graph, stream=gs):
+        y_graph = mod(A)
+torch.cuda.synchronize()
+for _ in range(3):
+    graph.replay()
+torch.cuda.synchronize()
+graph_ok = bool(torch.equal(y_graph.view(torch.int16), y_fused.view(torch.int16)))
+module_ok = rel < 2e-3 and graph_ok
+t_ok = torch.tensor([1 if module_ok else 0], device=dev)
+dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(json.dumps({"module_path": {"rel_diff_fused_vs_nccl": rel, "graph_replay_bit_equal": graph_ok}}), flush=True)
 dist.barrier()
 if rank == 0:
-    ok = all(r["mismatches"] == 0 for r in results)
+    ok = all(r["mismatches"] == 0 for r in results) and bool(t_ok.item())
     print("PASS" if ok else "FAIL", flush=True)
 dist.destroy_process_group()
