@@ -179,6 +179,10 @@ typedef struct mixq_peer_group {
     void* staging[MIXQ_MAX_RANKS];  /* every rank's staging area, >= mixq_allreduce_staging_size() bytes  */
     void* counters[MIXQ_MAX_RANKS]; /* every rank's counter block, >= mixq_allreduce_counter_size() bytes */
     size_t staging_bytes, counter_bytes;
+    void* out_multicast;            /* optional: NVSwitch multicast mapping of the Out buffers (a store to it lands in every
+                                       rank's Out): the result is then broadcast with one multimem store per row instead of
+                                       one TMA store per rank -- (world-1)x fewer bytes leave the GPU in that phase; the
+                                       arithmetic, and so the result, is unchanged.  NULL = per-rank stores.               */
 } mixq_peer_group;
 size_t mixq_allreduce_staging_size(int64_t M, int64_t N, int world);
 size_t mixq_allreduce_counter_size(int64_t M, int64_t N, int world);

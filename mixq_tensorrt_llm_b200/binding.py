@@ -56,7 +56,8 @@ class PeerGroup(ctypes.Structure):
     _fields_ = [("world", ctypes.c_int), ("rank", ctypes.c_int),
                 ("out", ctypes.c_void_p * MAX_RANKS), ("staging", ctypes.c_void_p * MAX_RANKS),
                 ("counters", ctypes.c_void_p * MAX_RANKS),
-                ("staging_bytes", ctypes.c_size_t), ("counter_bytes", ctypes.c_size_t)]
+                ("staging_bytes", ctypes.c_size_t), ("counter_bytes", ctypes.c_size_t),
+                ("out_multicast", ctypes.c_void_p)]
 
 
 _lib = None
@@ -231,10 +232,12 @@ def gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, stream=None, wo
               "mixq_gemm_dequant_ws")
 
 
-def make_peer_group(world: int, rank: int, out_ptrs, staging_ptrs, counter_ptrs, staging_bytes: int, counter_bytes: int) -> PeerGroup:
+def make_peer_group(world: int, rank: int, out_ptrs, staging_ptrs, counter_ptrs, staging_bytes: int, counter_bytes: int,
+                    out_multicast: int = 0) -> PeerGroup:
     """struct mixq_peer_group from raw addresses (ints) of every rank's Out / staging / counter buffers."""
     g = PeerGroup()
     g.world, g.rank = world, rank
+    g.out_multicast = out_multicast or None
     for i in range(world):
         g.out[i], g.staging[i], g.counters[i] = out_ptrs[i], staging_ptrs[i], counter_ptrs[i]
     g.staging_bytes, g.counter_bytes = staging_bytes, counter_bytes

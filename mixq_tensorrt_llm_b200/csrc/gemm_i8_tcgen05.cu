@@ -784,6 +784,11 @@ __device__ __forceinline__ void signal_add_relaxed_sys(uint32_t* p, uint32_t v) 
     asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+// 16-byte store to an NVSwitch multicast address: the switch replicates it into every rank's copy of the buffer
+__device__ __forceinline__ void multimem_st_v4(void* mc_ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_ptr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
 
 // ---- fused all-reduce of a row-parallel linear -------------------------------------------------
 // Every rank computes the fp16 partial of every output tile; tile t is OWNED by rank t % world.
@@ -811,6 +816,7 @@ struct alignas(64) ArParams {
                                             // (slot, 32-row group) is BLOCK_N/32 chunks of 32 rows x 32 columns, each the
                                             // 2 KB SWIZZLE_64B image of the shared-memory tile it was copied from
     const __half* stage_local;              // this rank's whole staging area: [world][slots][256][BLOCK_N] fp16
+    __half* out_mc;                         // NVSwitch multicast mapping of Out (a store lands in every rank's Out), or null
     int world, rank, slots;
 };
 struct ArNone {
@@ -1248,6 +1254,64 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
             const size_t region_vecs = static_cast<size_t>(ar.slots) * T::kTileM * BLOCK_N / 8;   // vectors per source rank
             uint32_t n_done = 0;
             int k = 0;
+            if (ar.out_mc != nullptr) {
+                // ---- broadcast through the switch: each warp reduces whole 512-byte rows (lane = chunk * 4 + 16-byte slot of the
+                // chunk-major staging image) and issues ONE multicast store per row; the egress of this phase drops from
+                // (world - 1) copies to one.
+                if (et == 0) {
+                    const uint32_t expect = static_cast<uint32_t>(world) * gridDim.x;
+                    uint32_t spins = 0;
+                    while (ld_acquire_sys(my_cnt + kArWordPushed + parity) < expect) {
+                        if (++spins > (1u << 24)) __trap();
+                    }
+                    trace_stamp(13);
+                }
+                ptx::named_bar_sync(2, kStashEpiThreads);
+                const int chunk = lane >> 2, slot = lane & 3;
+                const bool lane_ok = chunk < BLOCK_N / 32;
+                for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                    const int j = u >> 3, rg = u & 7;
+                    const TileCoord tc = tile_coord(ar.rank + j * world, m_tiles, n_tiles, group_m);
+                    const uint4* unit = reinterpret_cast<const uint4*>(ar.stage_local) + static_cast<size_t>(u) * kUnitVecs;
+                    uint4 v[4][MIXQ_MAX_RANKS];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = ew * 4 + i;                           // row of the 32-row group
+#pragma unroll
+                        for (int sr = 0; sr < MIXQ_MAX_RANKS; ++sr)
+                            if (sr < world && lane_ok) v[i][sr] = __ldcg(unit + sr * region_vecs + chunk * 128 + r * 4 + slot);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = ew * 4 + i;
+                        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int sr = 0; sr < MIXQ_MAX_RANKS; ++sr) {
+                            if (sr < world) {
+                                const uint32_t w[4] = {v[i][sr].x, v[i][sr].y, v[i][sr].z, v[i][sr].w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                                    acc[2 * e] = sr == 0 ? f.x : acc[2 * e] + f.x;       // rank order; world = 1 is the identity
+                                    acc[2 * e + 1] = sr == 0 ? f.y : acc[2 * e + 1] + f.y;
+                                }
+                            }
+                        }
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __half2 h = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
+                            pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        const int gm = tc.m_blk * T::kTileM + rg * 32 + r;
+                        const int col = tc.n_blk * BLOCK_N + chunk * 32 + ((slot ^ ((r >> 1) & 3)) << 3);   // un-swizzle the slot
+                        if (lane_ok && gm < M && col < N)
+                            multimem_st_v4(ar.out_mc + static_cast<size_t>(gm) * N + col, pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    ++n_done;
+                }
+                ptx::named_bar_sync(2, kStashEpiThreads);      // every thread's multicast stores precede the fence below
+            } else
             for (int u = blockIdx.x; u < units; u += gridDim.x, ++k) {
                 const int j = u >> 3, rg = u & 7;
                 const TileCoord tc = tile_coord(ar.rank + j * world, m_tiles, n_tiles, group_m);
@@ -1564,6 +1628,7 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
                     return rc;
             }
             ar.stage_local = static_cast<const __half*>(pg->staging[pg->rank]);
+            ar.out_mc = static_cast<__half*>(pg->out_multicast);
             auto kern_ar = KernelOf<T>::get_ar();
             static std::atomic<int> ar_attr_set_for_device{-1};
             if (ar_attr_set_for_device.load(std::memory_order_acquire) != dev.device) {

@@ -19,7 +19,7 @@ def _align(x: int, a: int = 256) -> int:
 class PeerBuffers:
     """One symmetric allocation per rank, carved into  Out [max_M, max_N] fp16 | staging | counters."""
 
-    def __init__(self, max_M: int, max_N: int, group=None, device=None):
+    def __init__(self, max_M: int, max_N: int, group=None, device=None, multicast: bool = True):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         lib = binding.load()
@@ -38,6 +38,9 @@ class PeerBuffers:
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, self.group)
         self.bases = [int(p) for p in self.handle.buffer_ptrs]
+        # NVSwitch multicast mapping of the same allocation (0 when the platform has none): used for the broadcast half
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        self.multicast_base = mc if (multicast and self.world > 1) else 0
         torch.cuda.synchronize(dev)
         self.handle.barrier()          # every rank's counters are zero before anybody launches
 
@@ -49,6 +52,9 @@ class PeerBuffers:
         if M * N * 2 > self.out_bytes:
             raise binding.MixQError("PeerBuffers: shape exceeds the allocation")
         b = self.bases
+        # Broadcast half through the switch only where it pays (measured on 8 B200s: 56.8 -> 50.9 us for an 8 MB result;
+        # equal or slower for 2 ranks and for bulk results, whose time is set by the bytes each GPU must RECEIVE).
+        mc = self.multicast_base if (self.world >= 4 and M * N * 2 <= (64 << 20)) else 0
         return binding.make_peer_group(self.world, self.rank, b, [x + self.out_bytes for x in b],
                                        [x + self.out_bytes + self.staging_bytes for x in b],
-                                       self.staging_bytes, self.counter_bytes)
+                                       self.staging_bytes, self.counter_bytes, out_multicast=mc)

@@ -28,7 +28,8 @@ lib = B.load()
 B.require_device()
 shapes = [tuple(int(x) for x in s.split("x")) for s in sys.argv[1:]] or [(512, 8192, 8192), (512, 4096, 4096), (8192, 4096, 4096)]
 maxM, maxN = max(s[0] for s in shapes), max(s[1] for s in shapes)
-pb = PeerBuffers(maxM, maxN, device=dev)
+pb = PeerBuffers(maxM, maxN, device=dev)                       # broadcast through the NVSwitch multicast mapping when there is one
+pb_uc = PeerBuffers(maxM, maxN, device=dev, multicast=False) if pb.multicast_base else None   # per-rank TMA stores, for A/B
 results = []
 
 
@@ -67,6 +68,8 @@ for (M, N, K) in shapes:
         ref = ref + parts[r].float()
     ref = ref.half()
     grp = pb.peer_group(M, N)
+    if pb.multicast_base:          # A/B: force the multicast broadcast here regardless of PeerBuffers' size policy
+        grp.out_multicast = pb.multicast_base
     out = pb.out(M, N)
     out.fill_(float("nan"))
     torch.cuda.synchronize()
@@ -86,6 +89,11 @@ for (M, N, K) in shapes:
 
     def fused():
         B.enqueue_allreduce(A, W8, sb, fw, ind, ws, grp)
+
+    grp_uc = pb_uc.peer_group(M, N) if pb_uc is not None else None
+
+    def fused_unicast():
+        B.enqueue_allreduce(A, W8, sb, fw, ind, ws, grp_uc)
 
     def gemm_only():
         B.enqueue(A, W8, sb, fw, ind, part, ws)
@@ -115,6 +123,16 @@ for (M, N, K) in shapes:
         if (~np.isnan(col)).any():
             tl[nm] = [round(float(np.nanmin(col)), 1), round(float(np.nanmedian(col)), 1), round(float(np.nanmax(col)), 1)]
     res["timeline_us_min_med_max"] = tl
+    res["multicast_broadcast"] = bool(pb.multicast_base)
+    if pb_uc is not None:
+        out_uc = pb_uc.out(M, N)
+        out_uc.fill_(float("nan"))
+        torch.cuda.synchronize()
+        dist.barrier()
+        fused_unicast()
+        torch.cuda.synchronize()
+        res["unicast_mismatches"] = int((out_uc.view(torch.int16) != ref.view(torch.int16)).sum())
+        res["fused_unicast_us"] = timeit(fused_unicast, iters)
     res["speedup"] = res["unfused_us"] / res["fused_us"]
     res["allreduce_bytes"] = M * N * 2
     if rank == 0:
@@ -158,6 +176,6 @@ if rank == 0:
     print(json.dumps({"module_path": {"rel_diff_fused_vs_nccl": rel, "graph_replay_bit_equal": graph_ok}}), flush=True)
 dist.barrier()
 if rank == 0:
-    ok = all(r["mismatches"] == 0 for r in results) and bool(t_ok.item())
+    ok = all(r["mismatches"] == 0 and r.get("unicast_mismatches", 0) == 0 for r in results) and bool(t_ok.item())
     print("PASS" if ok else "FAIL", flush=True)
 dist.destroy_process_group()

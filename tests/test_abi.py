@@ -187,8 +187,9 @@ def test_ctypes_structs_match_the_header(tmp_path):
 #include "mixq_b200.h"
 int main(void) {
     printf("%zu %zu %zu %zu\n", sizeof(mixq_tensors), offsetof(mixq_tensors, q_weight), offsetof(mixq_tensors, Out), (size_t)MIXQ_MAX_RANKS);
-    printf("%zu %zu %zu %zu %zu %zu\n", sizeof(mixq_peer_group), offsetof(mixq_peer_group, out), offsetof(mixq_peer_group, staging),
-           offsetof(mixq_peer_group, counters), offsetof(mixq_peer_group, staging_bytes), offsetof(mixq_peer_group, counter_bytes));
+    printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(mixq_peer_group), offsetof(mixq_peer_group, out), offsetof(mixq_peer_group, staging),
+           offsetof(mixq_peer_group, counters), offsetof(mixq_peer_group, staging_bytes), offsetof(mixq_peer_group, counter_bytes),
+           offsetof(mixq_peer_group, out_multicast));
     printf("%zu %zu\n", sizeof(mixq_epilogue), offsetof(mixq_epilogue, activation));
     return 0;
 }'''
@@ -200,5 +201,6 @@ int main(void) {
     a, b, e = (list(map(int, ln.split())) for ln in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
     T, P, E = binding.Tensors, binding.PeerGroup, binding.Epilogue
     assert a == [ctypes.sizeof(T), T.q_weight.offset, T.Out.offset, binding.MAX_RANKS]
-    assert b == [ctypes.sizeof(P), P.out.offset, P.staging.offset, P.counters.offset, P.staging_bytes.offset, P.counter_bytes.offset]
+    assert b == [ctypes.sizeof(P), P.out.offset, P.staging.offset, P.counters.offset, P.staging_bytes.offset, P.counter_bytes.offset,
+                 P.out_multicast.offset]
     assert e == [ctypes.sizeof(E), E.activation.offset]
