@@ -139,11 +139,11 @@ def shard(N, K, mode, tp):
 def run_reference(args, M, linears):
     """The reference's CPU path: oracle port (oracle/mixq_oracle.c), all host threads, on a
     bounded sample of `sample_tokens` tokens per step through the same five linears."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:            # under torchrun rank 0 alone runs the CPU arm; the others leave without touching the build
+        return
     from oracle import oracle as O
     O.build()
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
     O.set_threads()          # all host cores (torchrun exports OMP_NUM_THREADS=1)
     sample = args.cpu_sample_tokens
     lins, acts = [], {}
