@@ -219,12 +219,6 @@ int mixq_debug_set_trace(void* dev_buf);
  * next row slab instead of queueing behind it.  Returns the previous value. */
 int mixq_set_sm_limit(int num_sms);
 
-/* mixq_enqueue chains its two kernels with programmatic dependent launch.  For batches of at most `rows` tokens the
- * quantise kernel releases the GEMM at its START, so the GEMM's CTAs settle on the free SMs and stream the first weight
- * K-blocks into shared memory while the activations are still being quantised (they read the quantised activations
- * only after the quantise grid has completed).  0 disables; returns the previous value (default 256). */
-int mixq_set_pdl_early_rows(int rows);
-
 /* GEMM tile configuration override for tuning/tests: 0 = auto. Returns the
  * previous value. Valid ids are listed in DESIGN.md. */
 int mixq_set_gemm_config(int config_id);

@@ -23,7 +23,7 @@ EXPORTS = [
     "mixq_quant_extract", "mixq_rmsnorm_quant_extract", "mixq_gemv_w8a16", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
     "mixq_host_scratch_size", "mixq_linear_host",
     "mixq_allreduce_staging_size", "mixq_allreduce_counter_size", "mixq_enqueue_allreduce", "mixq_gemm_dequant_allreduce",
-    "mixq_launch_count", "mixq_set_gemm_config", "mixq_set_sm_limit", "mixq_set_pdl_early_rows", "mixq_debug_set_trace", "initOpenAiTritonPlugins", "mixq_plugin_create",
+    "mixq_launch_count", "mixq_set_gemm_config", "mixq_set_sm_limit", "mixq_debug_set_trace", "initOpenAiTritonPlugins", "mixq_plugin_create",
     "mixq_plugin_deserialize", "mixq_plugin_clone", "mixq_plugin_destroy", "mixq_plugin_type",
     "mixq_plugin_version", "mixq_plugin_namespace", "mixq_plugin_nb_outputs",
     "mixq_plugin_serialization_size", "mixq_plugin_serialize", "mixq_plugin_supports_format",
@@ -113,8 +113,6 @@ def load() -> ctypes.CDLL:
     L.mixq_debug_set_trace.argtypes = [vp]
     L.mixq_set_sm_limit.restype = ci
     L.mixq_set_sm_limit.argtypes = [ci]
-    L.mixq_set_pdl_early_rows.restype = ci
-    L.mixq_set_pdl_early_rows.argtypes = [ci]
     L.mixq_set_gemm_config.restype = ci
     L.mixq_set_gemm_config.argtypes = [ci]
     L.initOpenAiTritonPlugins.restype = ctypes.c_bool

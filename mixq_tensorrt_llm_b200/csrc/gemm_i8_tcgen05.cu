@@ -182,10 +182,9 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr_s;
 
-    // Everything above overlaps the tail of the previous kernel (PDL).  A8 / sa / fp_A are produced by it; the weights
-    // are not: the producer fills the W half of the whole ring BEFORE waiting for the prior grid (the quantise kernel
-    // releases its dependents at its start), so that a decode-sized GEMM finds its first K-blocks of W in shared memory
-    // when the activations arrive.  Every other reader of the prior grid's output waits at the start of its role.
+    // Everything above overlaps the tail of the previous kernel (PDL); A8/sa/fp_A are produced by it.
+    ptx::pdl_wait_prior_grid();
+
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = (K + kBlockKBytes - 1) / kBlockKBytes;
     const int n_f = has_outlier ? kOutlierKBlocks : 0;
@@ -196,31 +195,13 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
             // ===================== TMA producer (every CTA) =====================
             int stage = 0;
             uint32_t phase = 0;
-            const int pre = (group_id < num_tiles) ? min(num_items, T::kStages) : 0;   // items whose W load is issued early
-            bool first_tile = true;
-            if (pre > 0) {
-                const TileCoord tc = tile_coord(group_id, m_tiles, n_tiles, group_m);
-                const int n0 = tc.n_blk * BLOCK_N + static_cast<int>(cta_rank) * T::kLoadN;
-                for (int it = 0; it < pre; ++it) {     // stages 0..pre-1, first use: the slots are free
-                    if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[it], T::kStageBytes * CTA);
-                    uint8_t* sB = ring + static_cast<size_t>(it) * T::kStageBytes + T::kABytes;
-                    const CUtensorMap* mb = it < n_f ? &tm_fw : &tm_w8;
-                    const int k0 = it < n_f ? it * (kBlockKBytes / 2) : (it - n_f) * kBlockKBytes;
-                    if constexpr (CTA == 2) ptx::tma_load_2d_2cta(sB, mb, &full_bar[it], k0, n0, ptx::kEvictNormal);
-                    else ptx::tma_load_2d(sB, mb, &full_bar[it], k0, n0, ptx::kEvictNormal);
-                }
-            }
-            ptx::pdl_wait_prior_grid();
             for (int tile = group_id; tile < num_tiles; tile += num_groups) {
                 const TileCoord tc = tile_coord(tile, m_tiles, n_tiles, group_m);
                 const int m0 = tc.m_blk * T::kTileM + static_cast<int>(cta_rank) * kBlockM;
                 const int n0 = tc.n_blk * BLOCK_N + static_cast<int>(cta_rank) * T::kLoadN;
                 for (int it = 0; it < num_items; ++it) {
-                    const bool early = first_tile && it < pre;     // barrier armed and W already in flight
-                    if (!early) {
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], T::kStageBytes * CTA);
-                    }
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (is_leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], T::kStageBytes * CTA);
                     uint8_t* sA = ring + static_cast<size_t>(stage) * T::kStageBytes;
                     uint8_t* sB = sA + T::kABytes;
                     const CUtensorMap* ma = it < n_f ? &tm_fa : &tm_a8;
@@ -228,17 +209,16 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
                     const int k0 = it < n_f ? it * (kBlockKBytes / 2) : (it - n_f) * kBlockKBytes;
                     if constexpr (CTA == 2) {
                         ptx::tma_load_2d_2cta(sA, ma, &full_bar[stage], k0, m0, ptx::kEvictNormal);
-                        if (!early) ptx::tma_load_2d_2cta(sB, mb, &full_bar[stage], k0, n0, ptx::kEvictNormal);
+                        ptx::tma_load_2d_2cta(sB, mb, &full_bar[stage], k0, n0, ptx::kEvictNormal);
                     } else {
                         ptx::tma_load_2d(sA, ma, &full_bar[stage], k0, m0, ptx::kEvictNormal);
-                        if (!early) ptx::tma_load_2d(sB, mb, &full_bar[stage], k0, n0, ptx::kEvictNormal);
+                        ptx::tma_load_2d(sB, mb, &full_bar[stage], k0, n0, ptx::kEvictNormal);
                     }
                     if (++stage == T::kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                first_tile = false;
             }
         }
         __syncwarp();
@@ -303,7 +283,6 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
         __syncwarp();
     } else if (warp_idx >= kEpilogueWarp0) {
         // ===================== epilogue (every CTA: its own 128 accumulator rows) =====================
-        ptx::pdl_wait_prior_grid();                     // scale_a comes from the prior grid; Out may still be read by it
         const int quarter = warp_idx - kEpilogueWarp0;  // == warp_idx % 4: the TMEM lane quarter this warp may read
         const int et = threadIdx.x - kEpilogueWarp0 * 32;
         const int row = quarter * 32 + lane;

@@ -15,7 +15,6 @@ thread_local char g_err[256] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_gemm_cfg{0};
 std::atomic<int> g_sm_limit{0};
-std::atomic<int> g_pdl_early_rows{256};
 
 constexpr size_t kAlign = 128;  // kCudaMemAlign, TsinghuaMixQPlugin.cpp:204
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
@@ -49,8 +48,6 @@ int usable_sms() {
     const int n = device_info().num_sms, lim = g_sm_limit.load(std::memory_order_relaxed);
     return (lim > 0 && lim < n) ? lim : n;
 }
-
-int64_t pdl_early_rows() { return g_pdl_early_rows.load(std::memory_order_relaxed); }
 
 const DeviceInfo& device_info() {
     static DeviceInfo info;
@@ -90,11 +87,6 @@ uint64_t mixq_launch_count(void) { return g_launches.load(std::memory_order_rela
 int mixq_set_sm_limit(int num_sms) {
     if (num_sms < 0) return -1;
     return g_sm_limit.exchange(num_sms);
-}
-
-int mixq_set_pdl_early_rows(int rows) {
-    if (rows < 0) return -1;
-    return g_pdl_early_rows.exchange(rows);
 }
 
 int mixq_set_gemm_config(int config_id) {

@@ -56,7 +56,5 @@ enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, k
 int current_gemm_config();
 // SMs the persistent kernels may occupy (mixq_set_sm_limit; default: all)
 int usable_sms();
-// batches of at most this many rows release the dependent GEMM at the START of the quantise kernel (mixq_set_pdl_early_rows)
-int64_t pdl_early_rows();
 
 }  // namespace mixq

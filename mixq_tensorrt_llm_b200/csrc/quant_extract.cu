@@ -89,12 +89,6 @@ mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const 
 
     // The activations are produced by the previous kernel in the stream.
     ptx::pdl_wait_prior_grid();
-    // Decode-sized batches (bit 1 of the flag word): release the dependent GEMM now.  Its CTAs move in as soon as an SM
-    // has room (most SMs are free), run their prologue and prefetch the weights; they read this kernel's output only
-    // after their own griddepcontrol.wait, i.e. after this grid has completed.  Large batches release at the end.
-    const bool early_release = (mask_outliers & 2) != 0;
-    mask_outliers &= 1;
-    if (early_release) ptx::pdl_launch_dependents();
 
     // kernel 2's stream-K flags live in the same workspace; clearing them here costs no extra launch
     if (blockIdx.x == 0)
@@ -231,7 +225,8 @@ mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const 
         }
     }
     ptx::cp_async_wait<0>();
-    if (!early_release) ptx::pdl_launch_dependents();   // let the dependent GEMM start its prologue
+    // Let the dependent GEMM start its prologue.
+    ptx::pdl_launch_dependents();
 }
 
 using QuantKernel = void (*)(const __half*, int64_t, int, const int*, int, int8_t*, __half*, __half*, int, uint32_t*, int,
@@ -292,7 +287,7 @@ int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, i
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    const int mask = ((flags & MIXQ_FLAG_MASK_OUTLIERS) ? 1 : 0) | ((pdl && M <= pdl_early_rows()) ? 2 : 0);
+    const int mask = (flags & MIXQ_FLAG_MASK_OUTLIERS) ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<const __half*>(A), M,
                                        static_cast<int>(K), static_cast<const int*>(ind), n_ind,
                                        static_cast<int8_t*>(A8), static_cast<__half*>(scale_a),
