@@ -59,16 +59,40 @@ def shard_row(packed: dict, world: int, rank: int) -> dict:
                 ind=loc_ind, n_outliers_local=int(mine.size), n_range=(0, N), k_range=(lo, hi), mode="row")
 
 
+# ---- the weight-only copy (M <= 4 branch): EETQ-processed int8 [K, N] (checkpoint.eetq_preprocess).  Its bytes are rows
+# of 2K codes per PAIR of output channels, each row made of runs of 64 codes that alternate between the two channels
+# and cover 64 consecutive (permuted-in-16s) input channels: it can be cut along N at even channels and along K at
+# multiples of 64 without undoing the layout.
+def shard_qweight_column(qweight: np.ndarray, world: int, rank: int) -> np.ndarray:
+    """Column-parallel shard of the processed qweight: output channels [rank*N/world, (rank+1)*N/world)."""
+    K, N = qweight.shape
+    lo, hi = shard_bounds(N, world, rank, multiple=64)        # 64: what the reference packer accepts per shard
+    rows = qweight.reshape(N // 2, 2 * K)
+    return np.ascontiguousarray(rows[lo // 2: hi // 2]).reshape(K, hi - lo)
+
+
+def shard_qweight_row(qweight: np.ndarray, world: int, rank: int) -> np.ndarray:
+    """Row-parallel shard of the processed qweight: input channels [rank*K/world, (rank+1)*K/world)."""
+    K, N = qweight.shape
+    lo, hi = shard_bounds(K, world, rank, multiple=64)
+    runs = qweight.reshape(N // 2, K // 64, 128)              # per channel pair: K/64 blocks of (64 codes of ch 0 | 64 of ch 1)
+    return np.ascontiguousarray(runs[:, lo // 64: hi // 64]).reshape(hi - lo, N)
+
+
 def shard_linear(packed: dict, mode: str, world: int, rank: int) -> dict:
     if world == 1:
         d = dict(packed)
         d.update(n_range=(0, packed["W8"].shape[0]), k_range=(0, packed["W8"].shape[1]), mode=mode)
         return d
-    if mode == "column":
-        return shard_column(packed, world, rank)
-    if mode == "row":
-        return shard_row(packed, world, rank)
-    raise ValueError("mode must be 'column' or 'row'")
+    if mode not in ("column", "row"):
+        raise ValueError("mode must be 'column' or 'row'")
+    d = shard_column(packed, world, rank) if mode == "column" else shard_row(packed, world, rank)
+    if "qweight" in packed:                                   # the weight-only copy follows the same cut
+        d["qweight"] = (shard_qweight_column if mode == "column" else shard_qweight_row)(packed["qweight"], world, rank)
+        if "scales" in packed:
+            lo, hi = d["n_range"]
+            d["scales"] = np.ascontiguousarray(packed["scales"][lo:hi])
+    return d
 
 
 def shard_activations(A: np.ndarray, shard: dict) -> np.ndarray:

@@ -272,6 +272,12 @@ static inline f16 dev_hfma(f16 a, f16 b, f16 c) {
     return (f16)s;
 }
 
+/* test hook: the emulated device __hfma on raw fp16 bit patterns (tests/test_oracle.py checks it against exact rational
+   arithmetic) */
+uint16_t mixq_oracle_hfma(uint16_t a, uint16_t b, uint16_t c) {
+    return f16_to_bits(dev_hfma(bits_to_f16(a), bits_to_f16(b), bits_to_f16(c)));
+}
+
 static inline int gemv_byte_pos(int y) {
     const int p = (y / 8) * 2 + ((y % 8) / 2) * 4 + (y % 2);
     const int q = p & 3;

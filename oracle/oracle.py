@@ -63,6 +63,8 @@ def lib():
         L.mixq_oracle_rmsnorm.restype = None
         L.mixq_oracle_gemv_w8a16.argtypes = [u16p, ctypes.POINTER(ctypes.c_uint8), u16p, i64, i64, i64, u16p]
         L.mixq_oracle_gemv_w8a16.restype = None
+        L.mixq_oracle_hfma.argtypes = [ctypes.c_uint16] * 3
+        L.mixq_oracle_hfma.restype = ctypes.c_uint16
         L.mixq_oracle_num_threads.restype = i32
         L.mixq_oracle_set_threads.argtypes = [i32]
         L.mixq_oracle_set_threads.restype = None

@@ -255,3 +255,58 @@ def test_epilogue_ex_reduces_to_epilogue(oracle):
     d = oracle.epilogue_ex(acc, sa, sb, out0, silu=True).astype(np.float32)
     x = a.astype(np.float32)
     assert np.allclose(d, x / (1 + np.exp(-x)), rtol=2e-3, atol=2e-3)
+
+
+def test_emulated_hfma_is_the_exactly_rounded_fma(oracle):
+    """dev_hfma (the fp16 FMA chain of the weight-only GEMV restatement) against exact rational arithmetic: a*b+c
+    computed with fractions and rounded ONCE to fp16, round-to-nearest-even, over random and adversarial triples
+    (ties created by a tiny addend next to a 22-bit product, subnormals, overflow to inf, signed zeros)."""
+    from fractions import Fraction
+    L = oracle.lib()
+
+    def f16(bits):
+        return np.array([bits], dtype=np.uint16).view(np.float16)[0]
+
+    def round_f16(x: Fraction) -> int:
+        """exact RN-even rounding of a rational to fp16 bits"""
+        if x == 0:
+            return 0
+        sign = 0x8000 if x < 0 else 0
+        x = abs(x)
+        e = -24                                     # find e with 2^e <= ulp grid: value = m * 2^e, m < 2^11 for normals
+        import math
+        ex = math.floor(math.log2(float(x))) if x >= Fraction(1, 2 ** 30) else -40
+        while Fraction(2) ** ex > x:
+            ex -= 1
+        while Fraction(2) ** (ex + 1) <= x:
+            ex += 1
+        q = max(ex - 10, -24)                       # quantum exponent (subnormals share 2^-24)
+        m = x / Fraction(2) ** q
+        fl = m.numerator // m.denominator
+        rem = m - fl
+        if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and (fl & 1)):
+            fl += 1
+        val = Fraction(fl) * Fraction(2) ** q
+        if val >= Fraction(65520):
+            return sign | 0x7C00
+        return sign | int(np.array([float(val)], dtype=np.float16).view(np.uint16)[0])
+
+    rng = np.random.default_rng(0)
+    triples = []
+    for _ in range(4000):
+        a, b, c = (int(v) for v in rng.integers(0, 0x7C00, 3))       # finite, positive magnitudes ...
+        s = rng.integers(0, 2, 3) * 0x8000                            # ... random signs
+        triples.append((a | int(s[0]), b | int(s[1]), c | int(s[2])))
+    # adversarial: product exactly on an fp16 tie, addend far below -> the sticky information decides
+    for pa, pb in ((0x3C01, 0x3C01), (0x4401, 0x3C03), (0x3E01, 0x3A01), (0x7801, 0x3401)):
+        for cbits in (0x0001, 0x8001, 0x0000, 0x8000, 0x0400, 0x8400):
+            triples.append((pa, pb, cbits))
+    triples += [(0x7BFF, 0x7BFF, 0x0001), (0x0001, 0x0001, 0x0001), (0x0001, 0x3C00, 0x8001), (0x8000, 0x3C00, 0x0000)]
+    for a, b, c in triples:
+        exact = Fraction(float(f16(a))) * Fraction(float(f16(b))) + Fraction(float(f16(c)))
+        want = round_f16(exact)
+        got = int(L.mixq_oracle_hfma(a, b, c))
+        if exact == 0:                              # signed zero: IEEE sum rule, not representable in a Fraction
+            assert got & 0x7FFF == 0
+            continue
+        assert got == want, (hex(a), hex(b), hex(c), hex(got), hex(want))

@@ -118,3 +118,33 @@ def test_mixqlinear_tp_shapes():
     assert col.weights_scaling_factor.shape == (1536,) and col.weight.dtype == torch.float16
     row = MixQLinear(11008, 4096, tp_size=8, parallel_mode="row")
     assert row.weight.shape == (4096, 688) and row.in_features == 1376 and row.out_features == 4096
+
+
+def test_qweight_shards_equal_processing_the_sharded_codes():
+    """The EETQ-processed weight-only copy can be cut without undoing its layout: a column (N) or row (K) shard of the
+    processed tensor equals processing the matching slice of the plain codes, and the weight-only GEMV over the shards
+    reproduces the slice / sums to the unsharded product."""
+    import numpy as np
+    from oracle import oracle as O
+    from mixq_tensorrt_llm_b200 import tp
+    rng = np.random.default_rng(0)
+    K, N, world = 512, 256, 2
+    codes = rng.integers(-128, 128, (K, N), dtype=np.int8)
+    proc = O.eetq_preprocess(codes)
+    scales = (rng.random(N) * 1e-3 + 1e-4).astype(np.float16)
+    A = rng.standard_normal((2, K)).astype(np.float16)
+    full = O.gemv_w8a16(A, proc, scales)
+    packed = dict(W8=np.zeros((N, K), np.int8), scale_b=scales, fp_weight=np.zeros((N, 128), np.float16),
+                  ind=np.arange(128, dtype=np.int32), qweight=proc, scales=scales)
+    for r in range(world):
+        col = tp.shard_linear(packed, "column", world, r)
+        n0, n1 = col["n_range"]
+        assert np.array_equal(col["qweight"], O.eetq_preprocess(codes[:, n0:n1]))
+        assert np.array_equal(O.gemv_w8a16(A, col["qweight"], col["scales"]).view(np.uint16), full[:, n0:n1].view(np.uint16))
+        row = tp.shard_linear(packed, "row", world, r)
+        k0, k1 = row["k_range"]
+        assert np.array_equal(row["qweight"], O.eetq_preprocess(codes[k0:k1]))
+    parts = [O.gemv_w8a16(A[:, k0:k1], tp.shard_qweight_row(proc, world, r), scales).astype(np.float32)
+             for r, (k0, k1) in enumerate([(0, K // 2), (K // 2, K)])]
+    ref = A.astype(np.float64) @ (codes.astype(np.float64) * scales.astype(np.float64)[None, :])
+    assert np.abs(parts[0] + parts[1] - ref).max() <= 4e-3 * np.abs(ref).max() + 2e-3
