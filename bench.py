@@ -346,7 +346,9 @@ def run_ours(args, M, linears):
                 "achieved": round(achieved, 1), "peak": round(int8_peak, 1), "unit": "TFLOP/s",
                 "frac": round(achieved / int8_peak, 4),
                 "peak_source": f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({pk['src']}); INT8 dense = 2 x BF16 dense",
-                "frac_of_spec_4500": round(achieved / 4500.0, 4), "traffic": traffic_from_profile(),
+                "frac_of_spec_4500": round(achieved / 4500.0, 4),
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (ncu --set full capture)
+                "traffic": (traffic_from_profile() or {}).get("bytes"), "traffic_detail": traffic_from_profile(),
                 "share_of_step": round(tot_gemm / (tot_gemm + tot_quant), 4),
                 "quant_kernel": {"bound": "hbm", "achieved": round(sum((3.0 * M * k + 258.0 * M) for _, _, _, k, _ in mods) / tot_quant / 1e3, 1),
                                  "peak": pk["hbm"], "unit": "GB/s"},
