@@ -204,3 +204,46 @@ int main(void) {
     assert b == [ctypes.sizeof(P), P.out.offset, P.staging.offset, P.counters.offset, P.staging_bytes.offset, P.counter_bytes.offset,
                  P.out_multicast.offset]
     assert e == [ctypes.sizeof(E), E.activation.offset]
+
+
+def test_c_program_links_and_calls_the_abi(tmp_path, lib):
+    """A plain C translation unit includes the header, links libmixq_b200.so and calls the host-only entry points:
+    the boundary really is a C ABI (no C++ / torch types), and failures come back as status codes, not exceptions."""
+    from mixq_tensorrt_llm_b200 import binding
+    src = r'''
+#include <stdio.h>
+#include <string.h>
+#include "mixq_b200.h"
+int main(void) {
+    mixq_tensors t; memset(&t, 0, sizeof t);
+    mixq_peer_group g; memset(&g, 0, sizeof g);
+    mixq_epilogue e = {0, MIXQ_ACT_SILU};
+    printf("%s\n", mixq_version());
+    printf("%zu %zu %zu\n", mixq_workspace_size(512, 12288, 4096), mixq_allreduce_staging_size(512, 8192, 8), mixq_gemm_workspace_size());
+    printf("%d\n", mixq_enqueue(0, 8, 8, 16, 0, 0, 0, 0));                       /* null table  -> MIXQ_ERR_BAD_ARG */
+    printf("%d\n", mixq_enqueue(&t, 8, 8, 16, 0, 0, 0, 0));                      /* null tensor -> MIXQ_ERR_BAD_ARG */
+    printf("%d\n", mixq_enqueue_ex(&t, 0, 8, 16, 0, 0, &e, 0, 0));               /* M == 0      -> MIXQ_OK          */
+    printf("%d\n", mixq_enqueue_allreduce(&t, 8, 8, 16, 0, 0, &g, 0, 0));        /* null tensor -> MIXQ_ERR_BAD_ARG */
+    printf("%d\n", mixq_gemv_w8a16(0, 0, 0, 0, 2, 8, 64, 0));                    /* null ptr    -> MIXQ_ERR_BAD_ARG */
+    printf("%d\n", (int)initOpenAiTritonPlugins(0, "tensorrt_llm"));
+    mixq_plugin_t* p = mixq_plugin_create("tensorrt_llm", 1, 2, 3);
+    printf("%s %s %d\n", mixq_plugin_type(p), mixq_plugin_version(p), mixq_plugin_nb_outputs(p));
+    mixq_plugin_destroy(p);
+    printf("[%s]\n", strlen(mixq_last_error()) ? "has-error-text" : "");
+    return 0;
+}'''
+    c = tmp_path / "abi.c"
+    c.write_text(src)
+    exe = tmp_path / "abi"
+    libdir = binding.LIB_PATH.parent
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(c), "-o", str(exe),
+                        "-L", str(libdir), "-lmixq_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    ln = out.stdout.splitlines()
+    assert ln[0].startswith("mixq-b200")
+    ws, st, gw = map(int, ln[1].split())
+    assert ws >= 512 * 4096 + 2 * 512 + 256 * 512 and st == 512 * 8192 * 2 and gw > 0
+    assert [int(x) for x in ln[2:7]] == [-1, -1, 0, -1, -1]
+    assert ln[7] == "1" and ln[8] == "MixQ 1 1" and ln[9] == "[has-error-text]"
