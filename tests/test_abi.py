@@ -143,6 +143,12 @@ def test_no_cpu_fallback(lib):
     assert rc == -3 and b"device" in lib.mixq_last_error()
     rc = lib.mixq_gemm_dequant(p, p, p, p, None, None, p, 8, 8, 64, None)
     assert rc == -3
+    assert lib.mixq_gemv_w8a16(p, p, p, p, 2, 8, 64, None) == -3                        # the M <= 4 branch likewise
+    g = binding.PeerGroup()
+    g.world, g.rank = 1, 0
+    g.out[0] = g.staging[0] = g.counters[0] = p
+    g.staging_bytes, g.counter_bytes = 1 << 20, 4096
+    assert lib.mixq_gemm_dequant_allreduce(p, p, p, p, None, None, 8, 8, 64, ctypes.byref(g), None) == -3   # and the fused all-reduce
 
 
 def test_product_does_not_touch_oracle():
