@@ -15,6 +15,7 @@ SURVEY.md 8f "next #3".  The reference produces the layout in
                                        of W^T in the interleaved layout of cutlass_preprocessors.cc:497-533 (:437-440)
     scales                  [N]        its scales, max_k |W[n,k]| / 128 (:441; the plugin is fed weights_scaling_factor
                                        instead, plugin.py:149 -- kept as the reference has it)
+    bias                    [N]        optional (Qwen2's qkv): added after the plugin, plugin.py:158-160
 
 This module needs neither mixlib nor EETQ: their ``int8_matrix_to_half`` / ``int_to_half`` helpers are
 byte reinterpretations (``Tensor.view(torch.float16)``).  The reference hard-codes its activation
@@ -95,6 +96,8 @@ def to_checkpoint_tensors(packed: Mapping[str, torch.Tensor]) -> Dict[str, torch
     if "qweight" in packed:
         out["qweight"] = packed["qweight"].contiguous().view(torch.float16)      # [K, N/2], mixlib.int8_matrix_to_half
         out["scales"] = packed["scales"].contiguous()
+    if packed.get("bias") is not None:                                           # Qwen2's qkv bias: MixQLinear.bias, plugin.py:131-134
+        out["bias"] = packed["bias"].to(torch.float16).contiguous()
     return out
 
 
@@ -110,6 +113,8 @@ def from_checkpoint_tensors(t: Mapping[str, torch.Tensor]) -> Dict[str, torch.Te
         out["qweight"] = t["qweight"].contiguous().view(torch.int8)
         if "scales" in t:
             out["scales"] = t["scales"].reshape(-1)
+    if "bias" in t:
+        out["bias"] = t["bias"].reshape(-1)
     return out
 
 
@@ -144,7 +149,7 @@ def load_checkpoint(path, rank: int = 0) -> Dict[int, Dict[str, Dict[str, torch.
             if len(parts) < 6 or parts[0] != "transformer" or parts[1] != "layers":
                 continue
             lin, name = ".".join(parts[3:5]), parts[5]
-            if lin in MIXQ_LINEARS and name in ("weight", "weights_scaling_factor", "fp_weight", "fp_ind", "qweight", "scales"):
+            if lin in MIXQ_LINEARS and name in ("weight", "weights_scaling_factor", "fp_weight", "fp_ind", "qweight", "scales", "bias"):
                 raw.setdefault((int(parts[2]), lin), {})[name] = f.get_tensor(key)
     for (i, lin), t in raw.items():
         if all(k in t for k in ("weight", "weights_scaling_factor", "fp_weight", "fp_ind")):
@@ -155,6 +160,7 @@ def load_checkpoint(path, rank: int = 0) -> Dict[int, Dict[str, Dict[str, torch.
 def load_into(module, packed: Mapping[str, torch.Tensor]):
     """Fill a ``MixQLinear`` from a typed packed dict."""
     dev = module.weight.device
-    qw = packed.get("qweight")
+    qw, bias = packed.get("qweight"), packed.get("bias")
     return module.load_packed(packed["W8"].to(dev), packed["scale_b"].to(dev), packed["fp_weight"].to(dev),
-                              packed["ind"].to(dev), qweight=qw.to(dev) if qw is not None else None)
+                              packed["ind"].to(dev), bias=bias.to(dev) if bias is not None else None,
+                              qweight=qw.to(dev) if qw is not None else None)

@@ -97,3 +97,27 @@ def test_eetq_pair_matches_reference_packer_and_roundtrips(tmp_path, oracle):
     back = C.load_checkpoint(tmp_path)[0]["attention.qkv"]
     assert torch.equal(back["qweight"].reshape(-1), p["qweight"].reshape(-1)) and torch.equal(back["scales"], p["scales"])
     assert torch.equal(back["W8"].reshape(-1), p["W8"].reshape(-1))
+
+
+def test_qwen2_shaped_layer_with_qkv_bias_roundtrips(tmp_path):
+    """configs[3]: a Qwen2-7B-shaped layer (hidden 3584, qkv 4608 WITH bias, FFN 18944; scaled down 8x here) packed,
+    written in the reference's key layout, read back and sharded; the bias travels with the qkv linear."""
+    from mixq_tensorrt_llm_b200 import checkpoint as C
+    torch.manual_seed(1)
+    H, QKV, FFN = 3584 // 8, 4608 // 8, 18944 // 8       # 448, 576, 2368: K % 64 == 0, N % 64 == 0
+    act = {k: torch.rand(H) for k in ("qkv", "gate")}
+    layer = {
+        "attention.qkv": dict(C.pack_linear_weights((torch.randn(QKV, H) * 0.02).half(), act["qkv"], with_qweight=True),
+                              bias=(torch.randn(QKV) * 0.1).half()),
+        "mlp.gate": C.pack_linear_weights((torch.randn(FFN, H) * 0.02).half(), act["gate"]),
+        "mlp.proj": C.pack_linear_weights((torch.randn(H, FFN) * 0.02).half(), torch.rand(FFN)),
+    }
+    C.save_checkpoint(tmp_path, [layer], config={"architecture": "Qwen2ForCausalLM"})
+    back = C.load_checkpoint(tmp_path)[0]
+    assert set(back) == set(layer)
+    assert torch.equal(back["attention.qkv"]["bias"], layer["attention.qkv"]["bias"])
+    assert "bias" not in back["mlp.gate"]
+    for lin in layer:
+        for k in ("W8", "scale_b", "fp_weight", "ind"):
+            assert torch.equal(back[lin][k].reshape(-1), layer[lin][k].reshape(-1)), (lin, k)
+    assert back["attention.qkv"]["qweight"].numel() == QKV * H
