@@ -504,7 +504,7 @@ def run_ours(args, M, linears):
         from oracle import oracle as O
         O.build()
         O.set_threads()
-        sample = args.cpu_sample_tokens
+        sample = min(M, max(args.cpu_sample_tokens, args.cpu_baseline_tokens))   # ~10 s of host work on 16 cores
         t_cpu = 0.0
         for name, N, K, _ in linears:
             lin = O.synth_linear(N, K, None, seed=1)
@@ -546,7 +546,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="llama2-7b-linears-bs32xseq2048", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample-tokens", type=int, default=512)
+    ap.add_argument("--cpu-sample-tokens", type=int, default=512, help="tokens per step of the --impl reference arm")
+    ap.add_argument("--cpu-baseline-tokens", type=int, default=4096, help="token sample of the cpu_baseline leg of our arm")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--tp-chunks", type=int, default=4, help="row slabs per row-parallel linear (comm/compute overlap)")
     ap.add_argument("--comm-sms", type=int, default=40, help="SMs left free for NCCL when slabs overlap (tensor parallel only)")
