@@ -227,9 +227,21 @@ def run_ours(args, M, linears):
     # NVLink peer memory, fp32 reduce, result written to every rank) -- mixq_enqueue_allreduce.  --tp-reduce nccl keeps
     # the unfused baseline (mixq_enqueue + NCCL all-reduce in overlapped row slabs) for comparison.
     peer = None
+    peer_note = None
     if tp > 1 and args.tp_reduce == "fused":
         from mixq_tensorrt_llm_b200.peer import PeerBuffers
-        peer = PeerBuffers(M, max(Ns for _, _, Ns, _, mode in mods if mode == "row"), device=dev)
+        try:
+            peer = PeerBuffers(M, max(Ns for _, _, Ns, _, mode in mods if mode == "row"), device=dev)
+            ok = 1
+        except Exception as e:   # no peer mapping on this box (symmetric memory unavailable): every rank must agree
+            peer_note, ok = repr(e)[:160], 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            peer = None
+            peer_note = peer_note or "peer buffers unavailable on another rank"
+            print(f"[bench] fused all-reduce unavailable ({peer_note}); row-parallel linears use mixq_enqueue + NCCL",
+                  file=sys.stderr, flush=True)
 
     def step():
         for name, mod, Ns, Ks, mode in mods:
@@ -524,6 +536,7 @@ def run_ours(args, M, linears):
                 "config": {"workload": args.workload, "tokens_per_step": M,
                            "linears": [[n, N, K, m] for n, N, K, m in linears],
                            "comm_sms": args.comm_sms if (tp > 1 and chunks > 1 and peer is None) else 0,
+                           **({"fused_allreduce_unavailable": peer_note} if peer_note else {}),
                            "launch": "cuda-graph replay of the step" if use_graph else "direct launches",
                            "parallelism": ("single" if tp == 1 else
                                            f"tp{tp} (column: no collective; row: all-reduce fused into the GEMM kernel over NVLink peer memory)"
