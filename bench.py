@@ -255,17 +255,15 @@ def run_ours(args, M, linears):
                 # the NCCL all-reduce of slab c (on NCCL's stream) overlaps the GEMM of slab c+1.
                 works = []
                 rows = M // chunks
-                if chunks > 1 and args.comm_sms > 0:
-                    # the GEMM is persistent (one CTA per SM): while slabs of THIS linear are in flight keep a few
-                    # SMs free so NCCL's channels (32 CTAs) can run beside it (measured: 1.52 -> 1.43 ms for o_proj @ tp2)
-                    lib.mixq_set_sm_limit(nsm - args.comm_sms)
+                # the GEMM is persistent (one CTA per SM): while slabs of THIS linear are in flight keep a few
+                # SMs free so NCCL's channels (32 CTAs) can run beside it (measured: 1.52 -> 1.43 ms for o_proj @ tp2)
+                lim = nsm - args.comm_sms if (chunks > 1 and args.comm_sms > 0) else 0
                 for c in range(chunks):
                     a, o = acts[Ks][c * rows:(c + 1) * rows], out[c * rows:(c + 1) * rows]
-                    B.enqueue(a, W8, mod.weights_scaling_factor, mod.fp_weight, mod.fp_ind.view(torch.int32), o, ws)
+                    B.enqueue(a, W8, mod.weights_scaling_factor, mod.fp_weight, mod.fp_ind.view(torch.int32), o, ws, sm_limit=lim)
                     works.append(dist.all_reduce(o, async_op=True))
                 for w in works:
                     w.wait()
-                lib.mixq_set_sm_limit(0)
             else:
                 B.enqueue(acts[Ks], W8, mod.weights_scaling_factor, mod.fp_weight, mod.fp_ind.view(torch.int32), out, ws)
 

@@ -74,7 +74,9 @@ int mixq_device_ok(void);
 
 /* Bytes of device workspace mixq_enqueue needs for (M, N, K). Layout (each
  * block 128-byte aligned, as nextWorkspacePtr does, TsinghuaMixQPlugin.cpp:206-215):
- *   A8 int8 [M,K] | scale_a fp16 [M] | fp_A fp16 [M,128] | stream-K scratch (~10 MB, M-independent)
+ *   A8 int8 [M,K] | scale_a fp16 [M] | fp_A fp16 [M,128] | split-K scratch: flags + int32 partial-sum slots (31.4 MB,
+ *   M-independent) + fp16 outlier product of the decode kernel's tiles (2 * min(M,1024)pad256 * Npad256 bytes);
+ *   non-decreasing in M, so the size for a profile's maximum covers every smaller batch
  * Replaces the reference's max(M*K + 2M + 2*K*N, 16*M*N) (TsinghuaMixQPlugin.cpp:342-346). */
 size_t mixq_workspace_size(int64_t M, int64_t N, int64_t K);
 
@@ -214,14 +216,35 @@ uint64_t mixq_launch_count(void);
  * epilogue done); NULL (default) disables it. */
 int mixq_debug_set_trace(void* dev_buf);
 
-/* Cap the number of SMs the persistent kernels occupy (0 = all).  Leaving a few SMs free lets a
- * communication kernel (the NCCL all-reduce of a row-parallel linear) run concurrently with the GEMM of the
- * next row slab instead of queueing behind it.  Returns the previous value. */
-int mixq_set_sm_limit(int num_sms);
-
-/* GEMM tile configuration override for tuning/tests: 0 = auto. Returns the
- * previous value. Valid ids are listed in DESIGN.md. */
-int mixq_set_gemm_config(int config_id);
+/* ---- per-call tuning ------------------------------------------------------------------------------------------
+ * The library keeps no mutable process-wide state (SURVEY.md 8b "no static mutable state"): a caller that wants a
+ * particular tile configuration, or wants to leave SMs free for a concurrent communication kernel, says so on the
+ * call.  Nothing in mixq_options changes a result bit.  opt == NULL (and every entry point without an `opt`
+ * argument) means {0, 0}. */
+typedef struct mixq_options {
+    int gemm_config; /* 0 = pick by shape; ids are listed in DESIGN.md (tests pin every id against the oracle) */
+    int sm_limit;    /* SMs the persistent kernels may occupy, 0 = all of the current device                    */
+} mixq_options;
+/* mixq_enqueue_ex / mixq_gemm_dequant_ws+_ex / mixq_enqueue_allreduce / mixq_gemm_dequant_allreduce with options.
+ * Unknown config ids fail with MIXQ_ERR_BAD_ARG. */
+int mixq_enqueue_opt(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace,
+                     size_t workspace_bytes, const mixq_epilogue* epi, const mixq_options* opt,
+                     unsigned flags, void* stream);
+int mixq_gemm_dequant_opt(const void* A8, const void* W8, const void* scale_a, const void* scale_b,
+                          const void* fp_A, const void* fp_weight, void* Out, int64_t M, int64_t N,
+                          int64_t K, const mixq_epilogue* epi, const mixq_options* opt, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int mixq_enqueue_allreduce_opt(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace,
+                               size_t workspace_bytes, const mixq_peer_group* g, const mixq_options* opt,
+                               unsigned flags, void* stream);
+int mixq_gemm_dequant_allreduce_opt(const void* A8, const void* W8, const void* scale_a,
+                                    const void* scale_b, const void* fp_A, const void* fp_weight,
+                                    int64_t M, int64_t N, int64_t K, const mixq_peer_group* g,
+                                    const mixq_options* opt, void* stream);
+/* Scratch stage 2 needs to run the decode-batch kernel (M <= 1024: split-K partial sums + the fp16 outlier product
+ * of every tile): mixq_gemm_workspace_size() plus an (M, N)-dependent part.  mixq_workspace_size()
+ * already includes it; a mixq_gemm_dequant_ws/_opt call with less scratch uses the whole-tile kernels. */
+size_t mixq_decode_workspace_size(int64_t M, int64_t N);
 
 /* ---- TensorRT plugin surface through C handles (for ctypes / C callers) ----
  * Mirrors MixQPluginCreator / MixQPlugin (TsinghuaMixQPlugin.h:34-115). */

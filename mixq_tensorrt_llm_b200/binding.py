@@ -23,7 +23,9 @@ EXPORTS = [
     "mixq_quant_extract", "mixq_rmsnorm_quant_extract", "mixq_gemv_w8a16", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
     "mixq_host_scratch_size", "mixq_linear_host",
     "mixq_allreduce_staging_size", "mixq_allreduce_counter_size", "mixq_enqueue_allreduce", "mixq_gemm_dequant_allreduce",
-    "mixq_launch_count", "mixq_set_gemm_config", "mixq_set_sm_limit", "mixq_debug_set_trace", "initOpenAiTritonPlugins", "mixq_plugin_create",
+    "mixq_enqueue_opt", "mixq_gemm_dequant_opt", "mixq_enqueue_allreduce_opt", "mixq_gemm_dequant_allreduce_opt",
+    "mixq_decode_workspace_size",
+    "mixq_launch_count", "mixq_debug_set_trace", "initOpenAiTritonPlugins", "mixq_plugin_create",
     "mixq_plugin_deserialize", "mixq_plugin_clone", "mixq_plugin_destroy", "mixq_plugin_type",
     "mixq_plugin_version", "mixq_plugin_namespace", "mixq_plugin_nb_outputs",
     "mixq_plugin_serialization_size", "mixq_plugin_serialize", "mixq_plugin_supports_format",
@@ -49,6 +51,11 @@ class Epilogue(ctypes.Structure):
     """struct mixq_epilogue"""
     _fields_ = [("bias", ctypes.c_void_p), ("activation", ctypes.c_int)]
 
+
+
+class Options(ctypes.Structure):
+    """struct mixq_options: per-call tuning (tile configuration id, SM limit); never changes a result bit"""
+    _fields_ = [("gemm_config", ctypes.c_int), ("sm_limit", ctypes.c_int)]
 
 
 class PeerGroup(ctypes.Structure):
@@ -111,10 +118,17 @@ def load() -> ctypes.CDLL:
     L.mixq_launch_count.restype = ctypes.c_uint64
     L.mixq_debug_set_trace.restype = ci
     L.mixq_debug_set_trace.argtypes = [vp]
-    L.mixq_set_sm_limit.restype = ci
-    L.mixq_set_sm_limit.argtypes = [ci]
-    L.mixq_set_gemm_config.restype = ci
-    L.mixq_set_gemm_config.argtypes = [ci]
+    PE, PO, PT, PG = ctypes.POINTER(Epilogue), ctypes.POINTER(Options), ctypes.POINTER(Tensors), ctypes.POINTER(PeerGroup)
+    L.mixq_enqueue_opt.restype = ci
+    L.mixq_enqueue_opt.argtypes = [PT, i64, i64, i64, vp, sz, PE, PO, u32, vp]
+    L.mixq_gemm_dequant_opt.restype = ci
+    L.mixq_gemm_dequant_opt.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, PE, PO, vp, sz, vp]
+    L.mixq_enqueue_allreduce_opt.restype = ci
+    L.mixq_enqueue_allreduce_opt.argtypes = [PT, i64, i64, i64, vp, sz, PG, PO, u32, vp]
+    L.mixq_gemm_dequant_allreduce_opt.restype = ci
+    L.mixq_gemm_dequant_allreduce_opt.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, PG, PO, vp]
+    L.mixq_decode_workspace_size.restype = sz
+    L.mixq_decode_workspace_size.argtypes = [i64, i64]
     L.initOpenAiTritonPlugins.restype = ctypes.c_bool
     L.initOpenAiTritonPlugins.argtypes = [vp, ctypes.c_char_p]
     L.mixq_plugin_create.restype = vp
@@ -180,13 +194,22 @@ def make_tensors(A, W8, scale_b, fp_weight, ind, Out, q_weight=None, scaling_fac
     return t
 
 
+def _opts(config: int, sm_limit: int):
+    return ctypes.byref(Options(int(config), int(sm_limit))) if (config or sm_limit) else None
+
+
 def enqueue(A, W8, scale_b, fp_weight, ind, Out, workspace, flags: int = 0, stream=None, q_weight=None,
-            scaling_factors=None, bias=None, activation: int = 0) -> None:
+            scaling_factors=None, bias=None, activation: int = 0, config: int = 0, sm_limit: int = 0) -> None:
     """mixq_enqueue on torch CUDA tensors (A [M,K] fp16 contiguous, Out [M,N] fp16).  With q_weight / scaling_factors
     (the EETQ pair) a call with M <= 4 takes the weight-only branch, as the reference plugin does."""
     M, K = A.shape
     N = Out.shape[-1]
     t = make_tensors(A, W8, scale_b, fp_weight, ind, Out, q_weight, scaling_factors)
+    if config or sm_limit:
+        e = Epilogue(bias.data_ptr() if bias is not None else None, int(activation))
+        check(load().mixq_enqueue_opt(ctypes.byref(t), M, N, K, _ptr(workspace), workspace.numel() * workspace.element_size(),
+                                      ctypes.byref(e), _opts(config, sm_limit), flags, _stream(stream)), "mixq_enqueue_opt")
+        return
     if bias is not None or activation:
         e = Epilogue(bias.data_ptr() if bias is not None else None, int(activation))
         check(load().mixq_enqueue_ex(ctypes.byref(t), M, N, K, _ptr(workspace), workspace.numel() * workspace.element_size(),
@@ -212,9 +235,17 @@ def rmsnorm_quant_extract(X, gamma, eps, ind, A8, scale_a, fp_A, Y=None, flags: 
 
 
 def gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, stream=None, workspace=None, bias=None,
-                 activation: int = 0) -> None:
+                 activation: int = 0, config: int = 0, sm_limit: int = 0) -> None:
+    """Stage 2.  ``config`` / ``sm_limit`` are the per-call mixq_options (tests pin every tile configuration)."""
     M, K = A8.shape
     N = W8.shape[0]
+    if config or sm_limit:
+        e = Epilogue(bias.data_ptr() if bias is not None else None, int(activation))
+        check(load().mixq_gemm_dequant_opt(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A), _ptr(fp_weight),
+                                           _ptr(Out), M, N, K, ctypes.byref(e), _opts(config, sm_limit), _ptr(workspace),
+                                           workspace.numel() * workspace.element_size() if workspace is not None else 0,
+                                           _stream(stream)), "mixq_gemm_dequant_opt")
+        return
     if bias is not None or activation:
         e = Epilogue(bias.data_ptr() if bias is not None else None, int(activation))
         check(load().mixq_gemm_dequant_ex(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A), _ptr(fp_weight),
@@ -242,20 +273,22 @@ def make_peer_group(world: int, rank: int, out_ptrs, staging_ptrs, counter_ptrs,
     return g
 
 
-def enqueue_allreduce(A, W8, scale_b, fp_weight, ind, workspace, group: PeerGroup, flags: int = 0, stream=None) -> None:
+def enqueue_allreduce(A, W8, scale_b, fp_weight, ind, workspace, group: PeerGroup, flags: int = 0, stream=None,
+                      sm_limit: int = 0) -> None:
     """mixq_enqueue_allreduce: the reduced [M,N] result lands in group.out[i] on every rank i."""
     M, K = A.shape
     N = W8.shape[0]
     t = make_tensors(A, W8, scale_b, fp_weight, ind, None)
-    check(load().mixq_enqueue_allreduce(ctypes.byref(t), M, N, K, _ptr(workspace), workspace.numel() * workspace.element_size(),
-                                        ctypes.byref(group), flags, _stream(stream)), "mixq_enqueue_allreduce")
+    check(load().mixq_enqueue_allreduce_opt(ctypes.byref(t), M, N, K, _ptr(workspace), workspace.numel() * workspace.element_size(),
+                                            ctypes.byref(group), _opts(0, sm_limit), flags, _stream(stream)), "mixq_enqueue_allreduce")
 
 
-def gemm_dequant_allreduce(A8, W8, scale_a, scale_b, fp_A, fp_weight, group: PeerGroup, stream=None) -> None:
+def gemm_dequant_allreduce(A8, W8, scale_a, scale_b, fp_A, fp_weight, group: PeerGroup, stream=None, sm_limit: int = 0) -> None:
     M, K = A8.shape
     N = W8.shape[0]
-    check(load().mixq_gemm_dequant_allreduce(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A), _ptr(fp_weight),
-                                             M, N, K, ctypes.byref(group), _stream(stream)), "mixq_gemm_dequant_allreduce")
+    check(load().mixq_gemm_dequant_allreduce_opt(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A), _ptr(fp_weight),
+                                                 M, N, K, ctypes.byref(group), _opts(0, sm_limit), _stream(stream)),
+          "mixq_gemm_dequant_allreduce")
 
 
 def gemv_w8a16(A, q_weight, scales, Out, stream=None) -> None:

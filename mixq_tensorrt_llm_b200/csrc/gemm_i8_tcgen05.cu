@@ -769,6 +769,8 @@ __device__ __forceinline__ void multimem_st_v4(void* mc_ptr, uint32_t a, uint32_
                  : "memory");
 }
 
+#include "gemm_decode.cuh"
+
 // ---- fused all-reduce of a row-parallel linear -------------------------------------------------
 // Every rank computes the fp16 partial of every output tile; tile t is OWNED by rank t % world.
 //   phase A (GEMM epilogue):  the partial tile leaves shared memory through 2 KB bulk copies (one per 32x32 chunk)
@@ -1522,7 +1524,8 @@ struct IsStreamK<StreamKTraits<CTA, STAGES, BLOCK_N>> : std::true_type {};
 template <class T>
 int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl,
-               void* sk_ws = nullptr, int stream_k = 0, const mixq_peer_group* pg = nullptr, EpiArgs epi = EpiArgs{nullptr, 0}) {
+               void* sk_ws = nullptr, int stream_k = 0, const mixq_peer_group* pg = nullptr, EpiArgs epi = EpiArgs{nullptr, 0},
+               LaunchOpts opts = LaunchOpts{}) {
     const DeviceInfo& dev = device_info();
     CUtensorMap tm_a8, tm_w8, tm_fa, tm_fw;
     int rc;
@@ -1539,18 +1542,18 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     }
     auto kern = KernelOf<T>::get();
     cudaError_t e = cudaSuccess;
-    static std::atomic<int> attr_set_for_device{-1};   // per template instantiation
-    if (attr_set_for_device.load(std::memory_order_acquire) != dev.device) {
+    static std::atomic<uint64_t> attr_set_mask{0};   // per template instantiation: one bit per device ordinal
+    if (!(attr_set_mask.load(std::memory_order_acquire) >> dev.device & 1)) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::kSmemBytes));
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_dequant)");
-        attr_set_for_device.store(dev.device, std::memory_order_release);
+        attr_set_mask.fetch_or(uint64_t(1) << dev.device, std::memory_order_release);
     }
 
     const int m_tiles = static_cast<int>((M + T::kTileM - 1) / T::kTileM);
     const int n_tiles = static_cast<int>((N + T::kBlockN - 1) / T::kBlockN);
     const int64_t num_tiles = static_cast<int64_t>(m_tiles) * n_tiles;
     if (num_tiles > (1ll << 30)) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: too many tiles");
-    const int64_t max_groups = usable_sms() / T::kCta;
+    const int64_t max_groups = usable_sms(opts) / T::kCta;
     int grid = static_cast<int>(num_tiles < max_groups ? num_tiles : max_groups) * T::kCta;
     if (IsStreamK<T>::value && sk_ws && stream_k) {
         // one equal span of (tile, K-block) units per CTA group; never more groups than units
@@ -1609,11 +1612,11 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
             ar.stage_local = static_cast<const __half*>(pg->staging[pg->rank]);
             ar.out_mc = static_cast<__half*>(pg->out_multicast);
             auto kern_ar = KernelOf<T>::get_ar();
-            static std::atomic<int> ar_attr_set_for_device{-1};
-            if (ar_attr_set_for_device.load(std::memory_order_acquire) != dev.device) {
+            static std::atomic<uint64_t> ar_attr_set_mask{0};
+            if (!(ar_attr_set_mask.load(std::memory_order_acquire) >> dev.device & 1)) {
                 e = cudaFuncSetAttribute(kern_ar, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::kSmemBytes));
                 if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_dequant_allreduce)");
-                ar_attr_set_for_device.store(dev.device, std::memory_order_release);
+                ar_attr_set_mask.fetch_or(uint64_t(1) << dev.device, std::memory_order_release);
             }
             e = cudaLaunchKernelEx(&cfg, kern_ar, tm_a8, tm_w8, tm_fa, tm_fw, tm_a8 /* tm_out unused */,
                                    static_cast<const __half*>(scale_a), static_cast<const __half*>(scale_b),
@@ -1643,7 +1646,102 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     return MIXQ_OK;
 }
 
+// ---- decode kernel (gemm_decode.cuh) ---------------------------------------------------------------------------
+using DecodeT = DecodeTraits<6>;
+constexpr size_t kDecodeSlotRegion = static_cast<size_t>(kStreamKMaxWorkers) * kStreamKSlotBytes;   // shared with config 8
+static_assert(static_cast<size_t>(kDecodeMaxWorkers) * 2 * kDecodeSlotBytesPerCta <= kDecodeSlotRegion, "decode slots fit");
+static_assert(kDecodeFlagBytes == kStreamKFlagBytes && kDecodeMaxWorkers * 2 * 4 <= kDecodeFlagBytes, "decode flags fit");
+
+size_t decode_out0_bytes(int64_t M, int64_t N) {
+    if (M <= 0 || N <= 0) return 0;
+    const int64_t rows = M < kDecodeMaxM ? M : kDecodeMaxM;
+    const int64_t tiles = ((rows + DecodeT::kTileM - 1) / DecodeT::kTileM) * ((N + DecodeT::kBlockN - 1) / DecodeT::kBlockN);
+    return static_cast<size_t>(tiles) * 2 * kDecodeOut0BytesPerCta;
+}
+
+// Split decision of the two-phase schedule: the `r = tiles mod pairs` remainder tiles are cut along K when that
+// leaves every pair a span worth having; r == tiles (fewer tiles than pairs) splits everything.
+struct DecodePlan {
+    int groups, sk_tiles, gran;
+};
+DecodePlan plan_decode(int64_t num_tiles, int64_t num_kb, int64_t max_groups, bool allow_split) {
+    DecodePlan p{static_cast<int>(num_tiles < max_groups ? num_tiles : max_groups), 0, 1};
+    if (!allow_split || max_groups < 2 || max_groups > kDecodeMaxWorkers) return p;
+    const int64_t r = num_tiles % max_groups;
+    if (r == 0) return p;
+    const int64_t span = r * num_kb / max_groups;   // K-blocks per pair in the split region
+    if (span < 8) return p;                          // not worth a fix-up
+    p.groups = static_cast<int>(max_groups);
+    p.sk_tiles = static_cast<int>(r);
+    p.gran = (num_kb % 4 == 0 && span >= 16) ? 4 : 1;
+    return p;
+}
+
+int launch_decode(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
+                  const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl,
+                  void* sk_ws, bool allow_split, EpiArgs epi, LaunchOpts opts) {
+    using T = DecodeT;
+    const DeviceInfo& dev = device_info();
+    CUtensorMap tm_a8, tm_w8, tm_fa, tm_fw;
+    int rc;
+    if ((rc = make_tmap(&tm_a8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, A8, M, K, kBlockM))) return rc;
+    if ((rc = make_tmap(&tm_w8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W8, N, K, T::kLoadN))) return rc;
+    const int has_outlier = (fp_A && fp_weight) ? 1 : 0;
+    if (has_outlier) {
+        if ((rc = make_tmap(&tm_fa, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_A, M, MIXQ_NUM_OUTLIERS, kBlockM))) return rc;
+        if ((rc = make_tmap(&tm_fw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_weight, N, MIXQ_NUM_OUTLIERS, T::kLoadN))) return rc;
+    } else {
+        tm_fa = tm_a8;
+        tm_fw = tm_w8;
+    }
+    auto kern = mixq_gemm_dequant_decode_kernel<T>;
+    cudaError_t e = cudaSuccess;
+    static std::atomic<uint64_t> attr_set_mask{0};
+    if (!(attr_set_mask.load(std::memory_order_acquire) >> dev.device & 1)) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::kSmemBytes));
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_dequant_decode)");
+        attr_set_mask.fetch_or(uint64_t(1) << dev.device, std::memory_order_release);
+    }
+    const int m_tiles = static_cast<int>((M + T::kTileM - 1) / T::kTileM);
+    const int n_tiles = static_cast<int>((N + T::kBlockN - 1) / T::kBlockN);
+    const int64_t num_tiles = static_cast<int64_t>(m_tiles) * n_tiles;
+    const int64_t num_kb = (K + kBlockKBytes - 1) / kBlockKBytes;
+    const DecodePlan plan = plan_decode(num_tiles, num_kb, usable_sms(opts) / 2, allow_split);
+
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(plan.groups * 2);
+    cfg.blockDim = dim3(kStashThreads);
+    cfg.dynamicSmemBytes = T::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    uint8_t* ws = static_cast<uint8_t*>(sk_ws);
+    e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, static_cast<const __half*>(scale_a),
+                           static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M),
+                           static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, m_tiles /* one band */,
+                           plan.sk_tiles, plan.gran, reinterpret_cast<uint32_t*>(ws),
+                           reinterpret_cast<uint4*>(ws + kDecodeFlagBytes),
+                           reinterpret_cast<uint4*>(ws + kDecodeFlagBytes + kDecodeSlotRegion), epi);
+    if (e != cudaSuccess) return set_cuda_error(e, "launch gemm_dequant_decode");
+    count_launch();
+    return MIXQ_OK;
+}
+
 }  // namespace
+
+size_t decode_workspace_bytes(int64_t M, int64_t N) { return streamk_workspace_bytes() + decode_out0_bytes(M, N); }
 
 int set_trace_buffer(void* dev_buf) {
     unsigned long long* p = static_cast<unsigned long long*>(dev_buf);
@@ -1655,8 +1753,11 @@ size_t streamk_workspace_bytes() { return kStreamKFlagBytes + static_cast<size_t
 
 int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                         const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
-                        bool pdl, void* sk_ws, size_t sk_ws_bytes, bool sk_flags_clean, const void* bias, int act) {
+                        bool pdl, void* sk_ws, size_t sk_ws_bytes, bool sk_flags_clean, const void* bias, int act,
+                        LaunchOpts opts) {
     if (M == 0 || N == 0) return MIXQ_OK;
+    if (opts.cfg < 0 || opts.cfg >= kCfgCount) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: unknown config id");
+    if (opts.sm_limit < 0) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: negative sm_limit");
     if (act != MIXQ_ACT_NONE && act != MIXQ_ACT_SILU) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: unknown activation");
     const EpiArgs epi{static_cast<const __half*>(bias), act};
     if (!A8 || !W8 || !scale_a || !scale_b || !Out) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: null pointer");
@@ -1673,13 +1774,14 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
     if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
 
     const bool sk_ok = sk_ws && sk_ws_bytes >= streamk_workspace_bytes() && (reinterpret_cast<uintptr_t>(sk_ws) & 15) == 0;
-    int cfg = current_gemm_config();
+    const bool decode_ok = sk_ws && M <= kDecodeMaxM && sk_ws_bytes >= decode_workspace_bytes(M, N) &&
+                           (reinterpret_cast<uintptr_t>(sk_ws) & 15) == 0;
+    int cfg = opts.cfg;
     if (cfg == kCfgAuto) {
-        // Pick the tile shape with the lowest estimated time = waves x (cycles per K-block) x K-blocks + exposed
+        // Pick the tile shape with the lowest estimated time = K-blocks per worker x (cycles per K-block) + exposed
         // tail.  Cycles per K-block are the measured steady-state figures (profiles/): the 128-wide
         // tiles are shared-memory bound, only the 256-wide pair tile runs near the tensor peak, and wider tiles
         // leave a longer un-overlapped final epilogue.  A single row-block of tokens cannot use a CTA pair.
-        const DeviceInfo& dev = device_info();
         const int64_t nkb = (K + kBlockKBytes - 1) / kBlockKBytes + kOutlierKBlocks;
         struct Cand {
             int id, tile_m, tile_n, cta;
@@ -1692,12 +1794,13 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
         int64_t best = INT64_MAX;
         for (const Cand& c : cands) {
             if (M <= 128 && c.cta == 2) continue;
-            // decode batches (weights streamed from HBM once, one or two tiles per CTA pair): the wide TMA-store tiles lose to
-            // the 128-wide ones, whose 8-stage ring keeps more loads in flight and whose exposed epilogue is shorter
-            // (measured at M = 512 on every Llama-2 / Qwen2 shape but one, where they are 5 % ahead)
-            if (M <= 512 && (c.id == kCfg2CtaN192Tma || c.id == kCfg2CtaN256Tma)) continue;
+            // decode batches (weights streamed from HBM once, one or two tiles per CTA pair): every configuration is bound by
+            // the rate at which TMA lands operand bytes in an SM (~85-100 GB/s per SM, tools/microbench_ingest.cu), the wide
+            // tiles' lower bytes/MAC is eaten by their 1.3-wave schedule, and the split-K decode kernel (ids 11/12) pays more
+            // for its fix-up traffic than it gains (profiles/r2_decode_ab.txt): the 128-wide pair tile stays the choice
+            if (M <= kDecodeMaxM && (c.id == kCfg2CtaN192Tma || c.id == kCfg2CtaN256Tma)) continue;
             const int64_t tiles = ((M + c.tile_m - 1) / c.tile_m) * ((N + c.tile_n - 1) / c.tile_n);
-            const int64_t workers = usable_sms() / c.cta;
+            const int64_t workers = usable_sms(opts) / c.cta;
             const int64_t est = ((tiles + workers - 1) / workers) * c.kb_cycles * nkb + c.tail_cycles;
             if (est < best) {
                 best = est;
@@ -1705,33 +1808,43 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
             }
         }
     }
+    if (cfg == kCfg2CtaN256Decode || cfg == kCfg2CtaN256DecodeNoSplit) {
+        if (!decode_ok)
+            return set_error(MIXQ_ERR_WORKSPACE, "gemm_dequant: the decode kernel needs M <= 1024 and mixq_decode_workspace_size(M, N) bytes of workspace");
+        if (!sk_flags_clean) {
+            cudaError_t e = cudaMemsetAsync(sk_ws, 0, kDecodeFlagBytes, stream);
+            if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(split-K flags)");
+        }
+        return launch_decode(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, sk_ws,
+                             cfg == kCfg2CtaN256Decode, epi, opts);
+    }
     if (cfg == kCfg2CtaN192Tma)  // 256x192 pair tiles: more tiles per wave for decode-sized M
-        return launch_cfg<StreamKTraits<2, 5, 192>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
+        return launch_cfg<StreamKTraits<2, 5, 192>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
     if (cfg == kCfg2CtaN256Tma)  // the stream-K kernel with whole tiles: TMA-store epilogue, no scratch needed
-        return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
+        return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
     if (cfg == kCfg2CtaN256StreamK) {
         if (!sk_ok) return set_error(MIXQ_ERR_WORKSPACE, "gemm_dequant: stream-K needs mixq_gemm_workspace_size() bytes of workspace");
         if (!sk_flags_clean) {
             cudaError_t e = cudaMemsetAsync(sk_ws, 0, kStreamKFlagBytes, stream);
             if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(stream-K flags)");
         }
-        return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, sk_ws, 1, nullptr, epi);
+        return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, sk_ws, 1, nullptr, epi, opts);
     }
     switch (cfg) {
         case kCfgN128x2:
-            return launch_cfg<GemmTraits<1, 128, 2, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
+            return launch_cfg<GemmTraits<1, 128, 2, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         case kCfgN256x1:
-            return launch_cfg<GemmTraits<1, 256, 1, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
+            return launch_cfg<GemmTraits<1, 256, 1, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         case kCfgN64x2:
-            return launch_cfg<GemmTraits<1, 64, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
+            return launch_cfg<GemmTraits<1, 64, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         case kCfg2CtaN256x1:
-            return launch_cfg<GemmTraits<2, 256, 1, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
+            return launch_cfg<GemmTraits<2, 256, 1, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         case kCfg2CtaN128x2:
-            return launch_cfg<GemmTraits<2, 128, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
+            return launch_cfg<GemmTraits<2, 128, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         case kCfg2CtaN256Stash:
-            return launch_cfg<StashTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
+            return launch_cfg<StashTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         case kCfgN256Stash:
-            return launch_cfg<StashTraits<1, 3>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi);
+            return launch_cfg<StashTraits<1, 3>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         default:
             return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: unknown config id");
     }
@@ -1752,7 +1865,7 @@ size_t allreduce_counter_bytes(int64_t M, int64_t N, int world) {
 
 int launch_gemm_dequant_allreduce(const void* A8, const void* W8, const void* scale_a, const void* scale_b,
                                   const void* fp_A, const void* fp_weight, int64_t M, int64_t N, int64_t K,
-                                  const mixq_peer_group* pg, cudaStream_t stream, bool pdl) {
+                                  const mixq_peer_group* pg, cudaStream_t stream, bool pdl, LaunchOpts opts) {
     if (!pg) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_allreduce: null peer group");
     if (pg->world < 1 || pg->world > MIXQ_MAX_RANKS || pg->rank < 0 || pg->rank >= pg->world)
         return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_allreduce: bad world/rank");
@@ -1773,7 +1886,7 @@ int launch_gemm_dequant_allreduce(const void* A8, const void* W8, const void* sc
             return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_allreduce: peer buffers must be 16-byte aligned");
     if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
     return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, pg->out[pg->rank], M, N, K, stream, pdl,
-                                           nullptr, 0, pg);
+                                           nullptr, 0, pg, EpiArgs{nullptr, 0}, opts);
 }
 
 }  // namespace mixq

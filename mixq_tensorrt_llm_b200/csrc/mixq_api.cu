@@ -12,9 +12,7 @@ namespace mixq {
 
 namespace {
 thread_local char g_err[256] = "";
-std::atomic<uint64_t> g_launches{0};
-std::atomic<int> g_gemm_cfg{0};
-std::atomic<int> g_sm_limit{0};
+std::atomic<uint64_t> g_launches{0};   // statistics only (mixq_launch_count); no call reads it back
 
 constexpr size_t kAlign = 128;  // kCudaMemAlign, TsinghuaMixQPlugin.cpp:204
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
@@ -23,13 +21,13 @@ struct Carve {
     size_t off_a8, off_sa, off_fpa, off_sk, total;
 };
 // int8_out | scale_a | fp_activation, in the reference's order (TsinghuaMixQPlugin.cpp:410-421)
-inline Carve carve(int64_t M, int64_t K) {
+inline Carve carve(int64_t M, int64_t N, int64_t K) {
     Carve c;
     c.off_a8 = 0;
     c.off_sa = align_up(static_cast<size_t>(M) * static_cast<size_t>(K));
     c.off_fpa = c.off_sa + align_up(static_cast<size_t>(M) * 2);
     c.off_sk = c.off_fpa + align_up(static_cast<size_t>(M) * MIXQ_NUM_OUTLIERS * 2);
-    c.total = c.off_sk + align_up(streamk_workspace_bytes());  // stream-K flags + partial-sum slots (kernel 2)
+    c.total = c.off_sk + align_up(decode_workspace_bytes(M, N));  // split-K flags + partial-sum slots + decode out0 area
     return c;
 }
 }  // namespace
@@ -43,25 +41,28 @@ int set_cuda_error(cudaError_t e, const char* what) {
     return MIXQ_ERR_CUDA;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-int current_gemm_config() { return g_gemm_cfg.load(std::memory_order_relaxed); }
-int usable_sms() {
-    const int n = device_info().num_sms, lim = g_sm_limit.load(std::memory_order_relaxed);
-    return (lim > 0 && lim < n) ? lim : n;
+int usable_sms(const LaunchOpts& opts) {
+    const int n = device_info().num_sms;
+    return (opts.sm_limit > 0 && opts.sm_limit < n) ? opts.sm_limit : n;
 }
 
 const DeviceInfo& device_info() {
-    static DeviceInfo info;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        int n = 0;
-        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    // one entry per device ordinal, filled on first use with that device current
+    static DeviceInfo infos[kMaxDevices];
+    static std::once_flag once[kMaxDevices];
+    static const DeviceInfo none;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        cudaGetLastError();
+        return none;
+    }
+    std::call_once(once[dev], [dev] {
+        DeviceInfo& info = infos[dev];
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
             cudaGetLastError();
             return;
         }
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return;
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return;
         info.device = dev;
         info.cc_major = p.major;
         info.cc_minor = p.minor;
@@ -70,7 +71,7 @@ const DeviceInfo& device_info() {
         info.smem_per_sm = p.sharedMemPerMultiprocessor;
         info.ok = (p.major == 10);  // the cubin is sm_100a only
     });
-    return info;
+    return infos[dev];
 }
 
 }  // namespace mixq
@@ -84,21 +85,11 @@ const char* mixq_last_error(void) { return g_err; }
 int mixq_device_ok(void) { return device_info().ok ? 1 : 0; }
 uint64_t mixq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int mixq_set_sm_limit(int num_sms) {
-    if (num_sms < 0) return -1;
-    return g_sm_limit.exchange(num_sms);
-}
-
-int mixq_set_gemm_config(int config_id) {
-    if (config_id < 0 || config_id >= kCfgCount) return -1;
-    return g_gemm_cfg.exchange(config_id);
-}
-
 size_t mixq_workspace_size(int64_t M, int64_t N, int64_t K) {
-    (void)N;
     if (M <= 0 || K <= 0) return 0;
-    return carve(M, K).total + kAlign;  // + slack to align the base like nextWorkspacePtr does
+    return carve(M, N < 0 ? 0 : N, K).total + kAlign;  // + slack to align the base like nextWorkspacePtr does
 }
+size_t mixq_decode_workspace_size(int64_t M, int64_t N) { return decode_workspace_bytes(M, N); }
 
 int mixq_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8, void* scale_a,
                        void* fp_A, unsigned flags, void* stream) {
@@ -139,7 +130,15 @@ int mixq_gemm_dequant_ws(const void* A8, const void* W8, const void* scale_a, co
 
 int mixq_enqueue(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes,
                  unsigned flags, void* stream) {
-    return mixq_enqueue_ex(t, M, N, K, workspace, workspace_bytes, nullptr, flags, stream);
+    return mixq_enqueue_opt(t, M, N, K, workspace, workspace_bytes, nullptr, nullptr, flags, stream);
+}
+
+int mixq_gemm_dequant_opt(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
+                          const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, const mixq_epilogue* epi,
+                          const mixq_options* opt, void* workspace, size_t workspace_bytes, void* stream) {
+    return launch_gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, static_cast<cudaStream_t>(stream),
+                               /*pdl=*/false, workspace, workspace_bytes, false, epi ? epi->bias : nullptr,
+                               epi ? epi->activation : 0, make_opts(opt));
 }
 
 int mixq_gemm_dequant_ex(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
@@ -151,6 +150,12 @@ int mixq_gemm_dequant_ex(const void* A8, const void* W8, const void* scale_a, co
 
 int mixq_enqueue_ex(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes,
                     const mixq_epilogue* epi, unsigned flags, void* stream) {
+    return mixq_enqueue_opt(t, M, N, K, workspace, workspace_bytes, epi, nullptr, flags, stream);
+}
+
+int mixq_enqueue_opt(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes,
+                     const mixq_epilogue* epi, const mixq_options* opt, unsigned flags, void* stream) {
+    const LaunchOpts lo = make_opts(opt);
     const void* bias = epi ? epi->bias : nullptr;
     const int act = epi ? epi->activation : 0;
     if (act != MIXQ_ACT_NONE && act != MIXQ_ACT_SILU) return set_error(MIXQ_ERR_BAD_ARG, "enqueue: unknown activation");
@@ -167,7 +172,7 @@ int mixq_enqueue_ex(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void
     if (!t->A || !t->W8 || !t->scale_b || !t->fp_weight || !t->ind || !t->Out)
         return set_error(MIXQ_ERR_BAD_ARG, "enqueue: null tensor (A, W8, scale_b, fp_weight, ind and Out are required)");
     if (!workspace) return set_error(MIXQ_ERR_WORKSPACE, "enqueue: null workspace");
-    const Carve c = carve(M, K);
+    const Carve c = carve(M, N, K);
     // align the base the way nextWorkspacePtr(ptr, 0) does (TsinghuaMixQPlugin.cpp:206-215)
     uintptr_t base = reinterpret_cast<uintptr_t>(workspace);
     const uintptr_t aligned = (base + kAlign - 1) / kAlign * kAlign;
@@ -178,10 +183,11 @@ int mixq_enqueue_ex(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void
     void* fpA = ws + c.off_fpa;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     void* sk = ws + c.off_sk;
-    int rc = launch_quant_extract(t->A, M, K, t->ind, MIXQ_NUM_OUTLIERS, A8, sa, fpA, flags, s, /*pdl=*/true, sk, 1024);
+    int rc = launch_quant_extract(t->A, M, K, t->ind, MIXQ_NUM_OUTLIERS, A8, sa, fpA, flags, s, /*pdl=*/true, sk, 1024, nullptr,
+                                  0.0f, nullptr, lo);
     if (rc) return rc;
     return launch_gemm_dequant(A8, t->W8, sa, t->scale_b, fpA, t->fp_weight, t->Out, M, N, K, s, /*pdl=*/true, sk,
-                               streamk_workspace_bytes(), /*sk_flags_clean=*/true, bias, act);
+                               decode_workspace_bytes(M, N), /*sk_flags_clean=*/true, bias, act, lo);
 }
 
 size_t mixq_allreduce_staging_size(int64_t M, int64_t N, int world) { return allreduce_staging_bytes(M, N, world); }
@@ -189,29 +195,39 @@ size_t mixq_allreduce_counter_size(int64_t M, int64_t N, int world) { return all
 
 int mixq_gemm_dequant_allreduce(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                                 const void* fp_weight, int64_t M, int64_t N, int64_t K, const mixq_peer_group* g, void* stream) {
+    return mixq_gemm_dequant_allreduce_opt(A8, W8, scale_a, scale_b, fp_A, fp_weight, M, N, K, g, nullptr, stream);
+}
+int mixq_gemm_dequant_allreduce_opt(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
+                                    const void* fp_weight, int64_t M, int64_t N, int64_t K, const mixq_peer_group* g,
+                                    const mixq_options* opt, void* stream) {
     return launch_gemm_dequant_allreduce(A8, W8, scale_a, scale_b, fp_A, fp_weight, M, N, K, g,
-                                         static_cast<cudaStream_t>(stream), /*pdl=*/false);
+                                         static_cast<cudaStream_t>(stream), /*pdl=*/false, make_opts(opt));
 }
 
 int mixq_enqueue_allreduce(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes,
                            const mixq_peer_group* g, unsigned flags, void* stream) {
+    return mixq_enqueue_allreduce_opt(t, M, N, K, workspace, workspace_bytes, g, nullptr, flags, stream);
+}
+int mixq_enqueue_allreduce_opt(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace, size_t workspace_bytes,
+                               const mixq_peer_group* g, const mixq_options* opt, unsigned flags, void* stream) {
+    const LaunchOpts lo = make_opts(opt);
     if (!t || !g) return set_error(MIXQ_ERR_BAD_ARG, "enqueue_allreduce: null tensor table / peer group");
     if (M < 0 || N <= 0 || K <= 0) return set_error(MIXQ_ERR_BAD_ARG, "enqueue_allreduce: bad dimensions");
     if (M == 0) return MIXQ_OK;
     if (!t->A || !t->W8 || !t->scale_b || !t->fp_weight || !t->ind)
         return set_error(MIXQ_ERR_BAD_ARG, "enqueue_allreduce: null tensor (A, W8, scale_b, fp_weight and ind are required)");
     if (!workspace) return set_error(MIXQ_ERR_WORKSPACE, "enqueue_allreduce: null workspace");
-    const Carve c = carve(M, K);
+    const Carve c = carve(M, N, K);
     uintptr_t base = reinterpret_cast<uintptr_t>(workspace);
     const uintptr_t aligned = (base + kAlign - 1) / kAlign * kAlign;
     if (workspace_bytes < (aligned - base) + c.total) return set_error(MIXQ_ERR_WORKSPACE, "enqueue_allreduce: workspace too small");
     uint8_t* ws = reinterpret_cast<uint8_t*>(aligned);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int rc = launch_quant_extract(t->A, M, K, t->ind, MIXQ_NUM_OUTLIERS, ws + c.off_a8, ws + c.off_sa, ws + c.off_fpa, flags, s,
-                                  /*pdl=*/true);
+                                  /*pdl=*/true, nullptr, 0, nullptr, 0.0f, nullptr, lo);
     if (rc) return rc;
     return launch_gemm_dequant_allreduce(ws + c.off_a8, t->W8, ws + c.off_sa, t->scale_b, ws + c.off_fpa, t->fp_weight, M, N, K, g,
-                                         s, /*pdl=*/true);
+                                         s, /*pdl=*/true, lo);
 }
 
 size_t mixq_host_scratch_size(int64_t M, int64_t N, int64_t K) {

@@ -17,8 +17,17 @@ struct DeviceInfo {
     size_t smem_per_sm = 0;
 };
 
-// Queried once per process for the current device.
+// Properties of the CURRENT device (cudaGetDevice at the time of the call), cached per device ordinal:
+// a process that drives several GPUs gets each one's own SM count and its own one-time function attributes.
 const DeviceInfo& device_info();
+constexpr int kMaxDevices = 64;
+
+// Per-call tuning (mixq_options in the C ABI).  Nothing here changes a result bit; defaults = automatic.
+struct LaunchOpts {
+    int cfg = 0;        // GemmConfig id, 0 = auto
+    int sm_limit = 0;   // SMs the persistent kernels may occupy, 0 = all
+};
+inline LaunchOpts make_opts(const mixq_options* o) { return o ? LaunchOpts{o->gemm_config, o->sm_limit} : LaunchOpts{}; }
 
 // Error bookkeeping (thread-local text behind mixq_last_error()).
 int set_error(int status, const char* msg);
@@ -29,20 +38,24 @@ void count_launch();
 // clear_words: optional, `n_clear` 32-bit words zeroed by CTA 0 (the stream-K flags of kernel 2)
 int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8, void* scale_a,
                          void* fp_A, unsigned flags, cudaStream_t stream, bool pdl, void* clear_words = nullptr,
-                         int n_clear = 0, const void* gamma = nullptr, float eps = 0.0f, void* y_out = nullptr);
+                         int n_clear = 0, const void* gamma = nullptr, float eps = 0.0f, void* y_out = nullptr,
+                         LaunchOpts opts = LaunchOpts{});
 
 // stage 2 (gemm_i8_tcgen05.cu)
-// sk_ws: optional stream-K scratch (streamk_workspace_bytes(): flags first, then partial-sum slots);
+// sk_ws: optional scratch of the split-K schedules (flags first, then partial-sum slots, then the decode kernel's
+// outlier-product area): streamk_workspace_bytes() serves config 8, decode_workspace_bytes(M, N) also the decode kernel;
 // sk_flags_clean: the flags are already zero (mixq_enqueue lets kernel 1 clear them).
 int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                         const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream,
                         bool pdl, void* sk_ws = nullptr, size_t sk_ws_bytes = 0, bool sk_flags_clean = false,
-                        const void* bias = nullptr, int act = 0);   // fused epilogue: see mixq_epilogue
+                        const void* bias = nullptr, int act = 0,   // fused epilogue: see mixq_epilogue
+                        LaunchOpts opts = LaunchOpts{});
 size_t streamk_workspace_bytes();
+size_t decode_workspace_bytes(int64_t M, int64_t N);
 // stage 2 with the row-parallel all-reduce fused in (peer memory; see ArParams in gemm_i8_tcgen05.cu)
 int launch_gemm_dequant_allreduce(const void* A8, const void* W8, const void* scale_a, const void* scale_b,
                                   const void* fp_A, const void* fp_weight, int64_t M, int64_t N, int64_t K,
-                                  const mixq_peer_group* pg, cudaStream_t stream, bool pdl);
+                                  const mixq_peer_group* pg, cudaStream_t stream, bool pdl, LaunchOpts opts = LaunchOpts{});
 size_t allreduce_staging_bytes(int64_t M, int64_t N, int world);
 size_t allreduce_counter_bytes(int64_t M, int64_t N, int world);
 int set_trace_buffer(void* dev_buf);
@@ -52,9 +65,8 @@ int launch_gemv_w8a16(const void* A, const void* q_weight, const void* scales, v
                       cudaStream_t stream, const void* bias = nullptr, int act = 0);
 
 // GEMM tile configuration ids (mixq_set_gemm_config); 0 = pick automatically.
-enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfg2CtaN256Tma = 9, kCfg2CtaN192Tma = 10, kCfgCount };
-int current_gemm_config();
-// SMs the persistent kernels may occupy (mixq_set_sm_limit; default: all)
-int usable_sms();
+enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfg2CtaN256Tma = 9, kCfg2CtaN192Tma = 10, kCfg2CtaN256Decode = 11, kCfg2CtaN256DecodeNoSplit = 12, kCfgCount };
+// SMs the persistent kernels may occupy on the current device (all, or the caller's per-call limit)
+int usable_sms(const LaunchOpts& opts);
 
 }  // namespace mixq

@@ -244,7 +244,7 @@ const QuantVariant kQuantVariants[] = {MIXQ_QV(1),  MIXQ_QV(2),  MIXQ_QV(3),  MI
 
 int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8, void* scale_a,
                          void* fp_A, unsigned flags, cudaStream_t stream, bool pdl, void* clear_words, int n_clear,
-                         const void* gamma, float eps, void* y_out) {
+                         const void* gamma, float eps, void* y_out, LaunchOpts opts) {
     if (M == 0) return MIXQ_OK;
     if (K <= 0 || (K & 7) != 0) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: K must be a positive multiple of 8");
     if (n_ind < 0 || n_ind > kQuantThreads) return set_error(MIXQ_ERR_BAD_ARG, "quant_extract: n_ind must be in [0,256]");
@@ -274,7 +274,7 @@ int launch_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, i
     // resident CTAs per SM: limited by threads (2048/256 = 8) and by shared memory
     int per_sm = static_cast<int>(dev.smem_per_sm / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
-    int64_t grid = static_cast<int64_t>(usable_sms()) * per_sm;
+    int64_t grid = static_cast<int64_t>(usable_sms(opts)) * per_sm;
     if (grid > M) grid = M;
 
     cudaLaunchConfig_t cfg{};

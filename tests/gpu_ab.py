@@ -22,17 +22,16 @@ sb = (torch.rand(N, device=dev) * 0.002 + 1e-4).half()
 fpA = torch.randn(M, 128, device=dev).half()
 fw = (torch.randn(N, 128, device=dev) * 0.02).half()
 out = torch.empty(M, N, dtype=torch.float16, device=dev)
-ws = torch.zeros(lib.mixq_gemm_workspace_size(), dtype=torch.uint8, device=dev)
+ws = torch.zeros(lib.mixq_decode_workspace_size(min(M, 1024), N), dtype=torch.uint8, device=dev)
 reps = max(3, int(2e-3 / max(2.0 * M * N * K / 2.5e15, 1e-6)))   # ~2 ms of work per sample
 res = {c: [] for c in cfgs}
 for r in range(rounds + 1):
     for c in cfgs:
-        lib.mixq_set_gemm_config(c)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws)
+        B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws, config=c)
         e0.record()
         for _ in range(reps):
-            B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws)
+            B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws, config=c)
         e1.record()
         torch.cuda.synchronize()
         if r > 0:

@@ -1,5 +1,5 @@
 """Fused GEMM + all-reduce protocol test on ONE GPU: `world` virtual ranks = `world` concurrent launches on separate
-streams, each confined to 148/world SMs (mixq_set_sm_limit) so that all of them are co-resident; "peer" pointers are
+streams, each confined to 148/world SMs (mixq_options.sm_limit) so that all of them are co-resident; "peer" pointers are
 plain local pointers.  Checks, bit-exactly, that every rank's Out equals fp16(sum over ranks in order of fp32(partial_r))
 with partial_r from the unfused kernel, over several launches (counter re-arming) and shapes (edges).
 Run as a subprocess by tests/test_gpu_parity.py (a protocol bug traps the context instead of hanging pytest).
@@ -44,9 +44,7 @@ def main():
             fpA = torch.randn(M, 128, device=dev, generator=g).half()
             fw = (torch.randn(N, 128, device=dev, generator=g) * 0.02).half()
             p = torch.empty(M, N, dtype=torch.float16, device=dev)
-            lib.mixq_set_gemm_config(9)
-            B.gemm_dequant(A8, W8, sa, sb, fpA, fw, p)
-            lib.mixq_set_gemm_config(0)
+            B.gemm_dequant(A8, W8, sa, sb, fpA, fw, p, config=9)
             parts.append(p)
             args.append((A8, W8, sa, sb, fpA, fw))
             outs[r].fill_(float("nan"))
@@ -55,14 +53,12 @@ def main():
         for r in range(1, world):
             ref = ref + parts[r].float()
         ref = ref.half()
-        lib.mixq_set_sm_limit(lim)
         for r in range(world):
             grp = B.make_peer_group(world, r, [o.data_ptr() for o in outs], [s.data_ptr() for s in stag],
                                     [c.data_ptr() for c in cnts], st_bytes, ct_bytes)
             with torch.cuda.stream(streams[r]):
-                B.gemm_dequant_allreduce(*args[r], grp, stream=streams[r])
+                B.gemm_dequant_allreduce(*args[r], grp, stream=streams[r], sm_limit=lim)
         torch.cuda.synchronize()
-        lib.mixq_set_sm_limit(0)
         for r in range(world):
             got = outs[r][: M * N].view(M, N)
             same = torch.equal(got.view(torch.int16), ref.view(torch.int16))

@@ -26,7 +26,7 @@ _gws = []
 
 def GWS():
     if not _gws:
-        _gws.append(torch.zeros(B.load().mixq_gemm_workspace_size(), dtype=torch.uint8, device=DEV))
+        _gws.append(torch.zeros(B.load().mixq_decode_workspace_size(1024, 28672), dtype=torch.uint8, device=DEV))
     return _gws[0]
 
 
@@ -49,13 +49,9 @@ def run_gemm(cfg, q, w, sa, sb, fpA=None, fpW=None):
     lib = B.load()
     M, N = q.shape[0], w.shape[0]
     out = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
-    prev = lib.mixq_set_gemm_config(cfg)
-    try:
-        B.gemm_dequant(t(q), t(w), t(sa), t(sb), None if fpA is None else t(fpA), None if fpW is None else t(fpW), out,
-                       workspace=GWS())
-        torch.cuda.synchronize()
-    finally:
-        lib.mixq_set_gemm_config(prev)
+    B.gemm_dequant(t(q), t(w), t(sa), t(sb), None if fpA is None else t(fpA), None if fpW is None else t(fpW), out,
+                   workspace=GWS(), config=cfg)
+    torch.cuda.synchronize()
     return out.cpu().numpy()
 
 
@@ -124,13 +120,11 @@ def timings():
             r["quant_us"] = timeit(lambda: B.quant_extract(A, ind, A8, sa, fpA))
             r["quant_GBps"] = (3 * M * K + 258 * M) / r["quant_us"] / 1e3
             for cfg in CFGS:
-                lib.mixq_set_gemm_config(cfg)
-                us = timeit(lambda: B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=GWS()))
+                us = timeit(lambda: B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=GWS(), config=cfg))
                 r[f"gemm_cfg{cfg}_us"] = us
                 r[f"gemm_cfg{cfg}_TOPS"] = 2.0 * M * N * K / us / 1e6
-                us = timeit(lambda: B.gemm_dequant(A8, W8, sa, sb, None, None, out, workspace=GWS()))
+                us = timeit(lambda: B.gemm_dequant(A8, W8, sa, sb, None, None, out, workspace=GWS(), config=cfg))
                 r[f"gemm_cfg{cfg}_noout_TOPS"] = 2.0 * M * N * K / us / 1e6
-            lib.mixq_set_gemm_config(0)
             r["enqueue_us"] = timeit(lambda: B.enqueue(A, W8, sb, fw, ind, out, ws))
             r["enqueue_TOPS"] = 2.0 * M * N * K / r["enqueue_us"] / 1e6
             if refgpu.available():

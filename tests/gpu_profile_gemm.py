@@ -21,9 +21,8 @@ sb = (torch.rand(N, device=dev) * 0.002 + 1e-4).half()
 fpA = torch.randn(M, 128, device=dev).half()
 fw = (torch.randn(N, 128, device=dev) * 0.02).half()
 out = torch.empty(M, N, dtype=torch.float16, device=dev)
-ws = torch.zeros(lib.mixq_gemm_workspace_size(), dtype=torch.uint8, device=dev)
-lib.mixq_set_gemm_config(cfg)
+ws = torch.zeros(lib.mixq_decode_workspace_size(min(M, 1024), N), dtype=torch.uint8, device=dev)
 for _ in range(iters):
-    B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws)
+    B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws, config=cfg)
 torch.cuda.synchronize()
 print("done", cfg, M, N, K)

@@ -13,7 +13,6 @@ cfg, M, N, K = (int(x) for x in sys.argv[1:5])
 iters = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 dev = "cuda"
 B.require_device()
-B.load().mixq_set_gemm_config(cfg)
 A = (torch.randn(M, K, device=dev) * 0.5).half()
 W8 = torch.randint(-127, 128, (N, K), dtype=torch.int8, device=dev)
 sb = (torch.rand(N, device=dev) * 0.002 + 1e-4).half()
@@ -22,6 +21,6 @@ ind = torch.randperm(K, device=dev)[:128].int()
 out = torch.empty(M, N, dtype=torch.float16, device=dev)
 ws = torch.empty(B.workspace_size(M, N, K), dtype=torch.uint8, device=dev)
 for _ in range(iters):
-    B.enqueue(A, W8, sb, fw, ind, out, ws)
+    B.enqueue(A, W8, sb, fw, ind, out, ws, config=cfg)
 torch.cuda.synchronize()
 print("done", cfg, M, N, K)

@@ -42,7 +42,7 @@ def timeit(fn, iters=10):
 def compute(chunks):
     rows = M // chunks
     for c in range(chunks):
-        B.enqueue(A[c * rows:(c + 1) * rows], W8, sb, fw, ind, out[c * rows:(c + 1) * rows], ws)
+        B.enqueue(A[c * rows:(c + 1) * rows], W8, sb, fw, ind, out[c * rows:(c + 1) * rows], ws, sm_limit=SM_LIMIT)
 
 
 def comm(chunks):
@@ -56,13 +56,14 @@ def both(chunks):
     rows = M // chunks
     works = []
     for c in range(chunks):
-        B.enqueue(A[c * rows:(c + 1) * rows], W8, sb, fw, ind, out[c * rows:(c + 1) * rows], ws)
+        B.enqueue(A[c * rows:(c + 1) * rows], W8, sb, fw, ind, out[c * rows:(c + 1) * rows], ws, sm_limit=SM_LIMIT)
         works.append(dist.all_reduce(out[c * rows:(c + 1) * rows], async_op=True))
     for w in works:
         w.wait()
 
 
 side = torch.cuda.Stream()
+SM_LIMIT = 0
 
 
 def both_side_stream(chunks):
@@ -70,7 +71,7 @@ def both_side_stream(chunks):
     rows = M // chunks
     main = torch.cuda.current_stream()
     for c in range(chunks):
-        B.enqueue(A[c * rows:(c + 1) * rows], W8, sb, fw, ind, out[c * rows:(c + 1) * rows], ws)
+        B.enqueue(A[c * rows:(c + 1) * rows], W8, sb, fw, ind, out[c * rows:(c + 1) * rows], ws, sm_limit=SM_LIMIT)
         ev = torch.cuda.Event(); ev.record(main)
         with torch.cuda.stream(side):
             side.wait_event(ev)
@@ -79,7 +80,7 @@ def both_side_stream(chunks):
 
 
 for lim in (0, 16, 40):
-    lib.mixq_set_sm_limit(nsm - lim if lim else 0)
+    SM_LIMIT = nsm - lim if lim else 0
     r = {"compute1": timeit(lambda: compute(1)), "compute4": timeit(lambda: compute(4)), "comm1": timeit(lambda: comm(1)),
          "comm4": timeit(lambda: comm(4)), "both1": timeit(lambda: both(1)), "both4": timeit(lambda: both(4)),
          "both8": timeit(lambda: both(8)), "side4": timeit(lambda: both_side_stream(4))}

@@ -17,14 +17,13 @@ sb = (torch.rand(N, device=dev) * 0.002 + 1e-4).half()
 fpA = torch.randn(M, 128, device=dev).half()
 fw = (torch.randn(N, 128, device=dev) * 0.02).half()
 out = torch.empty(M, N, dtype=torch.float16, device=dev)
-ws = torch.zeros(lib.mixq_gemm_workspace_size(), dtype=torch.uint8, device=dev)
+ws = torch.zeros(lib.mixq_decode_workspace_size(min(M, 1024), N), dtype=torch.uint8, device=dev)
 trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
-lib.mixq_set_gemm_config(cfg)
 for it in range(4):
-    B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws)
+    B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws, config=cfg)
 torch.cuda.synchronize()
 B.check(lib.mixq_debug_set_trace(trace.data_ptr()), "trace")
-B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws)
+B.gemm_dequant(A8, W8, sa, sb, fpA, fw, out, workspace=ws, config=cfg)
 torch.cuda.synchronize()
 lib.mixq_debug_set_trace(None)
 t = trace.cpu().numpy().reshape(148, 16).astype(np.float64)

@@ -94,9 +94,12 @@ def test_workspace_size(lib):
     M, N, K = 512, 12288, 4096
     need = lib.mixq_workspace_size(M, N, K)
     raw = M * K + 2 * M + 256 * M                                  # A8 | scale_a | fp_A  (:406-421)
-    sk = lib.mixq_gemm_workspace_size()                            # + M-independent stream-K scratch
-    assert 0 < sk < 32 * 2**20
+    sk = lib.mixq_decode_workspace_size(M, N)                      # + split-K scratch: fixed part + fp16 out0 of the decode tiles
+    assert lib.mixq_gemm_workspace_size() < sk <= lib.mixq_gemm_workspace_size() + 2 * 512 * 12288 and sk < 48 * 2**20
     assert raw + sk <= need <= raw + sk + 6 * 128
+    # non-decreasing in M: the size for a profile's maximum covers every smaller batch
+    sizes = [lib.mixq_workspace_size(m, N, K) for m in (1, 32, 512, 1024, 1025, 4096, 65536)]
+    assert sizes == sorted(sizes)
     # far below the reference's max(M*K + 2M + 2KN, 16MN) (:342-346), and no int overflow for big M
     assert need < max(M * K + 2 * M + 2 * K * N, 16 * M * N)
     big = lib.mixq_workspace_size(65536, 12288, 11008)
@@ -124,7 +127,10 @@ def test_argument_validation_without_gpu(lib):
     assert lib.mixq_gemm_dequant(16, 16, 16, 16, None, None, 16, 8, 12, 32, None) == -4  # N % 8
     assert lib.mixq_gemm_dequant(16, 16, 16, 16, 16, None, 16, 8, 8, 32, None) == -1     # fp_A without fp_weight
     assert lib.mixq_quant_extract(16, 4, 20, None, 0, 16, 16, None, 0, None) == -1       # K % 8
-    assert lib.mixq_set_gemm_config(99) == -1
+    from mixq_tensorrt_llm_b200.binding import Options
+    bad = Options(99, 0)
+    assert lib.mixq_gemm_dequant_opt(16, 16, 16, 16, None, None, 16, 8, 8, 32, None, ctypes.byref(bad), None, 0, None) == -1   # unknown config id
+    assert not hasattr(lib, "mixq_set_gemm_config_")  # tuning is per call: no process-wide setters
 
 
 def test_no_cpu_fallback(lib):

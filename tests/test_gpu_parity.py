@@ -41,11 +41,12 @@ def _t(x):
 _GEMM_WS = {}
 
 
-def _gemm_ws(lib):
-    """stream-K scratch for mixq_gemm_dequant_ws, deliberately filled with garbage once: the library
-    must clear / re-arm its flags itself."""
-    if "ws" not in _GEMM_WS:
-        _GEMM_WS["ws"] = torch.randint(0, 255, (lib.mixq_gemm_workspace_size(),), dtype=torch.uint8, device=DEV)
+def _gemm_ws(lib, M=1024, N=12288):
+    """split-K scratch for mixq_gemm_dequant_ws/_opt (decode-kernel size for up to 1024 x 28672), deliberately filled
+    with garbage once: the library must clear / re-arm its flags itself."""
+    need = lib.mixq_decode_workspace_size(min(M, 1024), N)
+    if "ws" not in _GEMM_WS or _GEMM_WS["ws"].numel() < need:
+        _GEMM_WS["ws"] = torch.randint(0, 255, (max(need, lib.mixq_decode_workspace_size(1024, 28672)),), dtype=torch.uint8, device=DEV)
     return _GEMM_WS["ws"]
 
 
@@ -179,7 +180,7 @@ GEMM_SHAPES = [(128, 128, 128), (128, 128, 256), (256, 256, 512), (1, 8, 16), (1
                (512, 256, 28672)]
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     """No outlier slab: int32 accumulation is exact, the epilogue is one fma + one rounding, so
@@ -190,19 +191,15 @@ def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     sa = (rng.random(M) * 0.05 + 1e-3).astype(np.float16)
     sb = (rng.random(N) * 0.002 + 1e-4).astype(np.float16)
     out = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
-    prev = lib.mixq_set_gemm_config(cfg)
-    try:
-        B.gemm_dequant(_t(q), _t(w), _t(sa), _t(sb), None, None, out, workspace=_gemm_ws(lib))
-        torch.cuda.synchronize()
-    finally:
-        lib.mixq_set_gemm_config(prev)
+    B.gemm_dequant(_t(q), _t(w), _t(sa), _t(sb), None, None, out, workspace=_gemm_ws(lib, M, N), config=cfg)
+    torch.cuda.synchronize()
     ref = oracle.epilogue(oracle.igemm(q, w), sa, sb, None)
     got = out.cpu().numpy()
     bad = np.argwhere(got.view(np.uint16) != ref.view(np.uint16))
     assert bad.size == 0, f"{len(bad)} mismatches, first at {bad[:5].tolist()}: got {got[tuple(bad[0])]} want {ref[tuple(bad[0])]}"
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (100, 136, 144), (300, 520, 1040), (64, 512, 4096), (512, 1024, 4096)])
 def test_gemm_dequant_with_outlier_slab(B, lib, oracle, cfg, M, N, K):
     rng = np.random.default_rng(M + N + K)
@@ -213,12 +210,8 @@ def test_gemm_dequant_with_outlier_slab(B, lib, oracle, cfg, M, N, K):
     fpA = (rng.standard_normal((M, 128)) * 4).astype(np.float16)
     fpW = (rng.standard_normal((N, 128)) * 0.05).astype(np.float16)
     out = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
-    prev = lib.mixq_set_gemm_config(cfg)
-    try:
-        B.gemm_dequant(_t(q), _t(w), _t(sa), _t(sb), _t(fpA), _t(fpW), out, workspace=_gemm_ws(lib))
-        torch.cuda.synchronize()
-    finally:
-        lib.mixq_set_gemm_config(prev)
+    B.gemm_dequant(_t(q), _t(w), _t(sa), _t(sb), _t(fpA), _t(fpW), out, workspace=_gemm_ws(lib, M, N), config=cfg)
+    torch.cuda.synchronize()
     out0 = oracle.outlier_gemm(fpA, fpW)
     ref = oracle.epilogue(oracle.igemm(q, w), sa, sb, out0)
     got = out.cpu().numpy()
@@ -235,6 +228,50 @@ def test_gemm_dequant_with_outlier_slab(B, lib, oracle, cfg, M, N, K):
     mag = np.abs(fpA).astype(np.float64) @ np.abs(fpW).astype(np.float64).T
     bound = np.spacing(np.abs(ref2)).astype(np.float64) + mag * 2.0 ** -20
     assert (np.abs(out2.cpu().numpy().astype(np.float64) - ref2.astype(np.float64)) <= bound).all()
+
+
+DECODE_SHAPES = [(512, 4096, 4096), (512, 12288, 4096), (512, 4096, 11008), (1024, 4096, 4096), (700, 11008, 4096),
+                 (512, 2056, 8192), (260, 3584, 3584), (512, 8192, 1024), (1024, 28672, 1024)]
+
+
+@pytest.mark.parametrize("M,N,K", DECODE_SHAPES)
+def test_decode_kernel_split_schedules(B, lib, oracle, M, N, K):
+    """The decode kernel's two-phase schedule (remainder tiles cut along K, int32 partial sums through the workspace,
+    fp16 outlier product through the L2 scratch) on shapes that do split: the integer path is bit-exact vs the oracle,
+    the mixed output is bit-identical to the whole-tile kernel (config 5, itself pinned to the oracle) and to the
+    decode kernel with the split disabled (config 12); the flags re-arm themselves (second launch, garbage-filled scratch
+    only cleared by the library)."""
+    rng = np.random.default_rng(M + 3 * N + 5 * K)
+    q = rng.integers(-127, 128, (M, K), dtype=np.int8)
+    w = rng.integers(-128, 128, (N, K), dtype=np.int8)
+    sa = (rng.random(M) * 0.05 + 1e-3).astype(np.float16)
+    sb = (rng.random(N) * 0.002 + 1e-4).astype(np.float16)
+    fpA = (rng.standard_normal((M, 128)) * 4).astype(np.float16)
+    fpW = (rng.standard_normal((N, 128)) * 0.05).astype(np.float16)
+    tq, tw, tsa, tsb, tfa, tfw = _t(q), _t(w), _t(sa), _t(sb), _t(fpA), _t(fpW)
+    ws = _gemm_ws(lib, M, N)
+    outs = {}
+    for cfg in (11, 11, 12, 5):
+        o = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
+        B.gemm_dequant(tq, tw, tsa, tsb, None, None, o, workspace=ws, config=cfg)
+        torch.cuda.synchronize()
+        outs[cfg] = o
+    ref = oracle.epilogue(oracle.igemm(q, w), sa, sb, None)
+    for cfg, o in outs.items():
+        got = o.cpu().numpy()
+        bad = np.argwhere(got.view(np.uint16) != ref.view(np.uint16))
+        assert bad.size == 0, f"cfg {cfg}: {len(bad)} mismatches vs oracle, first at {bad[:5].tolist()}"
+    mixed = {}
+    for cfg in (11, 11, 12, 5):
+        o = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
+        B.gemm_dequant(tq, tw, tsa, tsb, tfa, tfw, o, workspace=ws, config=cfg)
+        torch.cuda.synchronize()
+        mixed[cfg] = o
+    assert torch.equal(mixed[11].view(torch.int16), mixed[12].view(torch.int16))
+    assert torch.equal(mixed[11].view(torch.int16), mixed[5].view(torch.int16))
+    out0 = oracle.outlier_gemm(fpA, fpW)
+    mag = np.abs(fpA).astype(np.float64) @ np.abs(fpW).astype(np.float64).T
+    _assert_mixed_close(mixed[11].cpu().numpy(), oracle.epilogue(oracle.igemm(q, w), sa, sb, out0), out0, "decode kernel vs oracle", mag)
 
 
 # ----------------------------------------------------------------------------- whole path
@@ -518,7 +555,7 @@ def test_plugin_module_takes_weight_only_branch_with_qweight(B, oracle):
 
 
 # ------------------------------------------------------------------ fused epilogue: bias / SiLU
-@pytest.mark.parametrize("cfg", [0, 1, 5, 6, 9, 10])
+@pytest.mark.parametrize("cfg", [0, 1, 5, 6, 9, 10, 11])
 def test_fused_bias_epilogue_bit_exact(B, lib, oracle, cfg):
     """mixq_gemm_dequant_ex with a bias and no outlier slab: Out == fp16(float(fp16(fma)) + bias[n]) bit for bit
     (int32 exact, one FMA, two roundings) for every kernel family."""
@@ -530,12 +567,9 @@ def test_fused_bias_epilogue_bit_exact(B, lib, oracle, cfg):
     sb = (rng.random(N) * 2e-3 + 1e-4).astype(np.float16)
     bias = rng.standard_normal(N).astype(np.float16)
     out = torch.empty(M, N, dtype=torch.float16, device=DEV)
-    lib.mixq_set_gemm_config(cfg)
-    try:
-        B.gemm_dequant(_t(q), _t(W8), _t(sa), _t(sb), None, None, out, bias=_t(bias))
-        torch.cuda.synchronize()
-    finally:
-        lib.mixq_set_gemm_config(0)
+    B.gemm_dequant(_t(q), _t(W8), _t(sa), _t(sb), None, None, out, bias=_t(bias), config=cfg,
+                   workspace=_gemm_ws(lib, M, N) if cfg in (11, 12) else None)
+    torch.cuda.synchronize()
     want = oracle.epilogue_ex(oracle.igemm(q, W8), sa, sb, None, bias=bias)
     assert np.array_equal(out.cpu().numpy().view(np.uint16), want.view(np.uint16))
 
