@@ -207,6 +207,15 @@ int mixq_linear_host(const mixq_tensors* t, const void* A_host, void* Out_host, 
                      int64_t N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes,
                      unsigned flags, void* stream);
 
+/* The same for several linears that consume the SAME host activations (the fused q/k/v projection, or the gate and up
+ * projections of one MLP: MixQ/src/mixquant/modules/fused/mlp.py:57-70 shares one quantised input between them): A
+ * crosses PCIe once, every linear i (tensors t[i], N[i] output channels, 1 <= count <= 8) writes its own Out_host[i]
+ * [M, N[i]].  The three-stage pipeline (H2D of row slab c+1 | kernels of slab c | D2H of slab c-1) is shared. */
+size_t mixq_linears_host_scratch_size(int64_t M, const int64_t* N, int count, int64_t K);
+int mixq_linears_host(const mixq_tensors* const* t, int count, const void* A_host, void* const* Out_host,
+                      int64_t M, const int64_t* N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes,
+                      unsigned flags, void* stream);
+
 /* Kernel launches issued by this library since load (all threads); bench.py
  * reads it to fill `gpu_launches`. */
 uint64_t mixq_launch_count(void);

@@ -21,7 +21,7 @@ EXPORTS = [
     "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_enqueue", "mixq_enqueue_ex",
     "mixq_gemm_dequant_ex",
     "mixq_quant_extract", "mixq_rmsnorm_quant_extract", "mixq_gemv_w8a16", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
-    "mixq_host_scratch_size", "mixq_linear_host",
+    "mixq_host_scratch_size", "mixq_linear_host", "mixq_linears_host_scratch_size", "mixq_linears_host",
     "mixq_allreduce_staging_size", "mixq_allreduce_counter_size", "mixq_enqueue_allreduce", "mixq_gemm_dequant_allreduce",
     "mixq_enqueue_opt", "mixq_gemm_dequant_opt", "mixq_enqueue_allreduce_opt", "mixq_gemm_dequant_allreduce_opt",
     "mixq_decode_workspace_size",
@@ -107,6 +107,11 @@ def load() -> ctypes.CDLL:
     L.mixq_host_scratch_size.argtypes = [i64, i64, i64]
     L.mixq_linear_host.restype = ci
     L.mixq_linear_host.argtypes = [ctypes.POINTER(Tensors), vp, vp, i64, i64, i64, vp, sz, u32, vp]
+    L.mixq_linears_host_scratch_size.restype = sz
+    L.mixq_linears_host_scratch_size.argtypes = [i64, ctypes.POINTER(i64), ci, i64]
+    L.mixq_linears_host.restype = ci
+    L.mixq_linears_host.argtypes = [ctypes.POINTER(ctypes.POINTER(Tensors)), ci, vp, ctypes.POINTER(vp), i64, ctypes.POINTER(i64), i64,
+                                    vp, sz, u32, vp]
     L.mixq_allreduce_staging_size.restype = sz
     L.mixq_allreduce_staging_size.argtypes = [i64, i64, ci]
     L.mixq_allreduce_counter_size.restype = sz
@@ -259,6 +264,23 @@ def gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, stream=None, wo
                                           _ptr(fp_weight), _ptr(Out), M, N, K, _ptr(workspace),
                                           workspace.numel() * workspace.element_size(), _stream(stream)),
               "mixq_gemm_dequant_ws")
+
+
+def linears_host(tensor_tables, A_host, outs_host, dev_scratch, flags: int = 0, stream=None) -> None:
+    """mixq_linears_host: ``tensor_tables`` are Tensors structs of linears that share the pinned-host activations A_host
+    [M, K]; outs_host[i] is the pinned-host output [M, N_i] of linear i."""
+    M, K = A_host.shape
+    n = len(tensor_tables)
+    tt = (ctypes.POINTER(Tensors) * n)(*[ctypes.pointer(t) for t in tensor_tables])
+    oo = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs_host])
+    nn = (ctypes.c_int64 * n)(*[o.shape[-1] for o in outs_host])
+    check(load().mixq_linears_host(tt, n, ctypes.c_void_p(A_host.data_ptr()), oo, M, nn, K, _ptr(dev_scratch),
+                                   dev_scratch.numel() * dev_scratch.element_size(), flags, _stream(stream)), "mixq_linears_host")
+
+
+def linears_host_scratch_size(M: int, Ns, K: int) -> int:
+    nn = (ctypes.c_int64 * len(Ns))(*Ns)
+    return int(load().mixq_linears_host_scratch_size(M, nn, len(Ns), K))
 
 
 def make_peer_group(world: int, rank: int, out_ptrs, staging_ptrs, counter_ptrs, staging_bytes: int, counter_bytes: int,

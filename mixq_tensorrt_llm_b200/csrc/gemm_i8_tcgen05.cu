@@ -770,6 +770,7 @@ __device__ __forceinline__ void multimem_st_v4(void* mc_ptr, uint32_t a, uint32_
 }
 
 #include "gemm_decode.cuh"
+#include "gemm_fat.cuh"
 
 // ---- fused all-reduce of a row-parallel linear -------------------------------------------------
 // Every rank computes the fp16 partial of every output tile; tile t is OWNED by rank t % world.
@@ -1739,6 +1740,94 @@ int launch_decode(const void* A8, const void* W8, const void* scale_a, const voi
     return MIXQ_OK;
 }
 
+// ---- fat-tile decode kernel (gemm_fat.cuh) ---------------------------------------------------------------------
+// One tile of 256 x Nt per CTA pair and wave: Nt is the widest multiple of 16 (<= 336) that still spreads the N range
+// of a row-block over all the pairs serving it.
+struct FatPlan {
+    int Nt, n_tiles, m_tiles, stages, stage_bytes, waves;
+};
+FatPlan plan_fat(int64_t M, int64_t N, int pairs) {
+    FatPlan p{};
+    p.m_tiles = static_cast<int>((M + 255) / 256);
+    const int per_m = pairs / p.m_tiles > 0 ? pairs / p.m_tiles : 1;
+    const int64_t waves = (N + static_cast<int64_t>(kFatMaxN) * per_m - 1) / (static_cast<int64_t>(kFatMaxN) * per_m);
+    const int64_t want = waves * per_m;                      // tiles per row-block
+    int64_t nt = ((N + want - 1) / want + 15) / 16 * 16;
+    if (nt > kFatMaxN) nt = kFatMaxN;
+    if (nt < 16) nt = 16;
+    p.Nt = static_cast<int>(nt);
+    p.n_tiles = static_cast<int>((N + nt - 1) / nt);
+    p.stage_bytes = kBlockM * kBlockKBytes + (p.Nt / 2) * kBlockKBytes;
+    int st = static_cast<int>((227 * 1024 - 1024 - kFatFixedBytes) / p.stage_bytes);
+    p.stages = st > kFatMaxStages ? kFatMaxStages : st;
+    const int64_t tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+    p.waves = static_cast<int>((tiles + pairs - 1) / pairs);
+    return p;
+}
+
+int launch_fat(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A, const void* fp_weight,
+               void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl, EpiArgs epi, LaunchOpts opts) {
+    const DeviceInfo& dev = device_info();
+    const int pairs = usable_sms(opts) / 2;
+    if (pairs < 1) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: sm_limit leaves no CTA pair");
+    const FatPlan pl = plan_fat(M, N, pairs);
+    if (pl.stages < 3) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: fat tile does not fit shared memory");
+    const int N1 = pl.Nt > 256 ? 256 : pl.Nt, N2 = pl.Nt - N1;
+    CUtensorMap tm_a8, tm_w1, tm_w2, tm_fa, tm_fw1, tm_fw2;
+    int rc;
+    if ((rc = make_tmap(&tm_a8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, A8, M, K, kBlockM))) return rc;
+    if ((rc = make_tmap(&tm_w1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W8, N, K, N1 / 2))) return rc;
+    tm_w2 = tm_w1;
+    if (N2 && (rc = make_tmap(&tm_w2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W8, N, K, N2 / 2))) return rc;
+    const int has_outlier = (fp_A && fp_weight) ? 1 : 0;
+    tm_fa = tm_a8;
+    tm_fw1 = tm_fw2 = tm_w1;
+    if (has_outlier) {
+        if ((rc = make_tmap(&tm_fa, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_A, M, MIXQ_NUM_OUTLIERS, kBlockM))) return rc;
+        if ((rc = make_tmap(&tm_fw1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_weight, N, MIXQ_NUM_OUTLIERS, N1 / 2))) return rc;
+        tm_fw2 = tm_fw1;
+        if (N2 && (rc = make_tmap(&tm_fw2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_weight, N, MIXQ_NUM_OUTLIERS, N2 / 2))) return rc;
+    }
+    CUtensorMap tm_out;
+    if ((rc = make_tmap(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Out, M, N, 32, 64))) return rc;
+    auto kern = mixq_gemm_dequant_fat_kernel;
+    constexpr int kMaxSmem = 227 * 1024;
+    cudaError_t e = cudaSuccess;
+    static std::atomic<uint64_t> attr_set_mask{0};
+    if (!(attr_set_mask.load(std::memory_order_acquire) >> dev.device & 1)) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_dequant_fat)");
+        attr_set_mask.fetch_or(uint64_t(1) << dev.device, std::memory_order_release);
+    }
+    const int64_t tiles = static_cast<int64_t>(pl.m_tiles) * pl.n_tiles;
+    const int groups = static_cast<int>(tiles < pairs ? tiles : pairs);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(groups * 2);
+    cfg.blockDim = dim3(kStashThreads);
+    cfg.dynamicSmemBytes = 1024 + static_cast<size_t>(pl.stages) * pl.stage_bytes + kFatFixedBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w1, tm_w2, tm_fa, tm_fw1, tm_fw2, tm_out, static_cast<const __half*>(scale_a),
+                           static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M), static_cast<int>(N),
+                           static_cast<int>(K), has_outlier, pl.m_tiles, pl.n_tiles, pl.Nt, pl.stages, epi);
+    if (e != cudaSuccess) return set_cuda_error(e, "launch gemm_dequant_fat");
+    count_launch();
+    return MIXQ_OK;
+}
+
 }  // namespace
 
 size_t decode_workspace_bytes(int64_t M, int64_t N) { return streamk_workspace_bytes() + decode_out0_bytes(M, N); }
@@ -1788,16 +1877,16 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
             int64_t kb_cycles, tail_cycles;
         };
         const Cand cands[] = {{kCfgN128x2, 128, 128, 1, 512, 3000},
-                              {kCfg2CtaN128x2, 256, 128, 2, 384, 3000},
+                              {kCfg2CtaN128x2, 256, 128, 2, M <= kDecodeMaxM ? 500 : 384, 3000},
                               {kCfg2CtaN192Tma, 256, 192, 2, 436, 4500},
                               {kCfg2CtaN256Tma, 256, 256, 2, 556, 6000}};
         int64_t best = INT64_MAX;
         for (const Cand& c : cands) {
             if (M <= 128 && c.cta == 2) continue;
-            // decode batches (weights streamed from HBM once, one or two tiles per CTA pair): every configuration is bound by
-            // the rate at which TMA lands operand bytes in an SM (~85-100 GB/s per SM, tools/microbench_ingest.cu), the wide
-            // tiles' lower bytes/MAC is eaten by their 1.3-wave schedule, and the split-K decode kernel (ids 11/12) pays more
-            // for its fix-up traffic than it gains (profiles/r2_decode_ab.txt): the 128-wide pair tile stays the choice
+            // decode batches (weights streamed from HBM once): every configuration is bound by the rate at which TMA lands
+            // operand bytes in an SM (85-100 GB/s per SM = ~48 B/clk at the 1.97 GHz these short kernels run at,
+            // tools/microbench_ingest.cu), so cycles per K-block are bytes per K-block and CTA / 48; the wide TMA-store tiles'
+            // lower bytes/MAC is eaten by their 1.3-wave schedule (profiles/r2_decode_ab.txt)
             if (M <= kDecodeMaxM && (c.id == kCfg2CtaN192Tma || c.id == kCfg2CtaN256Tma)) continue;
             const int64_t tiles = ((M + c.tile_m - 1) / c.tile_m) * ((N + c.tile_n - 1) / c.tile_n);
             const int64_t workers = usable_sms(opts) / c.cta;
@@ -1807,6 +1896,19 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
                 cfg = c.id;
             }
         }
+        if (M > 128 && M <= kDecodeMaxM && usable_sms(opts) >= 2) {
+            // one fat tile per CTA pair and wave (gemm_fat.cuh): longer exposed head (outlier product first) and tail
+            const FatPlan pl = plan_fat(M, N, usable_sms(opts) / 2);
+            const int64_t est = static_cast<int64_t>(pl.waves) * (pl.stage_bytes / 48) * nkb + 7000;
+            if (pl.stages >= 4 && est < best) {
+                best = est;
+                cfg = kCfg2CtaFat;
+            }
+        }
+    }
+    if (cfg == kCfg2CtaFat) {
+        if (M > kDecodeMaxM) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: the fat-tile kernel serves M <= 1024");
+        return launch_fat(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, epi, opts);
     }
     if (cfg == kCfg2CtaN256Decode || cfg == kCfg2CtaN256DecodeNoSplit) {
         if (!decode_ok)

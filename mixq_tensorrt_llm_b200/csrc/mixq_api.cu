@@ -230,11 +230,18 @@ int mixq_enqueue_allreduce_opt(const mixq_tensors* t, int64_t M, int64_t N, int6
                                          s, /*pdl=*/true, lo);
 }
 
-size_t mixq_host_scratch_size(int64_t M, int64_t N, int64_t K) {
-    if (M <= 0 || N <= 0 || K <= 0) return 0;
-    return align_up(static_cast<size_t>(M) * K * 2) + align_up(static_cast<size_t>(M) * N * 2) +
-           mixq_workspace_size(M, N, K) + kAlign;
+size_t mixq_linears_host_scratch_size(int64_t M, const int64_t* N, int count, int64_t K) {
+    if (M <= 0 || K <= 0 || count <= 0 || !N) return 0;
+    size_t total = align_up(static_cast<size_t>(M) * K * 2), ws = 0;
+    for (int i = 0; i < count; ++i) {
+        if (N[i] <= 0) return 0;
+        total += align_up(static_cast<size_t>(M) * N[i] * 2);
+        const size_t w = mixq_workspace_size(M, N[i], K);
+        ws = w > ws ? w : ws;
+    }
+    return total + ws + kAlign;
 }
+size_t mixq_host_scratch_size(int64_t M, int64_t N, int64_t K) { return mixq_linears_host_scratch_size(M, &N, 1, K); }
 
 }  // extern "C" (part 1)
 
@@ -262,20 +269,32 @@ HostPipe& host_pipe() {
 }
 }  // namespace
 
-extern "C" int mixq_linear_host(const mixq_tensors* t, const void* A_host, void* Out_host, int64_t M, int64_t N, int64_t K,
-                                void* dev_scratch, size_t dev_scratch_bytes, unsigned flags, void* stream) {
-    if (!t || !A_host || !Out_host || !dev_scratch) return set_error(MIXQ_ERR_BAD_ARG, "linear_host: null pointer");
-    if (M <= 0 || N <= 0 || K <= 0) return set_error(MIXQ_ERR_BAD_ARG, "linear_host: bad dimensions");
-    if (dev_scratch_bytes < mixq_host_scratch_size(M, N, K)) return set_error(MIXQ_ERR_WORKSPACE, "linear_host: scratch too small");
+extern "C" int mixq_linears_host(const mixq_tensors* const* t, int count, const void* A_host, void* const* Out_host, int64_t M,
+                                 const int64_t* N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes, unsigned flags,
+                                 void* stream) {
+    if (!t || !N || !Out_host || !A_host || !dev_scratch || count <= 0 || count > 8)
+        return set_error(MIXQ_ERR_BAD_ARG, "linears_host: null pointer / count not in [1, 8]");
+    if (M <= 0 || K <= 0) return set_error(MIXQ_ERR_BAD_ARG, "linears_host: bad dimensions");
+    for (int i = 0; i < count; ++i)
+        if (!t[i] || !Out_host[i] || N[i] <= 0) return set_error(MIXQ_ERR_BAD_ARG, "linears_host: null tensor table / output or bad N");
+    if (dev_scratch_bytes < mixq_linears_host_scratch_size(M, N, count, K))
+        return set_error(MIXQ_ERR_WORKSPACE, "linears_host: scratch too small");
     if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
     HostPipe& hp = host_pipe();
-    if (!hp.ok) return set_error(MIXQ_ERR_CUDA, "linear_host: could not create the copy streams");
+    if (!hp.ok) return set_error(MIXQ_ERR_CUDA, "linears_host: could not create the copy streams");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     uintptr_t base = (reinterpret_cast<uintptr_t>(dev_scratch) + kAlign - 1) / kAlign * kAlign;
     uint8_t* dA = reinterpret_cast<uint8_t*>(base);
-    uint8_t* dOut = dA + align_up(static_cast<size_t>(M) * K * 2);
-    uint8_t* ws = dOut + align_up(static_cast<size_t>(M) * N * 2);
-    const size_t ws_bytes = mixq_workspace_size(M, N, K);
+    uint8_t* dOut[8];
+    uint8_t* cur = dA + align_up(static_cast<size_t>(M) * K * 2);
+    size_t ws_bytes = 0;
+    for (int i = 0; i < count; ++i) {
+        dOut[i] = cur;
+        cur += align_up(static_cast<size_t>(M) * N[i] * 2);
+        const size_t w = mixq_workspace_size(M, N[i], K);
+        ws_bytes = w > ws_bytes ? w : ws_bytes;
+    }
+    uint8_t* ws = cur;
 
     // ~32 slabs of >= 1024 rows (a multiple of the 256-row tile), at most 64 of them: the call is PCIe-bound, so short
     // slabs (small fill / drain bubbles of the three-stage pipeline) matter more than GEMM efficiency per slab
@@ -287,9 +306,9 @@ extern "C" int mixq_linear_host(const mixq_tensors* t, const void* A_host, void*
     cudaError_t e = cudaEventRecord(hp.entry, s);  // earlier work on the caller's stream may still use the scratch
     if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.h2d, hp.entry, 0);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.d2h, hp.entry, 0);
-    if (e != cudaSuccess) return set_cuda_error(e, "linear_host: stream setup");
+    if (e != cudaSuccess) return set_cuda_error(e, "linears_host: stream setup");
     const uint8_t* hA = static_cast<const uint8_t*>(A_host);
-    uint8_t* hO = static_cast<uint8_t*>(Out_host);
+    // the activations cross PCIe ONCE, whatever the number of linears that consume them
     for (int c = 0; c < n_slabs; ++c) {
         const int64_t r0 = c * rows, nr = (r0 + rows <= M) ? rows : M - r0;
         e = cudaMemcpyAsync(dA + r0 * K * 2, hA + r0 * K * 2, static_cast<size_t>(nr) * K * 2, cudaMemcpyHostToDevice, hp.h2d);
@@ -299,16 +318,19 @@ extern "C" int mixq_linear_host(const mixq_tensors* t, const void* A_host, void*
     for (int c = 0; c < n_slabs; ++c) {
         const int64_t r0 = c * rows, nr = (r0 + rows <= M) ? rows : M - r0;
         e = cudaStreamWaitEvent(s, hp.up[c], 0);
-        if (e != cudaSuccess) return set_cuda_error(e, "linear_host: wait H2D");
-        mixq_tensors d = *t;
-        d.A = dA + r0 * K * 2;
-        d.Out = dOut + r0 * N * 2;
-        const int rc = mixq_enqueue(&d, nr, N, K, ws, ws_bytes, flags, stream);
-        if (rc) return rc;
+        if (e != cudaSuccess) return set_cuda_error(e, "linears_host: wait H2D");
+        for (int i = 0; i < count; ++i) {
+            mixq_tensors d = *t[i];
+            d.A = dA + r0 * K * 2;
+            d.Out = dOut[i] + r0 * N[i] * 2;
+            const int rc = mixq_enqueue(&d, nr, N[i], K, ws, ws_bytes, flags, stream);
+            if (rc) return rc;
+        }
         e = cudaEventRecord(hp.done[c], s);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.d2h, hp.done[c], 0);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(hO + r0 * N * 2, dOut + r0 * N * 2, static_cast<size_t>(nr) * N * 2, cudaMemcpyDeviceToHost, hp.d2h);
+        for (int i = 0; i < count && e == cudaSuccess; ++i)
+            e = cudaMemcpyAsync(static_cast<uint8_t*>(Out_host[i]) + r0 * N[i] * 2, dOut[i] + r0 * N[i] * 2,
+                                static_cast<size_t>(nr) * N[i] * 2, cudaMemcpyDeviceToHost, hp.d2h);
         if (e != cudaSuccess) return set_cuda_error(e, "D2H output");
     }
     e = cudaEventRecord(hp.drained, hp.d2h);
@@ -318,3 +340,9 @@ extern "C" int mixq_linear_host(const mixq_tensors* t, const void* A_host, void*
     return MIXQ_OK;
 }
 
+extern "C" int mixq_linear_host(const mixq_tensors* t, const void* A_host, void* Out_host, int64_t M, int64_t N, int64_t K,
+                                void* dev_scratch, size_t dev_scratch_bytes, unsigned flags, void* stream) {
+    if (!t || !A_host || !Out_host || !dev_scratch) return set_error(MIXQ_ERR_BAD_ARG, "linear_host: null pointer");
+    if (M <= 0 || N <= 0 || K <= 0) return set_error(MIXQ_ERR_BAD_ARG, "linear_host: bad dimensions");
+    return mixq_linears_host(&t, 1, A_host, &Out_host, M, &N, K, dev_scratch, dev_scratch_bytes, flags, stream);
+}

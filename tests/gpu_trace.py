@@ -14,8 +14,9 @@ A8 = torch.randint(-127, 128, (M, K), dtype=torch.int8, device=dev)
 W8 = torch.randint(-127, 128, (N, K), dtype=torch.int8, device=dev)
 sa = (torch.rand(M, device=dev) * 0.01 + 1e-3).half()
 sb = (torch.rand(N, device=dev) * 0.002 + 1e-4).half()
-fpA = torch.randn(M, 128, device=dev).half()
-fw = (torch.randn(N, 128, device=dev) * 0.02).half()
+import os
+fpA = torch.randn(M, 128, device=dev).half() if not os.environ.get("NO_OUTLIER") else None
+fw = (torch.randn(N, 128, device=dev) * 0.02).half() if not os.environ.get("NO_OUTLIER") else None
 out = torch.empty(M, N, dtype=torch.float16, device=dev)
 ws = torch.zeros(lib.mixq_decode_workspace_size(min(M, 1024), N), dtype=torch.uint8, device=dev)
 trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
@@ -29,7 +30,7 @@ lib.mixq_debug_set_trace(None)
 t = trace.cpu().numpy().reshape(148, 16).astype(np.float64)
 t0 = t[:, 0][t[:, 0] > 0].min()
 names = ["entry", "prologue", "firstTMA", "tile0issued", "mmaDone", "acc0ready", "accLast", "epiDone",
-         "peersIn", "chunksDone", "loopExit", "storesDone"]
+         "peersIn", "chunksDone", "loopExit", "storesDone", "fDrained", "s13", "s14", "s15"]
 rel = np.where(t > 0, (t - t0) / 1e3, np.nan)
 print("shape", M, N, K, "cfg", cfg, "us relative to first CTA entry")
 for i, n in enumerate(names):
@@ -38,4 +39,4 @@ for i, n in enumerate(names):
     if ok.any():
         print(f"{n:12s} min {np.nanmin(col):7.2f} med {np.nanmedian(col):7.2f} max {np.nanmax(col):7.2f}  (n={ok.sum()})")
 for c in (0, 2, 72, 146):
-    print("cta", c, np.round(rel[c][:12], 2).tolist())
+    print("cta", c, np.round(rel[c][:13], 2).tolist())

@@ -16,20 +16,39 @@ def _bench():
 
 
 def test_helpers():
+    import numpy as np
+    import torch
     b = _bench()
-    t = b.traffic_from_profile()
-    assert t is None or (t["bytes"] > 0 and t["algorithmic_bytes"] > 0 and len(t["shape"]) == 3)
     pk = b.peaks()
     assert pk["hbm"] > 1000 and pk["bf16_sustained"] > 100
-    assert b.shard(12288, 4096, "column", 8) == (1536, 4096) and b.shard(4096, 11008, "row", 8) == (4096, 1376)
-    for M, lins in b.WORKLOADS.values():
-        for _, N, K, mode in lins:
+    assert b.DEFAULT_WORKLOAD == "llama2-7b-linears-decode-bs512" and b.WORKLOADS[b.DEFAULT_WORKLOAD]["M"] == 512   # BASELINE.json's metric config
+    for wl in b.WORKLOADS.values():
+        for _, N, K, mode, key in wl["linears"]:
+            s, src = b.act_scales(wl["scales"], key, K)
+            assert s.shape == (K,) and src.startswith("reference")                     # the committed act_scales fixture covers every shape
             for tp in (1, 2, 4, 8):
-                n, k = b.shard(N, K, mode, tp)
-                assert n % 8 == 0 and k % 16 == 0 and k >= 128, (N, K, mode, tp)   # kernel requirements per shard
+                n, k = (N // tp, K) if mode == "column" else (N, K // tp)
+                assert n % 8 == 0 and k % 16 == 0 and k >= 128, (N, K, mode, tp)       # kernel requirements per shard
+    # the device packer / sharder of the bench are the product's host packer and tp.py (CPU tensors here)
+    from mixq_tensorrt_llm_b200 import checkpoint, tp
+    g = torch.Generator().manual_seed(3)
+    W = (torch.randn(96, 512, generator=g) * 0.02).half()
+    sc = torch.rand(512, generator=g)
+    want = checkpoint.pack_linear_weights(W, sc)
+    W8, sb, fw, ind = b.pack_gpu(torch, W.clone(), sc)
+    assert torch.equal(W8, want["W8"]) and torch.equal(sb, want["scale_b"]) and torch.equal(fw, want["fp_weight"]) and torch.equal(ind, want["ind"])
+    packed = {k: v.numpy() for k, v in want.items()}
+    for mode in ("column", "row"):
+        for r in range(4):
+            ref = tp.shard_linear(packed, mode, 4, r)
+            w8, s_, f_, i_, (lo, hi) = b.shard_packed(torch, W8, sb, fw, ind, mode, 4, r)
+            assert np.array_equal(w8.numpy(), ref["W8"]) and np.array_equal(s_.numpy(), ref["scale_b"])
+            assert np.array_equal(f_.numpy(), ref["fp_weight"]) and np.array_equal(i_.numpy(), ref["ind"]) and (lo, hi) == tuple(ref["k_range"])
+    assert b.linear_bytes(512, 12288, 4096) == 2 * 512 * 4096 + 12288 * 4096 + 256 * 12288 + 2 * 12288 + 512 + 2 * 512 * 12288   # 70.3 MB
     s = b.ClockSampler(0)
-    s.lines = [(1.0, "1500, 1965, 900.5, Not Active, Not Active, Not Active, Active\n"), (5.0, "300, 1965, 100, Not Active, Not Active, Not Active, Not Active\n")]
-    s.proc, s.t = type("P", (), {"terminate": lambda self: None})(), type("T", (), {"join": lambda self, timeout=None: None})()
+    s.how, s.sm_max = "nvml", 1965.0
+    s.samples = [(1.0, 1500.0, 900.5, 0x4), (5.0, 300.0, 100.0, 0)]
+    s.t = type("T", (), {"join": lambda self, timeout=None: None})()
     s.t0, s.t1 = 0.5, 2.0
     r = s.stop()
     assert r["sm_mhz"] == 1500.0 and r["reasons"] == ["sw_power_cap"] and r["samples"] == 1
@@ -45,6 +64,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "TFLOP/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["config"]["workload"] == "llama2-7b-linears-decode-bs512" and d["config"]["tokens_per_step"] == 512
+    assert set(d["config"]) == {"workload", "tokens_per_step", "layers_per_step", "linears", "parallelism"}
 
 
 def test_reference_arm_other_ranks_exit_quietly():
