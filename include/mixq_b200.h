@@ -117,6 +117,32 @@ int mixq_gemm_dequant_ex(const void* A8, const void* W8, const void* scale_a, co
                          const void* fp_A, const void* fp_weight, void* Out, int64_t M, int64_t N,
                          int64_t K, const mixq_epilogue* epi, void* stream);
 
+/* ---- gated MLP input half in one call -------------------------------------------------------
+ * The gate and up projections of one MLP consume the same activations; the reference's fused MLP quantises them once
+ * (MixGemmCache), runs the gate projection with SiLU fused into the dequant epilogue and multiplies the two fp16 results
+ * (MixQ/src/mixquant/modules/fused/mlp.py:57-70; modules/linear.py:288-373; epilogue
+ * kernel/symmetric/epilogue/thread/linear_combination_dequant.h:167-272):
+ *   g   = fp16( silu( fma(float(acc_gate), sb_gate*sa, float(out0_gate)) ) )
+ *   u   = fp16(       fma(float(acc_up),   sb_up*sa,   float(out0_up))    )
+ *   Out = fp16( float(g) * float(u) )                                       [M, N], written to gate->Out
+ * `gate` and `up` are the two linears' plugin tensor tables: same A, same `ind` (both see the same activation
+ * statistics; gate->ind is the one read), each its own W8 / scale_b / fp_weight of N output channels; up->Out and the
+ * q_weight fields are ignored (the mixed path serves every M).  For M <= 1024 this is ONE quantise launch and ONE GEMM
+ * launch whose CTA pairs hold a gate tile and the matching up tile side by side in TMEM; the two [M, N] intermediates
+ * never reach memory.  Larger M runs the two GEMMs over the shared quantised A plus one elementwise pass (same roundings)
+ * and needs M*N*2 more bytes of workspace than mixq_workspace_size: mixq_gated_workspace_size includes them. */
+size_t mixq_gated_workspace_size(int64_t M, int64_t N, int64_t K);
+struct mixq_options;
+int mixq_enqueue_gated(const mixq_tensors* gate, const mixq_tensors* up, int64_t M, int64_t N, int64_t K,
+                       void* workspace, size_t workspace_bytes, const struct mixq_options* opt, unsigned flags,
+                       void* stream);
+/* Stage 2 of it alone (A already quantised); scratch: M*N*2 bytes, only read for M > 1024 (may be NULL otherwise). */
+int mixq_gemm_dequant_gated(const void* A8, const void* scale_a, const void* fp_A, const void* W8_gate,
+                            const void* scale_b_gate, const void* fp_weight_gate, const void* W8_up,
+                            const void* scale_b_up, const void* fp_weight_up, void* Out, int64_t M, int64_t N,
+                            int64_t K, const struct mixq_options* opt, void* scratch, size_t scratch_bytes,
+                            void* stream);
+
 /* Stage 1 alone. Replaces int8quant (kernel/i8gemm.cu:66-107,139-150) and
  * ExtractOutliersAndSetToZeros (kernel/i8gemm.cu:198-244) in one pass over A.
  *   sa[m]   = hdiv(max_k |A[m,k]|, 127)

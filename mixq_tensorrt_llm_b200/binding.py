@@ -19,7 +19,7 @@ FLAG_FORCE_MIXED = 2
 # every symbol include/mixq_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_enqueue", "mixq_enqueue_ex",
-    "mixq_gemm_dequant_ex",
+    "mixq_gemm_dequant_ex", "mixq_gated_workspace_size", "mixq_enqueue_gated", "mixq_gemm_dequant_gated",
     "mixq_quant_extract", "mixq_rmsnorm_quant_extract", "mixq_gemv_w8a16", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
     "mixq_host_scratch_size", "mixq_linear_host", "mixq_linears_host_scratch_size", "mixq_linears_host",
     "mixq_allreduce_staging_size", "mixq_allreduce_counter_size", "mixq_enqueue_allreduce", "mixq_gemm_dequant_allreduce",
@@ -91,6 +91,12 @@ def load() -> ctypes.CDLL:
     L.mixq_enqueue_ex.argtypes = [ctypes.POINTER(Tensors), i64, i64, i64, vp, sz, ctypes.POINTER(Epilogue), u32, vp]
     L.mixq_gemm_dequant_ex.restype = ci
     L.mixq_gemm_dequant_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, ctypes.POINTER(Epilogue), vp]
+    L.mixq_gated_workspace_size.restype = sz
+    L.mixq_gated_workspace_size.argtypes = [i64, i64, i64]
+    L.mixq_enqueue_gated.restype = ci
+    L.mixq_enqueue_gated.argtypes = [ctypes.POINTER(Tensors), ctypes.POINTER(Tensors), i64, i64, i64, vp, sz, ctypes.POINTER(Options), u32, vp]
+    L.mixq_gemm_dequant_gated.restype = ci
+    L.mixq_gemm_dequant_gated.argtypes = [vp] * 10 + [i64, i64, i64, ctypes.POINTER(Options), vp, sz, vp]
     L.mixq_quant_extract.restype = ci
     L.mixq_quant_extract.argtypes = [vp, i64, i64, vp, ci, vp, vp, vp, u32, vp]
     L.mixq_rmsnorm_quant_extract.restype = ci
@@ -222,6 +228,32 @@ def enqueue(A, W8, scale_b, fp_weight, ind, Out, workspace, flags: int = 0, stre
         return
     check(load().mixq_enqueue(ctypes.byref(t), M, N, K, _ptr(workspace), workspace.numel() * workspace.element_size(),
                               flags, _stream(stream)), "mixq_enqueue")
+
+
+def gated_workspace_size(M: int, N: int, K: int) -> int:
+    return int(load().mixq_gated_workspace_size(M, N, K))
+
+
+def enqueue_gated(A, gate, up, ind, Out, workspace, flags: int = 0, stream=None, config: int = 0, sm_limit: int = 0) -> None:
+    """mixq_enqueue_gated: Out [M,N] = fp16(silu(gate(A))) * fp16(up(A)); ``gate`` / ``up`` are (W8, scale_b, fp_weight)
+    triples of the two projections, ``ind`` their common outlier index vector."""
+    M, K = A.shape
+    N = Out.shape[-1]
+    tg = make_tensors(A, gate[0], gate[1], gate[2], ind, Out)
+    tu = make_tensors(A, up[0], up[1], up[2], ind, None)
+    check(load().mixq_enqueue_gated(ctypes.byref(tg), ctypes.byref(tu), M, N, K, _ptr(workspace),
+                                    workspace.numel() * workspace.element_size(), _opts(config, sm_limit), flags, _stream(stream)),
+          "mixq_enqueue_gated")
+
+
+def gemm_dequant_gated(A8, scale_a, fp_A, gate, up, Out, stream=None, scratch=None, config: int = 0, sm_limit: int = 0) -> None:
+    """mixq_gemm_dequant_gated (stage 2 of the gated call); ``gate`` / ``up`` = (W8, scale_b, fp_weight or None)."""
+    M, K = A8.shape
+    N = Out.shape[-1]
+    check(load().mixq_gemm_dequant_gated(_ptr(A8), _ptr(scale_a), _ptr(fp_A), _ptr(gate[0]), _ptr(gate[1]), _ptr(gate[2]),
+                                         _ptr(up[0]), _ptr(up[1]), _ptr(up[2]), _ptr(Out), M, N, K, _opts(config, sm_limit),
+                                         _ptr(scratch), scratch.numel() * scratch.element_size() if scratch is not None else 0,
+                                         _stream(stream)), "mixq_gemm_dequant_gated")
 
 
 def quant_extract(A, ind, A8, scale_a, fp_A, flags: int = 0, stream=None) -> None:

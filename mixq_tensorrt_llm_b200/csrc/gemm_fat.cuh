@@ -19,6 +19,16 @@
 // 32 x 32 SWIZZLE_64B tiles (32 KB in all, double-buffered) and leaves through TMA stores.
 // Arithmetic and rounding points are those of the other stage-2 kernels (reference
 // kernel/symmetric/gemm/kernel/gemm_dequant.h:224-292, epilogue/thread/linear_combination_dequant.h:152-157).
+//
+// Gated mode (`gated` != 0): the gate and up projections of one MLP in ONE launch.  The two tcgen05.mma
+// of a K step then read the gate rows and the up rows of the SAME Ng = Nt/2 output channels (two tensor maps over the two
+// weight tensors as the checkpoint holds them: no interleaved repacking), the accumulators sit side by side in TMEM
+// (gate [0, Ng), up [Ng, 2 Ng), parked outlier products behind them) and the epilogue writes
+//     Out[m, n] = fp16( fp16(silu(gate[m, n])) * fp16(up[m, n]) )            [M, N], N = channels of ONE projection
+// i.e. MixLlamaMLP.forward's  gate_proj.forward_without_preconditionFusedSilu(x) *= up_proj(x)
+// (MixQ/src/mixquant/modules/fused/mlp.py:57-70, modules/linear.py:288-373): SiLU in fp32 before the rounding of the gate
+// (epilogue/thread/linear_combination_dequant.h:167-272), the up projection rounded to fp16, an fp16 multiply.  One
+// quantised A serves both (the reference's MixGemmCache), the [M, N] intermediate of each projection never exists.
 
 constexpr int kFatMaxN = 336;          // Nt + Nt / 2 <= 512 TMEM columns, Nt % 16 == 0
 constexpr int kFatMaxStages = 8;
@@ -34,12 +44,13 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                              const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_fa,
                              const __grid_constant__ CUtensorMap tm_fw1, const __grid_constant__ CUtensorMap tm_fw2,
                              const __grid_constant__ CUtensorMap tm_out, const __half* __restrict__ scale_a, const __half* __restrict__ scale_b,
-                             __half* __restrict__ Out, int M, int N, int K, int has_outlier, int m_tiles, int n_tiles,
-                             int Nt, int stages, EpiArgs epi) {
+                             const __half* __restrict__ scale_b2, __half* __restrict__ Out, int M, int N, int K, int has_outlier,
+                             int m_tiles, int n_tiles, int Nt, int stages, int gated, EpiArgs epi) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int N1 = Nt > 256 ? 256 : Nt;            // columns of the first / second tcgen05.mma of a K step
+    const int N1 = gated ? Nt / 2 : (Nt > 256 ? 256 : Nt);   // columns of the first / second tcgen05.mma of a K step
     const int N2 = Nt - N1;
+    const int tile_cols = gated ? N1 : Nt;         // output columns per tile
     const int w1_bytes = (N1 / 2) * kBlockKBytes;  // W rows each CTA stages for MMA 1 (half of them: cta_group::2)
     const int stage_bytes = kBlockM * kBlockKBytes + (Nt / 2) * kBlockKBytes;
     uint8_t* ring = smem;
@@ -122,8 +133,8 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
             for (int tile = group_id; tile < num_tiles; tile += num_groups) {
                 const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;   // the row-blocks that share a W tile run side by side
                 const int m0 = m_blk * 256 + static_cast<int>(cta_rank) * kBlockM;
-                const int n1 = n_blk * Nt + static_cast<int>(cta_rank) * (N1 / 2);
-                const int n2 = n_blk * Nt + N1 + static_cast<int>(cta_rank) * (N2 / 2);
+                const int n1 = n_blk * tile_cols + static_cast<int>(cta_rank) * (N1 / 2);
+                const int n2 = n_blk * tile_cols + (gated ? 0 : N1) + static_cast<int>(cta_rank) * (N2 / 2);   // gated: the same channels of the up projection
                 for (int it = 0; it < n_f; ++it) load_block(&tm_fa, &tm_fw1, &tm_fw2, it * (kBlockKBytes / 2), m0, n1, n2);
                 for (int kb = 0; kb < num_kb; ++kb) load_block(&tm_a8, &tm_w1, &tm_w2, kb * kBlockKBytes, m0, n1, n2);
             }
@@ -139,7 +150,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
             const uint64_t desc_b0 = ptx::make_smem_desc_sw128(ptx::smem_u32(ring) + kBlockM * kBlockKBytes);
             const uint64_t desc_c0 = ptx::make_smem_desc_sw128(ptx::smem_u32(ring) + kBlockM * kBlockKBytes + w1_bytes);
             const uint32_t stage_step = static_cast<uint32_t>(stage_bytes) >> 4;
-            const uint32_t tmem_2 = tmem_base + 256;
+            const uint32_t tmem_2 = tmem_base + static_cast<uint32_t>(N1);
             int stage = 0;
             uint32_t phase = 0;
             bool ready = false;
@@ -209,7 +220,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
         for (int tile = group_id; tile < num_tiles; tile += num_groups, ++lt) {
             const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
             const int m0 = m_blk * 256 + static_cast<int>(cta_rank) * kBlockM;
-            const int n0 = n_blk * Nt;
+            const int n0 = n_blk * tile_cols;
             const int gm = m0 + row;
             const bool row_ok = gm < M;
             const float sa_f = row_ok ? __half2float(scale_a[gm]) : 0.0f;
@@ -247,8 +258,13 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
             // the staging vectors are single-buffered: past this barrier every thread is done with the previous tile
             ptx::named_bar_sync(1, kStashEpiThreads);
             for (int j = et; j < Nt; j += kStashEpiThreads) {
-                sb_s[j] = (n0 + j < N) ? __half2float(scale_b[n0 + j]) : 0.0f;
-                if (epi.bias) bias_sm[j] = (n0 + j < N) ? __half2float(epi.bias[n0 + j]) : 0.0f;
+                if (gated) {   // [0, Ng): gate scales, [Ng, 2 Ng): up scales of the same channels
+                    const int jj = j < N1 ? j : j - N1;
+                    sb_s[j] = (n0 + jj < N) ? __half2float((j < N1 ? scale_b : scale_b2)[n0 + jj]) : 0.0f;
+                } else {
+                    sb_s[j] = (n0 + j < N) ? __half2float(scale_b[n0 + j]) : 0.0f;
+                    if (epi.bias) bias_sm[j] = (n0 + j < N) ? __half2float(epi.bias[n0 + j]) : 0.0f;
+                }
             }
             ptx::named_bar_sync(1, kStashEpiThreads);
 
@@ -321,6 +337,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                 ptx::tmem_ld_32x16(t_acc + c * 16, vi);
                 if (has_outlier) ptx::tmem_ld_32x8(t_out0 + c * 8, vo);
             };
+            if (!gated) {
             if (c_begin < c_end) load(ia, oa, c_begin);
             for (int c = c_begin; c < c_end; c += 2) {
                 uint32_t pa[8], pb[8];
@@ -347,6 +364,75 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                     }
                 } else {
                     store_direct(pa, c);
+                }
+            }
+            } else {
+                // ---- gated: out = fp16(silu(gate)) * fp16(up) over the tile's Ng channels; gate accumulators in columns [0, Ng), up
+                // in [Ng, 2 Ng), their parked outlier products in [Nt, Nt + Ng/2) and [Nt + Ng/2, Nt + Ng)
+                const int g_chunks = N1 >> 4;
+                const int g_split = min(g_chunks, ((g_chunks + 1) / 2 + 1) & ~1);
+                const int g_begin = half == 0 ? 0 : g_split, g_end = half == 0 ? g_split : g_chunks;
+                const uint32_t t_up = t_acc + static_cast<uint32_t>(N1), t_out0_up = t_out0 + static_cast<uint32_t>(N1 >> 1);
+                uint32_t iu[16], ou[8];
+                if (!has_outlier) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) ou[q] = 0u;
+                }
+                auto gload = [&](int c) {
+                    ptx::tmem_ld_32x16(t_acc + c * 16, ia);
+                    ptx::tmem_ld_32x16(t_up + c * 16, iu);
+                    if (has_outlier) {
+                        ptx::tmem_ld_32x8(t_out0 + c * 8, oa);
+                        ptx::tmem_ld_32x8(t_out0_up + c * 8, ou);
+                    }
+                };
+                auto gfinish = [&](int c, uint32_t (&packed)[8]) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 sg = ptx::ld_shared_f4(sb_addr + (c * 16 + g * 4) * 4);
+                        const float4 su = ptx::ld_shared_f4(sb_addr + (N1 + c * 16 + g * 4) * 4);
+                        const float sgv[4] = {sg.x, sg.y, sg.z, sg.w}, suv[4] = {su.x, su.y, su.z, su.w};
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const int q = g * 2 + h2;
+                            const float2 og = __half22float2(*reinterpret_cast<const __half2*>(&oa[q]));
+                            const float2 ouf = __half22float2(*reinterpret_cast<const __half2*>(&ou[q]));
+                            float g0 = __fmaf_rn(__int2float_rn(static_cast<int>(ia[2 * q])), __fmul_rn(sgv[2 * h2], sa_f), og.x);
+                            float g1 = __fmaf_rn(__int2float_rn(static_cast<int>(ia[2 * q + 1])), __fmul_rn(sgv[2 * h2 + 1], sa_f), og.y);
+                            const float u0 = __fmaf_rn(__int2float_rn(static_cast<int>(iu[2 * q])), __fmul_rn(suv[2 * h2], sa_f), ouf.x);
+                            const float u1 = __fmaf_rn(__int2float_rn(static_cast<int>(iu[2 * q + 1])), __fmul_rn(suv[2 * h2 + 1], sa_f), ouf.y);
+                            g0 = __fdividef(g0, 1.0f + __expf(-g0));     // SiLU in fp32 before the gate's rounding (epi_finish)
+                            g1 = __fdividef(g1, 1.0f + __expf(-g1));
+                            const __half2 o = __hmul2(__floats2half2_rn(g0, g1), __floats2half2_rn(u0, u1));
+                            packed[q] = *reinterpret_cast<const uint32_t*>(&o);
+                        }
+                    }
+                };
+                for (int c = g_begin; c < g_end; c += 2) {
+                    uint32_t pa[8], pb[8];
+                    const bool pair = c + 1 < g_end;
+                    const int pi = ((c - g_begin) >> 1) & 1;
+                    const uint32_t t = tiles_addr + pi * 2048;
+                    gload(c);
+                    ptx::tmem_ld_wait();
+                    gfinish(c, pa);
+                    if (pair) {
+                        gload(c + 1);
+                        if (lane == 0) ptx::tma_store_wait_read<1>();
+                        __syncwarp();
+                        store_staged(pa, t, 0u);
+                        ptx::tmem_ld_wait();
+                        gfinish(c + 1, pb);
+                        store_staged(pb, t, 2u);
+                        ptx::fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&tm_out, my_tiles + pi * 2048, n0 + c * 16, m0 + quarter * 32);
+                            ptx::tma_store_commit();
+                        }
+                    } else {
+                        store_direct(pa, c);
+                    }
                 }
             }
             if (et == 0) trace_stamp(9);

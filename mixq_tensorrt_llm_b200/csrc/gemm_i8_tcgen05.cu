@@ -26,6 +26,7 @@
 //            tile i overlaps the main loop of tile i+1.
 // Barriers: full[kStages] (TMA -> MMA, tx bytes), empty[kStages] (MMA -> TMA, tcgen05.commit),
 //           tmem_full[kAccStages] (MMA -> epilogue), tmem_empty[kAccStages] (epilogue -> MMA).
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -1746,15 +1747,19 @@ int launch_decode(const void* A8, const void* W8, const void* scale_a, const voi
 struct FatPlan {
     int Nt, n_tiles, m_tiles, stages, stage_bytes, waves;
 };
-FatPlan plan_fat(int64_t M, int64_t N, int pairs) {
+FatPlan plan_fat(int64_t M, int64_t N, int pairs, bool gated = false) {
+    // N: accumulator columns of the whole problem (gated: gate + up = 2 x the output channels; a tile then holds Nt / 2
+    // channels of each, so Nt is a multiple of 32)
     FatPlan p{};
+    const int gran = gated ? 32 : 16;
+    const int max_nt = kFatMaxN / gran * gran;
     p.m_tiles = static_cast<int>((M + 255) / 256);
     const int per_m = pairs / p.m_tiles > 0 ? pairs / p.m_tiles : 1;
-    const int64_t waves = (N + static_cast<int64_t>(kFatMaxN) * per_m - 1) / (static_cast<int64_t>(kFatMaxN) * per_m);
+    const int64_t waves = (N + static_cast<int64_t>(max_nt) * per_m - 1) / (static_cast<int64_t>(max_nt) * per_m);
     const int64_t want = waves * per_m;                      // tiles per row-block
-    int64_t nt = ((N + want - 1) / want + 15) / 16 * 16;
-    if (nt > kFatMaxN) nt = kFatMaxN;
-    if (nt < 16) nt = 16;
+    int64_t nt = ((N + want - 1) / want + gran - 1) / gran * gran;
+    if (nt > max_nt) nt = max_nt;
+    if (nt < gran) nt = gran;
     p.Nt = static_cast<int>(nt);
     p.n_tiles = static_cast<int>((N + nt - 1) / nt);
     p.stage_bytes = kBlockM * kBlockKBytes + (p.Nt / 2) * kBlockKBytes;
@@ -1765,20 +1770,30 @@ FatPlan plan_fat(int64_t M, int64_t N, int pairs) {
     return p;
 }
 
+// the second projection of the gated mode (gemm_fat.cuh): up-projection weights of the same shape as the gate's
+struct FatGated {
+    const void* W8_up;
+    const void* scale_b_up;
+    const void* fp_weight_up;
+};
+
 int launch_fat(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A, const void* fp_weight,
-               void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl, EpiArgs epi, LaunchOpts opts) {
+               void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl, EpiArgs epi, LaunchOpts opts,
+               const FatGated* gated = nullptr) {
     const DeviceInfo& dev = device_info();
     const int pairs = usable_sms(opts) / 2;
     if (pairs < 1) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: sm_limit leaves no CTA pair");
-    const FatPlan pl = plan_fat(M, N, pairs);
+    const FatPlan pl = plan_fat(M, gated ? 2 * N : N, pairs, gated != nullptr);
     if (pl.stages < 3) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: fat tile does not fit shared memory");
-    const int N1 = pl.Nt > 256 ? 256 : pl.Nt, N2 = pl.Nt - N1;
+    const int N1 = gated ? pl.Nt / 2 : (pl.Nt > 256 ? 256 : pl.Nt), N2 = pl.Nt - N1;
+    const void* W2 = gated ? gated->W8_up : W8;
+    const void* fw2 = gated ? gated->fp_weight_up : fp_weight;
     CUtensorMap tm_a8, tm_w1, tm_w2, tm_fa, tm_fw1, tm_fw2;
     int rc;
     if ((rc = make_tmap(&tm_a8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, A8, M, K, kBlockM))) return rc;
     if ((rc = make_tmap(&tm_w1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W8, N, K, N1 / 2))) return rc;
     tm_w2 = tm_w1;
-    if (N2 && (rc = make_tmap(&tm_w2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W8, N, K, N2 / 2))) return rc;
+    if (N2 && (rc = make_tmap(&tm_w2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W2, N, K, N2 / 2))) return rc;
     const int has_outlier = (fp_A && fp_weight) ? 1 : 0;
     tm_fa = tm_a8;
     tm_fw1 = tm_fw2 = tm_w1;
@@ -1786,7 +1801,7 @@ int launch_fat(const void* A8, const void* W8, const void* scale_a, const void* 
         if ((rc = make_tmap(&tm_fa, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_A, M, MIXQ_NUM_OUTLIERS, kBlockM))) return rc;
         if ((rc = make_tmap(&tm_fw1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_weight, N, MIXQ_NUM_OUTLIERS, N1 / 2))) return rc;
         tm_fw2 = tm_fw1;
-        if (N2 && (rc = make_tmap(&tm_fw2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_weight, N, MIXQ_NUM_OUTLIERS, N2 / 2))) return rc;
+        if (N2 && (rc = make_tmap(&tm_fw2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fw2, N, MIXQ_NUM_OUTLIERS, N2 / 2))) return rc;
     }
     CUtensorMap tm_out;
     if ((rc = make_tmap(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Out, M, N, 32, 64))) return rc;
@@ -1821,11 +1836,19 @@ int launch_fat(const void* A8, const void* W8, const void* scale_a, const void* 
     cfg.attrs = attr;
     cfg.numAttrs = na;
     e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w1, tm_w2, tm_fa, tm_fw1, tm_fw2, tm_out, static_cast<const __half*>(scale_a),
-                           static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M), static_cast<int>(N),
-                           static_cast<int>(K), has_outlier, pl.m_tiles, pl.n_tiles, pl.Nt, pl.stages, epi);
+                           static_cast<const __half*>(scale_b), static_cast<const __half*>(gated ? gated->scale_b_up : scale_b),
+                           static_cast<__half*>(Out), static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), has_outlier,
+                           pl.m_tiles, pl.n_tiles, pl.Nt, pl.stages, gated ? 1 : 0, epi);
     if (e != cudaSuccess) return set_cuda_error(e, "launch gemm_dequant_fat");
     count_launch();
     return MIXQ_OK;
+}
+
+// out[i] *= other[i] (fp16): the last step of the gated linear where the two projections ran as separate GEMMs (M > 1024)
+__global__ void mixq_mul_inplace_kernel(__half2* __restrict__ out, const __half2* __restrict__ other, size_t n2) {
+    ptx::pdl_wait_prior_grid();
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n2; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = __hmul2(out[i], other[i]);
 }
 
 }  // namespace
@@ -1952,6 +1975,49 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
     }
 }
 
+
+int launch_gemm_dequant_gated(const void* A8, const void* scale_a, const void* fp_A, const void* W8_gate, const void* sb_gate,
+                              const void* fpw_gate, const void* W8_up, const void* sb_up, const void* fpw_up, void* Out, int64_t M,
+                              int64_t N, int64_t K, cudaStream_t stream, bool pdl, void* scratch, size_t scratch_bytes,
+                              LaunchOpts opts) {
+    if (M == 0 || N == 0) return MIXQ_OK;
+    if (opts.sm_limit < 0) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_gated: negative sm_limit");
+    if (!A8 || !scale_a || !W8_gate || !sb_gate || !W8_up || !sb_up || !Out) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_gated: null pointer");
+    if ((fp_A == nullptr) != (fpw_gate == nullptr) || (fp_A == nullptr) != (fpw_up == nullptr))
+        return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_gated: fp_A and both fp_weight tensors must all be given or all be null");
+    if (M < 0 || N < 0 || K <= 0 || M > INT32_MAX || N > INT32_MAX || K > INT32_MAX)
+        return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_gated: bad dimensions");
+    if ((K & 15) != 0 || (N & 7) != 0) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant_gated: K must be a multiple of 16 and N of 8");
+    const uintptr_t al = reinterpret_cast<uintptr_t>(A8) | reinterpret_cast<uintptr_t>(W8_gate) | reinterpret_cast<uintptr_t>(W8_up) |
+                         reinterpret_cast<uintptr_t>(Out) | reinterpret_cast<uintptr_t>(fp_A) | reinterpret_cast<uintptr_t>(fpw_gate) |
+                         reinterpret_cast<uintptr_t>(fpw_up);
+    if (al & 15) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_gated: tensors must be 16-byte aligned");
+    if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
+    if (M <= kDecodeMaxM && usable_sms(opts) >= 2 && opts.cfg != kCfgGatedUnfused) {
+        const FatGated g{W8_up, sb_up, fpw_up};
+        return launch_fat(A8, W8_gate, scale_a, sb_gate, fp_A, fpw_gate, Out, M, N, K, stream, pdl, EpiArgs{nullptr, 0}, opts, &g);
+    }
+    // prefill-sized batches are tensor-bound and their tiles fill the machine: two GEMMs over the shared quantised A
+    // (the gate's with the fused SiLU) and one elementwise pass, the same roundings in the same order
+    const size_t need = static_cast<size_t>(M) * N * 2;
+    if (!scratch || scratch_bytes < need || (reinterpret_cast<uintptr_t>(scratch) & 15))
+        return set_error(MIXQ_ERR_WORKSPACE, "gemm_dequant_gated: M > 1024 needs M*N*2 bytes of 16-byte aligned scratch");
+    LaunchOpts o2 = opts;
+    o2.cfg = kCfgAuto;
+    int rc = launch_gemm_dequant(A8, W8_gate, scale_a, sb_gate, fp_A, fpw_gate, Out, M, N, K, stream, pdl, nullptr, 0, false, nullptr,
+                                 MIXQ_ACT_SILU, o2);
+    if (rc) return rc;
+    rc = launch_gemm_dequant(A8, W8_up, scale_a, sb_up, fp_A, fpw_up, scratch, M, N, K, stream, /*pdl=*/false, nullptr, 0, false, nullptr,
+                             MIXQ_ACT_NONE, o2);
+    if (rc) return rc;
+    const size_t n2 = static_cast<size_t>(M) * N / 2;
+    const int blocks = static_cast<int>(std::min<size_t>((n2 + 255) / 256, static_cast<size_t>(usable_sms(opts)) * 8));
+    mixq_mul_inplace_kernel<<<blocks, 256, 0, stream>>>(static_cast<__half2*>(Out), static_cast<const __half2*>(scratch), n2);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "launch mul_inplace");
+    count_launch();
+    return MIXQ_OK;
+}
 
 size_t allreduce_staging_bytes(int64_t M, int64_t N, int world) {
     if (M <= 0 || N <= 0 || world <= 0) return 0;

@@ -190,6 +190,45 @@ int mixq_enqueue_opt(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, voi
                                decode_workspace_bytes(M, N), /*sk_flags_clean=*/true, bias, act, lo);
 }
 
+size_t mixq_gated_workspace_size(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || K <= 0 || N <= 0) return 0;
+    return mixq_workspace_size(M, N, K) + align_up(static_cast<size_t>(M) * N * 2);
+}
+
+int mixq_gemm_dequant_gated(const void* A8, const void* scale_a, const void* fp_A, const void* W8_gate, const void* scale_b_gate,
+                            const void* fp_weight_gate, const void* W8_up, const void* scale_b_up, const void* fp_weight_up, void* Out,
+                            int64_t M, int64_t N, int64_t K, const mixq_options* opt, void* scratch, size_t scratch_bytes, void* stream) {
+    return launch_gemm_dequant_gated(A8, scale_a, fp_A, W8_gate, scale_b_gate, fp_weight_gate, W8_up, scale_b_up, fp_weight_up, Out, M,
+                                     N, K, static_cast<cudaStream_t>(stream), /*pdl=*/false, scratch, scratch_bytes, make_opts(opt));
+}
+
+int mixq_enqueue_gated(const mixq_tensors* gate, const mixq_tensors* up, int64_t M, int64_t N, int64_t K, void* workspace,
+                       size_t workspace_bytes, const mixq_options* opt, unsigned flags, void* stream) {
+    const LaunchOpts lo = make_opts(opt);
+    if (!gate || !up) return set_error(MIXQ_ERR_BAD_ARG, "enqueue_gated: null tensor table");
+    if (M < 0 || N <= 0 || K <= 0) return set_error(MIXQ_ERR_BAD_ARG, "enqueue_gated: bad dimensions");
+    if (M == 0) return MIXQ_OK;
+    if (!gate->A || !gate->W8 || !gate->scale_b || !gate->fp_weight || !gate->ind || !gate->Out || !up->W8 || !up->scale_b || !up->fp_weight)
+        return set_error(MIXQ_ERR_BAD_ARG, "enqueue_gated: null tensor (gate: A, W8, scale_b, fp_weight, ind, Out; up: W8, scale_b, fp_weight)");
+    if (up->A && up->A != gate->A) return set_error(MIXQ_ERR_BAD_ARG, "enqueue_gated: gate and up must read the same activations");
+    if (!workspace) return set_error(MIXQ_ERR_WORKSPACE, "enqueue_gated: null workspace");
+    const Carve c = carve(M, N, K);
+    uintptr_t base = reinterpret_cast<uintptr_t>(workspace);
+    const uintptr_t aligned = (base + kAlign - 1) / kAlign * kAlign;
+    if (workspace_bytes < (aligned - base) + c.total) return set_error(MIXQ_ERR_WORKSPACE, "enqueue_gated: workspace too small");
+    // the [M, N] scratch of the two-GEMM composition (M > 1024) follows the plugin workspace when the caller provided it
+    size_t extra = align_up(static_cast<size_t>(M) * N * 2);
+    if (workspace_bytes < (aligned - base) + c.total + extra) extra = 0;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(aligned);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = launch_quant_extract(gate->A, M, K, gate->ind, MIXQ_NUM_OUTLIERS, ws + c.off_a8, ws + c.off_sa, ws + c.off_fpa, flags, s,
+                                  /*pdl=*/true, nullptr, 0, nullptr, 0.0f, nullptr, lo);
+    if (rc) return rc;
+    return launch_gemm_dequant_gated(ws + c.off_a8, ws + c.off_sa, ws + c.off_fpa, gate->W8, gate->scale_b, gate->fp_weight, up->W8,
+                                     up->scale_b, up->fp_weight, gate->Out, M, N, K, s, /*pdl=*/true, extra ? ws + c.total : nullptr, extra,
+                                     lo);
+}
+
 size_t mixq_allreduce_staging_size(int64_t M, int64_t N, int world) { return allreduce_staging_bytes(M, N, world); }
 size_t mixq_allreduce_counter_size(int64_t M, int64_t N, int world) { return allreduce_counter_bytes(M, N, world); }
 

@@ -50,6 +50,12 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
                         bool pdl, void* sk_ws = nullptr, size_t sk_ws_bytes = 0, bool sk_flags_clean = false,
                         const void* bias = nullptr, int act = 0,   // fused epilogue: see mixq_epilogue
                         LaunchOpts opts = LaunchOpts{});
+// gate and up projections of one MLP over one quantised A: Out = fp16(silu(gate)) * fp16(up) (gemm_fat.cuh, gated mode);
+// scratch (M*N*2 bytes) is only needed for M > 1024
+int launch_gemm_dequant_gated(const void* A8, const void* scale_a, const void* fp_A, const void* W8_gate, const void* sb_gate,
+                              const void* fpw_gate, const void* W8_up, const void* sb_up, const void* fpw_up, void* Out, int64_t M,
+                              int64_t N, int64_t K, cudaStream_t stream, bool pdl, void* scratch, size_t scratch_bytes,
+                              LaunchOpts opts = LaunchOpts{});
 size_t streamk_workspace_bytes();
 size_t decode_workspace_bytes(int64_t M, int64_t N);
 // stage 2 with the row-parallel all-reduce fused in (peer memory; see ArParams in gemm_i8_tcgen05.cu)
@@ -65,7 +71,8 @@ int launch_gemv_w8a16(const void* A, const void* q_weight, const void* scales, v
                       cudaStream_t stream, const void* bias = nullptr, int act = 0);
 
 // GEMM tile configuration ids (mixq_set_gemm_config); 0 = pick automatically.
-enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfg2CtaN256Tma = 9, kCfg2CtaN192Tma = 10, kCfg2CtaN256Decode = 11, kCfg2CtaN256DecodeNoSplit = 12, kCfg2CtaFat = 13, kCfgCount };
+enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfg2CtaN256Tma = 9, kCfg2CtaN192Tma = 10, kCfg2CtaN256Decode = 11, kCfg2CtaN256DecodeNoSplit = 12, kCfg2CtaFat = 13, kCfgCount,
+                  kCfgGatedUnfused = 100 /* mixq_*_gated only: the two-GEMM + multiply composition for every M (tests) */ };
 // SMs the persistent kernels may occupy on the current device (all, or the caller's per-call limit)
 int usable_sms(const LaunchOpts& opts);
 

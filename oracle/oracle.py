@@ -227,6 +227,21 @@ def forward(A, W8, sb, fp_weight, ind, mask: bool = False, use_table: bool = Tru
     return out
 
 
+def gated_mlp_half(A, gate: dict, up: dict, mask: bool = False, use_table: bool = True) -> np.ndarray:
+    """Input half of the reference's fused Llama MLP, MixLlamaMLP.forward (MixQ/src/mixquant/modules/fused/mlp.py:57-70):
+        up_output   = up_proj(x, cache)                                        fp16 [M, N]
+        gate_output = gate_proj.forward_without_preconditionFusedSilu(x, cache) fp16, SiLU fused in the dequant epilogue
+                      (modules/linear.py:288-373 -> int8FusedDequantizeSilu, linear_combination_dequant.h:167-272)
+        gate_output *= up_output                                                fp16 multiply (one rounding)
+    One quantised A serves both projections (the MixGemmCache); `gate` / `up` are packed linears (W8, scale_b, fp_weight, ind)
+    with identical `ind`."""
+    assert np.array_equal(gate["ind"], up["ind"]), "gate and up share the activation's outlier columns"
+    g = forward(A, gate["W8"], gate["scale_b"], gate["fp_weight"], gate["ind"], mask=mask, use_table=use_table, return_parts=True)
+    u = forward(A, up["W8"], up["scale_b"], up["fp_weight"], up["ind"], mask=mask, use_table=use_table, return_parts=True)
+    gs = epilogue_ex(g["acc"], g["sa"], gate["scale_b"], g["out0"], silu=True)
+    return (gs.astype(np.float32) * u["out"].astype(np.float32)).astype(np.float16)
+
+
 def forward_f64(A, W8, sb, fp_weight, ind, q, sa):
     """Higher-precision 'truth' for error reporting: same quantised operands, float64 math, no
     intermediate fp16 rounding of the outlier product."""
