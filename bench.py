@@ -4,7 +4,9 @@
 One *step* = one decode step of the model's MixQ linears: for each of the 32 decoder layers the five linear shapes
 (qkv 12288x4096, o 4096x4096, gate 11008x4096, up 11008x4096, down 4096x11008) are run over the same batch of 512
 synthetic tokens through the reference-facing call `mixq_enqueue` (= MixQPlugin::enqueue: per-token INT8 quantise +
-outlier gather kernel, then the tcgen05 INT8 GEMM with the fused fp16 outlier GEMM and dequant epilogue).  Every layer
+outlier gather kernel, then the tcgen05 INT8 GEMM with the fused fp16 outlier GEMM and dequant epilogue); the gate and up
+projections, which read the same activations, go through ONE `mixq_enqueue_gated` call that also applies the SiLU and
+the gate*up multiply of the reference's fused MLP (--mlp split: two plain plugin calls instead).  Every layer
 has its own weights (6.5 GB in total), so every weight byte of a step comes from HBM.  The step is replayed from a
 CUDA graph, as a serving runtime would.
     value        = sum over the 160 linears of 2*M*N*K / step time            (W8A8O16 GEMM TFLOP/s)
@@ -333,16 +335,38 @@ def run_ours(args, wl):
             W8, sb, fw, ind = pack_gpu(torch, W, acts[name][1])
             full = (W8, sb, fw, ind) if (li == 0 and tp > 1 and rank == 0) else None     # kept for the TP parity check
             W8, sb, fw, ind, (klo, khi) = shard_packed(torch, W8, sb, fw, ind, mode, tp, rank)
-            lay.append(dict(name=name, N=W8.shape[0], K=W8.shape[1], mode=mode, W8=W8, sb=sb, fw=fw, ind=ind, k=(klo, khi), full=full))
+            lay.append(dict(name=name, N=W8.shape[0], K=W8.shape[1], mode=mode, W8=W8, sb=sb, fw=fw, ind=ind, k=(klo, khi), full=full,
+                            n_acc=W8.shape[0], full_n=N, full_k=K))
             del W
         layers.append(lay)
+    # The gate and up projections of a layer read the same activations: by default they run as ONE mixq_enqueue_gated call
+    # (one quantise launch, one GEMM launch, Out = fp16(silu(gate)) * fp16(up) -- the reference's fused MLP,
+    # MixQ/src/mixquant/modules/fused/mlp.py:57-70); --mlp split keeps the two plugin calls.
+    plain_layers = layers
+    if args.mlp == "fused":
+        fused = []
+        for lay in layers:
+            calls, i = [], 0
+            while i < len(lay):
+                if (lay[i]["name"] == "gate" and i + 1 < len(lay) and lay[i + 1]["name"] == "up"
+                        and (lay[i]["N"], lay[i]["K"]) == (lay[i + 1]["N"], lay[i + 1]["K"])):
+                    calls.append(dict(lay[i], name="gate_up", up=lay[i + 1], n_acc=2 * lay[i]["N"]))
+                    i += 2
+                else:
+                    calls.append(lay[i])
+                    i += 1
+            fused.append(calls)
+        layers = fused
     A_in = {}
     for lin in layers[0]:
-        a = acts[lin["name"]][0]
+        a = acts["gate" if lin["name"] == "gate_up" else lin["name"]][0]
         A_in[lin["name"]] = a[:, lin["k"][0]:lin["k"][1]].contiguous() if lin["mode"] == "row" and tp > 1 else a
+    for lin in plain_layers[0]:
+        A_in.setdefault(lin["name"], A_in.get("gate_up") if lin["name"] in ("gate", "up") else None)
     max_out = max(lin["N"] for lin in layers[0])
     out_buf = torch.empty(M * max_out, dtype=torch.float16, device=dev)
-    ws = torch.empty(max(B.workspace_size(M, lin["N"], lin["K"]) for lin in layers[0]), dtype=torch.uint8, device=dev)
+    ws = torch.empty(max(B.gated_workspace_size(M, lin["N"], lin["K"]) if "up" in lin else B.workspace_size(M, lin["N"], lin["K"])
+                         for lin in layers[0]), dtype=torch.uint8, device=dev)
     flops_layer = sum(2.0 * M * N * K for _, N, K, _, _ in linears)      # whole job, all ranks together
     flops_step = flops_layer * n_layers
     stream = torch.cuda.current_stream()
@@ -371,7 +395,10 @@ def run_ours(args, wl):
     def run_linear(lin, out=None):
         a = A_in[lin["name"]]
         o = out if out is not None else out_buf[: M * lin["N"]].view(M, lin["N"])
-        if tp > 1 and lin["mode"] == "row" and peer is not None:
+        if "up" in lin:
+            u = lin["up"]
+            B.enqueue_gated(a, (lin["W8"], lin["sb"], lin["fw"]), (u["W8"], u["sb"], u["fw"]), lin["ind"], o, ws)
+        elif tp > 1 and lin["mode"] == "row" and peer is not None:
             B.enqueue_allreduce(a, lin["W8"], lin["sb"], lin["fw"], lin["ind"], ws, peer.peer_group(M, lin["N"]))
         elif tp > 1 and lin["mode"] == "row":
             # The one exchange step of the path.  The token dimension is cut into `chunks` row slabs: the NCCL all-reduce of
@@ -492,11 +519,20 @@ def run_ours(args, wl):
         o = out_buf[: M * Ns].view(M, Ns)
         qu = time_kernel(lambda i: B.quant_extract(a, layers[i][idx]["ind"], a8, sa, fpA), reps)
         B.quant_extract(a, lin["ind"], a8, sa, fpA)
-        gu = time_kernel(lambda i: B.gemm_dequant(a8, layers[i][idx]["W8"], sa, layers[i][idx]["sb"], fpA, layers[i][idx]["fw"], o,
-                                                  workspace=gws), reps)
+        if "up" in lin:
+            def gemm(i):
+                L, U = layers[i][idx], layers[i][idx]["up"]
+                B.gemm_dequant_gated(a8, sa, fpA, (L["W8"], L["sb"], L["fw"]), (U["W8"], U["sb"], U["fw"]), o)
+        else:
+            def gemm(i):
+                L = layers[i][idx]
+                B.gemm_dequant(a8, L["W8"], sa, L["sb"], fpA, L["fw"], o, workspace=gws)
+        gu = time_kernel(gemm, reps)
         tot_gemm += gu
         tot_quant += qu
-        per_linear[name] = {"N": Ns, "K": Ks, "gemm_us": round(gu, 2), "gemm_tflops": round(2.0 * M * Ns * Ks / gu / 1e6, 1),
+        n_acc = lin["n_acc"]      # accumulator columns: 2 N for the gated call (gate and up)
+        per_linear[name] = {"N": Ns, "K": Ks, "acc_columns": n_acc, "gemm_us": round(gu, 2),
+                            "gemm_tflops": round(2.0 * M * n_acc * Ks / gu / 1e6, 1),
                             "quant_us": round(qu, 2), "quant_gbs": round((3.0 * M * Ks + 258.0 * M) / qu / 1e3, 1)}
 
     # ---- INT8 tensor peak measured in this process (cuBLASLt 8192^3): burst for short timed regions at full clocks,
@@ -514,28 +550,34 @@ def run_ours(args, wl):
     else:
         int8_peak = 2.0 * pk["bf16_burst"]
         peak_src = f"2 x bf16_tflops of MEASURED_PEAKS.json ({pk['src']}); cuBLASLt INT8 unavailable"
+    def call_bytes(v):
+        """compulsory HBM bytes of a call: a gated call reads A once and both weight sets, and writes ONE [M, N] result"""
+        if v["acc_columns"] == v["N"]:
+            return linear_bytes(M, v["N"], v["K"])
+        return 2.0 * M * v["K"] + 2.0 * v["N"] * v["K"] + 512.0 * v["N"] + 4.0 * v["N"] + 512 + 2.0 * M * v["N"]
     for name, v in per_linear.items():
         Ns, Ks = v["N"], v["K"]
-        t_tensor = 2.0 * M * Ns * Ks / int8_peak / 1e6          # us
-        t_hbm = linear_bytes(M, Ns, Ks) / pk["hbm"] / 1e3       # us
+        t_tensor = 2.0 * M * v["acc_columns"] * Ks / int8_peak / 1e6          # us
+        t_hbm = call_bytes(v) / pk["hbm"] / 1e3                                # us
         v["floor_us"] = round(max(t_tensor, t_hbm), 2)
         v["floor_bound"] = "tensor" if t_tensor >= t_hbm else "hbm"
         v["frac_of_floor"] = round(max(t_tensor, t_hbm) / (v["gemm_us"] + v["quant_us"]), 4)
         floor_us += max(t_tensor, t_hbm)
     dom = max(per_linear.items(), key=lambda kv: kv[1]["gemm_us"])
-    gemm_flops = sum(2.0 * M * v["N"] * v["K"] for v in per_linear.values())
+    gemm_flops = sum(2.0 * M * v["acc_columns"] * v["K"] for v in per_linear.values())
     achieved = gemm_flops / tot_gemm / 1e6
     layer_ms = ms_step / n_layers
     hbm_bound = all(v["floor_bound"] == "hbm" for v in per_linear.values())
     if hbm_bound:
-        ach_b = sum(linear_bytes(M, v["N"], v["K"]) for v in per_linear.values()) / (tot_gemm + tot_quant) / 1e3
+        ach_b = sum(call_bytes(v) for v in per_linear.values()) / (tot_gemm + tot_quant) / 1e3
         head = {"bound": "hbm", "achieved": round(ach_b, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(ach_b / pk["hbm"], 4),
                 "peak_source": f"hbm_gbs of MEASURED_PEAKS.json ({pk['src']})"}
     else:
         head = {"bound": "tensor", "achieved": round(achieved, 1), "peak": round(int8_peak, 1), "unit": "TFLOP/s",
                 "frac": round(achieved / int8_peak, 4), "peak_source": peak_src}
     roofline = {**head,
-                "kernel": ("mixq_gemm_dequant_kernel (tcgen05 kind::i8 + kind::f16, cta_group::2, 256x128 pair tiles)" if 128 < M <= 1024 else
+                "kernel": ("mixq_gemm_dequant_fat_kernel (tcgen05 kind::i8 + kind::f16, cta_group::2, one 256 x Nt<=336 tile per CTA pair and wave; "
+                           "256x128 pair tiles where the cost model prefers them)" if 128 < M <= 1024 else
                            "mixq_gemm_dequant_kernel (tcgen05 kind::i8 + kind::f16, 128x128 tiles)" if M <= 128 else
                            "mixq_gemm_dequant_streamk_kernel, whole-tile schedule (tcgen05 kind::i8 + kind::f16, cta_group::2, TMA-store epilogue)"),
                 "gemm_tflops": round(achieved, 1), "frac_of_spec_4500": round(achieved / SPEC_INT8_TOPS, 4),
@@ -578,16 +620,46 @@ def run_ours(args, wl):
                     B.quant_extract(a, lin["ind"], a8, sa, fpA)
                     bit = bool(torch.equal(rq, a8) and torch.equal(rsa.view(torch.int16), sa.view(torch.int16))
                                and torch.equal(refgpu.extract(a, lin["ind"]).view(torch.int16), fpA.view(torch.int16)))
-                    del rq
-                    ref = refgpu.enqueue(a, lin["W8"], lin["sb"], lin["fw"], lin["ind"], None, rws)
                     rows = slice(0, M) if M <= 8192 else slice(M - 4096, M)     # the fp32 bound needs M x N floats
-                    ok, worst, rel = mixed_close(torch, got[rows], ref[rows], a[rows], lin["fw"], lin["ind"])
+                    if "up" in lin:
+                        # reference sequence of the fused MLP half (MixQ/src/mixquant/modules/fused/mlp.py:57-70): up through the
+                        # plugin kernels, gate through the reference's GemmDequantSilu (oracle/_ref/libref_mixsrc.so) over the
+                        # reference's own INT8 codes and cuBLAS outlier product, then an fp16 multiply
+                        U = lin["up"]
+                        ref_u = refgpu.enqueue(a, U["W8"], U["sb"], U["fw"], lin["ind"], None, rws)
+                        out0_g = refgpu.enqueue(a, torch.zeros_like(lin["W8"]), lin["sb"], lin["fw"], lin["ind"], None, rws)
+                        if refgpu.mixsrc_available():
+                            ref_g = refgpu.int8_fused_dequant_silu(rq, lin["W8"], rsa, lin["sb"], out0_g)
+                            how = "GemmDequantSilu"
+                        else:
+                            x = refgpu.enqueue(a, lin["W8"], lin["sb"], lin["fw"], lin["ind"], None, rws).float()
+                            ref_g = (x * torch.sigmoid(x)).half()
+                            how = "torch SiLU of the plugin output (libref_mixsrc.so missing: one extra rounding)"
+                        ref = ref_g * ref_u
+                        fa = a[rows][:, lin["ind"].long()].float()
+
+                        def ulp(x):
+                            return torch.exp2(torch.floor(torch.log2(x.abs().float().clamp_min(2.0 ** -14))) - 10)
+                        out0_u = (fa @ U["fw"].float().t()).half()
+                        bg = 2 * ulp(ref_g[rows]) + 1.2 * ulp(out0_g[rows]) + (fa.abs() @ lin["fw"].float().abs().t()) * 2.0 ** -20
+                        bu = ulp(ref_u[rows]) + ulp(out0_u) + (fa.abs() @ U["fw"].float().abs().t()) * 2.0 ** -20
+                        bound = ref_u[rows].float().abs() * bg + ref_g[rows].float().abs() * bu + bg * bu + ulp(ref[rows])
+                        d = (got[rows].float() - ref[rows].float()).abs()
+                        worst = float((d / bound).max())
+                        rel = float(torch.linalg.norm(d.double()) / torch.linalg.norm(ref[rows].float().double()).clamp_min(1e-30))
+                        ok = bool(worst <= 1.0 and rel <= 2e-3)
+                        parity.setdefault("gated_against", how)
+                        del ref_u, ref_g, out0_g, out0_u, bg, bu, bound, d, fa
+                    else:
+                        ref = refgpu.enqueue(a, lin["W8"], lin["sb"], lin["fw"], lin["ind"], None, rws)
+                        ok, worst, rel = mixed_close(torch, got[rows], ref[rows], a[rows], lin["fw"], lin["ind"])
+                    del rq
                     same = float((got.view(torch.int16) == ref.view(torch.int16)).float().mean())
                     relf = float(torch.linalg.norm((got.float() - ref.float()).flatten()[:: max(1, got.numel() // (1 << 26))].double()) /
                                  torch.linalg.norm(ref.float().flatten()[:: max(1, got.numel() // (1 << 26))].double()))
                     parity["linears"][lin["name"]] = {"quant_bit_exact": bit, "within_bound": ok, "worst_over_bound": round(worst, 3),
                                                       "rel_frobenius": rel, "rel_frobenius_all_rows": relf, "bit_identical_frac": same}
-                    parity["ok"] = parity["ok"] and ok and bit and relf <= 1e-3
+                    parity["ok"] = parity["ok"] and ok and bit and relf <= (2e-3 if "up" in lin else 1e-3)
                     del got, ref
                 del rws
             elif world > 1:
@@ -603,8 +675,12 @@ def run_ours(args, wl):
                     if rank == 0:
                         W8f, sbf, fwf, indf = lin["full"]
                         ref = torch.empty(M, W8f.shape[0], dtype=torch.float16, device=dev)
-                        wsf = torch.empty(B.workspace_size(M, W8f.shape[0], W8f.shape[1]), dtype=torch.uint8, device=dev)
-                        B.enqueue(acts[lin["name"]][0], W8f, sbf, fwf, indf, ref, wsf)
+                        if "up" in lin:
+                            wsf = torch.empty(B.gated_workspace_size(M, W8f.shape[0], W8f.shape[1]), dtype=torch.uint8, device=dev)
+                            B.enqueue_gated(acts["gate"][0], (W8f, sbf, fwf), lin["up"]["full"][:3], indf, ref, wsf)
+                        else:
+                            wsf = torch.empty(B.workspace_size(M, W8f.shape[0], W8f.shape[1]), dtype=torch.uint8, device=dev)
+                            B.enqueue(acts[lin["name"]][0], W8f, sbf, fwf, indf, ref, wsf)
                         rel = float(torch.linalg.norm((res.float() - ref.float()).double()) / torch.linalg.norm(ref.float().double()))
                         same = bool(torch.equal(res.view(torch.int16), ref.view(torch.int16)))
                         okl = rel <= 2e-3 and (same or lin["mode"] == "row")   # column-parallel shards are bit-identical slices
@@ -622,16 +698,16 @@ def run_ours(args, wl):
     e2e = None
     if not args.no_e2e:
         try:
-            groups = []   # lists of linear indices sharing their input
-            for i, (name, *_r) in enumerate(linears):
-                if name == "up" and groups and linears[groups[-1][0]][0] == "gate":
+            groups = []   # lists of call indices sharing their input
+            for i, lin in enumerate(layers[0]):
+                if lin["name"] == "up" and groups and layers[0][groups[-1][0]]["name"] == "gate":
                     groups[-1].append(i)
                 else:
                     groups.append([i])
             hA, hO = {}, {}
             for gi, grp in enumerate(groups):
                 lin0 = layers[0][grp[0]]
-                src = acts[lin0["name"]][0]
+                src = acts["gate" if lin0["name"] == "gate_up" else lin0["name"]][0]
                 if tp > 1 and lin0["mode"] == "column":
                     rows = M // tp                                   # each rank uploads 1/tp of the rows; NVLink all-gather
                     hA[gi] = torch.empty(rows, src.shape[1], dtype=torch.float16).pin_memory()
@@ -646,20 +722,27 @@ def run_ours(args, wl):
             h2d = sum(h.numel() * 2 for h in hA.values()) * n_layers * tp
             d2h = sum(h.numel() * 2 for h in hO.values()) * n_layers * tp
             if tp == 1:
-                scratch = torch.empty(max(B.linears_host_scratch_size(M, [layers[0][i]["N"] for i in grp], layers[0][grp[0]]["K"]) for grp in groups),
+                scratch = torch.empty(max(B.gated_host_scratch_size(M, layers[0][grp[0]]["N"], layers[0][grp[0]]["K"]) if "up" in layers[0][grp[0]] else
+                                          B.linears_host_scratch_size(M, [layers[0][i]["N"] for i in grp], layers[0][grp[0]]["K"]) for grp in groups),
                                       dtype=torch.uint8, device=dev)
+
+                def table(L):
+                    return B.make_tensors(None, L["W8"], L["sb"], L["fw"], L["ind"], None)
 
                 def e2e_step():
                     for lay in layers:
                         for gi, grp in enumerate(groups):
-                            tabs = [B.make_tensors(None, lay[i]["W8"], lay[i]["sb"], lay[i]["fw"], lay[i]["ind"], None) for i in grp]
-                            B.linears_host(tabs, hA[gi], [hO[i] for i in grp], scratch, stream=stream)
-                path = "mixq_linears_host (C ABI): pinned host A -> H2D once per distinct activation -> mixq_enqueue per linear -> D2H Out"
+                            if "up" in lay[grp[0]]:
+                                B.gated_host(table(lay[grp[0]]), table(lay[grp[0]]["up"]), hA[gi], hO[grp[0]], scratch, stream=stream)
+                            else:
+                                B.linears_host([table(lay[i]) for i in grp], hA[gi], [hO[i] for i in grp], scratch, stream=stream)
+                path = ("mixq_linears_host / mixq_gated_host (C ABI): pinned host A -> H2D once per distinct activation -> mixq_enqueue per "
+                        "linear (mixq_enqueue_gated for gate+up) -> D2H Out")
             else:
                 dA = {}
                 for gi, grp in enumerate(groups):
                     lin0 = layers[0][grp[0]]
-                    dA[gi] = torch.empty(M, acts[lin0["name"]][0].shape[1] if lin0["mode"] == "column" else lin0["K"], dtype=torch.float16, device=dev)
+                    dA[gi] = torch.empty(M, lin0["full_k"] if lin0["mode"] == "column" else lin0["K"], dtype=torch.float16, device=dev)
                 dO = {i: torch.empty(M, layers[0][i]["N"], dtype=torch.float16, device=dev) for grp in groups for i in grp}
 
                 def e2e_step():
@@ -677,6 +760,10 @@ def run_ours(args, wl):
                                 if lin["mode"] == "row" and peer is not None:
                                     B.enqueue_allreduce(dA[gi], lin["W8"], lin["sb"], lin["fw"], lin["ind"], ws, peer.peer_group(M, lin["N"]))
                                     res = peer.out(M, lin["N"])
+                                elif "up" in lin:
+                                    B.enqueue_gated(dA[gi], (lin["W8"], lin["sb"], lin["fw"]), (lin["up"]["W8"], lin["up"]["sb"], lin["up"]["fw"]),
+                                                    lin["ind"], dO[i], ws)
+                                    res = dO[i]
                                 else:
                                     B.enqueue(dA[gi], lin["W8"], lin["sb"], lin["fw"], lin["ind"], dO[i], ws)
                                     if lin["mode"] == "row":
@@ -713,10 +800,10 @@ def run_ours(args, wl):
             sys.path.insert(0, str(ROOT / "tests"))
             import refgpu
             if refgpu.available():
-                rws = torch.empty(max(refgpu.load().ref_workspace_size(M, lin["N"], lin["K"]) for lin in layers[0]), dtype=torch.uint8, device=dev)
+                rws = torch.empty(max(refgpu.load().ref_workspace_size(M, lin["N"], lin["K"]) for lin in plain_layers[0]), dtype=torch.uint8, device=dev)
 
                 def ref_step():
-                    for lay in layers:
+                    for lay in plain_layers:
                         for lin in lay:
                             refgpu.enqueue(A_in[lin["name"]], lin["W8"], lin["sb"], lin["fw"], lin["ind"], out_buf[: M * lin["N"]].view(M, lin["N"]), rws)
                 ref_step(); torch.cuda.synchronize()
@@ -726,7 +813,8 @@ def run_ours(args, wl):
                     ref_step()
                 r1.record(); torch.cuda.synchronize()
                 rms = r0.elapsed_time(r1) / 2
-                ref_gpu = {"what": "reference kernel/i8gemm.cu + cuBLAS fp16, 4 launches per linear, recompiled for sm_100a, direct launches",
+                ref_gpu = {"what": "reference kernel/i8gemm.cu + cuBLAS fp16, 4 launches per linear, five linears per layer (gate and up as two "
+                                   "plugin calls, no SiLU / multiply), recompiled for sm_100a, direct launches",
                            "ms_per_step": rms, "value": flops_step / (rms * 1e-3) / 1e12, "unit": UNIT, "speedup_ours": rms / ms_step}
                 del rws
         except Exception as e:
@@ -760,6 +848,10 @@ def run_ours(args, wl):
                     comm_sms=args.comm_sms if (tp > 1 and chunks > 1 and peer is None) else 0,
                     **({"fused_allreduce_unavailable": peer_note} if peer_note else {}),
                     launch="cuda-graph replay of the step" if use_graph else "direct launches",
+                    mlp=("gate and up projections in one mixq_enqueue_gated call: Out = fp16(silu(gate)) * fp16(up), the reference's fused MLP "
+                         "(MixQ/src/mixquant/modules/fused/mlp.py:57-70); FLOPs counted for both projections" if args.mlp == "fused"
+                         else "gate and up as two mixq_enqueue calls"),
+                    calls_per_layer=len(layers[0]),
                     parallelism=("single" if tp == 1 else
                                  f"tp{tp} (column: no collective; row: all-reduce fused into the GEMM kernel over NVLink peer memory)"
                                  if peer is not None else
@@ -795,6 +887,8 @@ def main():
                     help="row-parallel linears: all-reduce fused into the GEMM kernel (default) or NCCL after it")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto: decode-sized M)")
+    ap.add_argument("--mlp", default="fused", choices=["fused", "split"],
+                    help="gate and up projections: one mixq_enqueue_gated call (default) or two mixq_enqueue calls")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")

@@ -242,6 +242,13 @@ int mixq_linears_host(const mixq_tensors* const* t, int count, const void* A_hos
                       int64_t M, const int64_t* N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes,
                       unsigned flags, void* stream);
 
+/* mixq_enqueue_gated with HOST buffers: A crosses PCIe once, one [M, N] result comes back (half the bytes of the two
+ * projections' outputs). */
+size_t mixq_gated_host_scratch_size(int64_t M, int64_t N, int64_t K);
+int mixq_gated_host(const mixq_tensors* gate, const mixq_tensors* up, const void* A_host, void* Out_host,
+                    int64_t M, int64_t N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes,
+                    unsigned flags, void* stream);
+
 /* Kernel launches issued by this library since load (all threads); bench.py
  * reads it to fill `gpu_launches`. */
 uint64_t mixq_launch_count(void);

@@ -21,7 +21,7 @@ EXPORTS = [
     "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_enqueue", "mixq_enqueue_ex",
     "mixq_gemm_dequant_ex", "mixq_gated_workspace_size", "mixq_enqueue_gated", "mixq_gemm_dequant_gated",
     "mixq_quant_extract", "mixq_rmsnorm_quant_extract", "mixq_gemv_w8a16", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
-    "mixq_host_scratch_size", "mixq_linear_host", "mixq_linears_host_scratch_size", "mixq_linears_host",
+    "mixq_host_scratch_size", "mixq_linear_host", "mixq_linears_host_scratch_size", "mixq_linears_host", "mixq_gated_host_scratch_size", "mixq_gated_host",
     "mixq_allreduce_staging_size", "mixq_allreduce_counter_size", "mixq_enqueue_allreduce", "mixq_gemm_dequant_allreduce",
     "mixq_enqueue_opt", "mixq_gemm_dequant_opt", "mixq_enqueue_allreduce_opt", "mixq_gemm_dequant_allreduce_opt",
     "mixq_decode_workspace_size",
@@ -118,6 +118,10 @@ def load() -> ctypes.CDLL:
     L.mixq_linears_host.restype = ci
     L.mixq_linears_host.argtypes = [ctypes.POINTER(ctypes.POINTER(Tensors)), ci, vp, ctypes.POINTER(vp), i64, ctypes.POINTER(i64), i64,
                                     vp, sz, u32, vp]
+    L.mixq_gated_host_scratch_size.restype = sz
+    L.mixq_gated_host_scratch_size.argtypes = [i64, i64, i64]
+    L.mixq_gated_host.restype = ci
+    L.mixq_gated_host.argtypes = [ctypes.POINTER(Tensors), ctypes.POINTER(Tensors), vp, vp, i64, i64, i64, vp, sz, u32, vp]
     L.mixq_allreduce_staging_size.restype = sz
     L.mixq_allreduce_staging_size.argtypes = [i64, i64, ci]
     L.mixq_allreduce_counter_size.restype = sz
@@ -308,6 +312,18 @@ def linears_host(tensor_tables, A_host, outs_host, dev_scratch, flags: int = 0, 
     nn = (ctypes.c_int64 * n)(*[o.shape[-1] for o in outs_host])
     check(load().mixq_linears_host(tt, n, ctypes.c_void_p(A_host.data_ptr()), oo, M, nn, K, _ptr(dev_scratch),
                                    dev_scratch.numel() * dev_scratch.element_size(), flags, _stream(stream)), "mixq_linears_host")
+
+
+def gated_host(gate_table, up_table, A_host, out_host, dev_scratch, flags: int = 0, stream=None) -> None:
+    """mixq_gated_host: pinned-host A [M, K] -> Out_host [M, N] = fp16(silu(gate(A))) * fp16(up(A))"""
+    M, K = A_host.shape
+    check(load().mixq_gated_host(ctypes.byref(gate_table), ctypes.byref(up_table), ctypes.c_void_p(A_host.data_ptr()),
+                                 ctypes.c_void_p(out_host.data_ptr()), M, out_host.shape[-1], K, _ptr(dev_scratch),
+                                 dev_scratch.numel() * dev_scratch.element_size(), flags, _stream(stream)), "mixq_gated_host")
+
+
+def gated_host_scratch_size(M: int, N: int, K: int) -> int:
+    return int(load().mixq_gated_host_scratch_size(M, N, K))
 
 
 def linears_host_scratch_size(M: int, Ns, K: int) -> int:

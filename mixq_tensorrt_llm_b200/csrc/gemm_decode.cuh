@@ -145,6 +145,7 @@ mixq_gemm_dequant_decode_kernel(const __grid_constant__ CUtensorMap tm_a8, const
 
     if (threadIdx.x == 0) trace_stamp(1);
     ptx::pdl_wait_prior_grid();
+    ptx::pdl_launch_dependents();   // dependents may be scheduled as our CTAs retire; they wait for this grid's completion themselves
 
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = (K + kBlockKBytes - 1) / kBlockKBytes;
@@ -441,7 +442,6 @@ mixq_gemm_dequant_decode_kernel(const __grid_constant__ CUtensorMap tm_a8, const
     }
 
     if (threadIdx.x == kEpilogueWarp0 * 32) trace_stamp(7);
-    ptx::pdl_launch_dependents();
     ptx::tc_fence_before_sync();
     ptx::cluster_sync();
     if (warp_idx == 2) ptx::tmem_dealloc_2cta(tmem_base, T::kTmemCols);

@@ -34,7 +34,8 @@ constexpr int kFatMaxN = 336;          // Nt + Nt / 2 <= 512 TMEM columns, Nt % 
 constexpr int kFatMaxStages = 8;
 constexpr int kFatSbFloats = 352;
 constexpr int kFatOutStageBytes = 8 * 2 * 2048;   // per epilogue warp two 32-row x 32-column fp16 tiles (double-buffered TMA-store staging)
-constexpr int kFatFixedBytes = 3072 + kFatOutStageBytes;   // + scale_b / bias staging (2 x 352 floats, one tile at a time), barriers, TMEM pointer
+constexpr int kFatMaxPartPairs = 6;                // split-K: chunk pairs (32 columns) per epilogue warp, (336 / 16 / 2 + 1) / 2 rounded up
+constexpr int kFatFixedBytes = 3072 + 512 + kFatOutStageBytes;   // + scale_b / bias staging (2 x 352 floats, one tile at a time), barriers, TMEM pointer
 
 __device__ __forceinline__ uint32_t fat_idesc_i8(int n) { return ptx::make_idesc_i8(256, n); }
 __device__ __forceinline__ uint32_t fat_idesc_f16(int n) { return ptx::make_idesc_f16(256, n); }
@@ -45,7 +46,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                              const __grid_constant__ CUtensorMap tm_fw1, const __grid_constant__ CUtensorMap tm_fw2,
                              const __grid_constant__ CUtensorMap tm_out, const __half* __restrict__ scale_a, const __half* __restrict__ scale_b,
                              const __half* __restrict__ scale_b2, __half* __restrict__ Out, int M, int N, int K, int has_outlier,
-                             int m_tiles, int n_tiles, int Nt, int stages, int gated, EpiArgs epi) {
+                             int m_tiles, int n_tiles, int Nt, int stages, int gated, int ksplit, EpiArgs epi) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int N1 = gated ? Nt / 2 : (Nt > 256 ? 256 : Nt);   // columns of the first / second tcgen05.mma of a K step
@@ -63,14 +64,30 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
     uint64_t* f_drained_bar = f_full_bar + 1;            // ... rounded to fp16 and parked in columns [Nt, Nt + Nt/2)
     uint64_t* tmem_full_bar = f_drained_bar + 1;         // int32 accumulators complete
     uint64_t* tmem_empty_bar = tmem_full_bar + 1;        // epilogue has read them
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+    uint64_t* ring_free_bar = tmem_empty_bar + 1;        // split-K, in the sending CTA: the finishing CTA's ring may be overwritten
+    uint64_t* part_bar = ring_free_bar + 1;              // split-K, in the finishing CTA: [8 warps][kFatMaxPartPairs] partial sums landed
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(part_bar + 8 * kFatMaxPartPairs);
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t cta_rank = ptx::cluster_ctarank();
+    // Split-K (ksplit == 2): a cluster of 4 = two CTA pairs on one tile.  Pair 0 (cluster ranks 0, 1) reduces the outlier
+    // product and the first K-blocks and FINISHES the tile; pair 1 (ranks 2, 3) reduces the remaining K-blocks and SENDS its
+    // int32 partial sums into the finishing CTAs' shared memory (the ring, idle by then) with st.async, 16 bytes a lane,
+    // counted on mbarriers there.  Integer addition is associative: the result is bit-identical to the unsplit kernel.
+    const uint32_t crank = ptx::cluster_ctarank();
+    const uint32_t cta_rank = crank & 1u;              // rank inside the CTA pair
+    const uint32_t kpart = crank >> 1;                 // which K range this pair reduces
+    const uint32_t leader_rank = crank & ~1u;
+    const uint16_t pair_mask = static_cast<uint16_t>(3u << (kpart * 2));
     const bool is_leader = cta_rank == 0;
-    const int group_id = blockIdx.x >> 1;
-    const int num_groups = gridDim.x >> 1;
+    const bool sender = kpart != 0;
+    const int cluster_ctas = 2 * ksplit;
+    const int group_id = blockIdx.x / cluster_ctas;
+    const int num_groups = gridDim.x / cluster_ctas;
+    if (sender) has_outlier = 0;                        // the outlier product belongs to the finishing pair
+    // chunk (16 accumulator columns) ranges of the two epilogue warps that share a TMEM lane quarter
+    const int n_chunks_all = Nt >> 4;
+    const int c_split_all = min(n_chunks_all, ((n_chunks_all + 1) / 2 + 1) & ~1);   // even: both halves start on a 32-column boundary
     if (threadIdx.x == 0) trace_stamp(0);
 
     if (warp_idx == 0 && ptx::elect_one()) {
@@ -93,6 +110,16 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
         ptx::mbar_init(tmem_full_bar, 1);
         ptx::mbar_init(f_drained_bar, 2 * kStashEpiThreads / 32);
         ptx::mbar_init(tmem_empty_bar, 2 * kStashEpiThreads / 32);
+        ptx::mbar_init(ring_free_bar, 1);
+        for (int i = 0; i < 8 * kFatMaxPartPairs; ++i) ptx::mbar_init(&part_bar[i], 1);
+        if (ksplit == 2 && !sender) {
+            // arm the landing barriers: warp w's pair p of chunks brings 2 KB per chunk (32 lanes x 16 columns x 4 bytes)
+            for (int w = 0; w < 8; ++w) {
+                const int cb = (w >> 2) == 0 ? 0 : c_split_all, ce = (w >> 2) == 0 ? c_split_all : n_chunks_all;
+                for (int c = cb, pp = 0; c < ce; c += 2, ++pp)
+                    ptx::mbar_arrive_expect_tx(&part_bar[w * kFatMaxPartPairs + pp], static_cast<uint32_t>(min(2, ce - c)) * 2048u);
+            }
+        }
         ptx::fence_barrier_init();
     }
     if (warp_idx == 2) {
@@ -106,9 +133,14 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
 
     if (threadIdx.x == 0) trace_stamp(1);
     ptx::pdl_wait_prior_grid();
+    ptx::pdl_launch_dependents();   // dependents may be scheduled as our CTAs retire; they wait for this grid's completion themselves
 
     const int num_tiles = m_tiles * n_tiles;
-    const int num_kb = (K + kBlockKBytes - 1) / kBlockKBytes;
+    const int num_kb_all = (K + kBlockKBytes - 1) / kBlockKBytes;
+    // the finishing pair also does the outlier K-blocks and waits for their drain: it gets ~4 K-blocks less
+    const int kb_cut = ksplit == 2 ? max(1, min(num_kb_all - 1, (num_kb_all - 4) / 2)) : num_kb_all;
+    const int kb_first = sender ? kb_cut : 0;
+    const int num_kb = sender ? num_kb_all - kb_cut : kb_cut;      // K-blocks of THIS pair
     const int n_f = has_outlier ? kOutlierKBlocks : 0;
 
     if (warp_idx == 0) {
@@ -136,7 +168,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                 const int n1 = n_blk * tile_cols + static_cast<int>(cta_rank) * (N1 / 2);
                 const int n2 = n_blk * tile_cols + (gated ? 0 : N1) + static_cast<int>(cta_rank) * (N2 / 2);   // gated: the same channels of the up projection
                 for (int it = 0; it < n_f; ++it) load_block(&tm_fa, &tm_fw1, &tm_fw2, it * (kBlockKBytes / 2), m0, n1, n2);
-                for (int kb = 0; kb < num_kb; ++kb) load_block(&tm_a8, &tm_w1, &tm_w2, kb * kBlockKBytes, m0, n1, n2);
+                for (int kb = 0; kb < num_kb; ++kb) load_block(&tm_a8, &tm_w1, &tm_w2, (kb_first + kb) * kBlockKBytes, m0, n1, n2);
             }
         }
         __syncwarp();
@@ -174,7 +206,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                         if (N2) ptx::umma_i8_2cta(tmem_2, da + k * kDescStep, dc + k * kDescStep, idesc_i8_2, acc);
                     }
                 }
-                ptx::umma_commit_2cta(&empty_bar[stage]);
+                ptx::umma_commit_2cta_mask(&empty_bar[stage], pair_mask);
                 stage = nstage;
                 phase = nphase;
             };
@@ -186,12 +218,12 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                 }
                 if (has_outlier) {
                     for (int it = 0; it < kOutlierKBlocks; ++it) issue_block(std::integral_constant<int, 0>{}, it == 0);
-                    ptx::umma_commit_2cta(f_full_bar);
+                    ptx::umma_commit_2cta_mask(f_full_bar, pair_mask);
                     ptx::mbar_wait(f_drained_bar, lt & 1);   // columns [0, Nt) are free again (the ring keeps filling meanwhile)
                     ptx::tc_fence_after_sync();
                 }
                 for (int kb = 0; kb < num_kb; ++kb) issue_block(std::integral_constant<int, 1>{}, kb == 0);
-                ptx::umma_commit_2cta(tmem_full_bar);
+                ptx::umma_commit_2cta_mask(tmem_full_bar, pair_mask);
                 if (lt == 0) trace_stamp(3);
             }
             trace_stamp(4);
@@ -205,8 +237,8 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
         const int et = threadIdx.x - kEpilogueWarp0 * 32;   // 0..255
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-        const int n_chunks = Nt >> 4;
-        const int c_split = min(n_chunks, ((n_chunks + 1) / 2 + 1) & ~1);   // even: both halves start on a 32-column boundary
+        const int n_chunks = n_chunks_all;
+        const int c_split = c_split_all;
         const int c_begin = half == 0 ? 0 : c_split;
         const int c_end = half == 0 ? c_split : n_chunks;
         const uint32_t t_acc = tmem_base + lane_base;                                   // int32 / fp32 accumulators
@@ -214,7 +246,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
         auto arrive = [&](uint64_t* bar) {
             ptx::tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_cluster(bar, 0);
+            if (lane == 0) ptx::mbar_arrive_cluster(bar, leader_rank);
         };
         int lt = 0;
         for (int tile = group_id; tile < num_tiles; tile += num_groups, ++lt) {
@@ -224,6 +256,42 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
             const int gm = m0 + row;
             const bool row_ok = gm < M;
             const float sa_f = row_ok ? __half2float(scale_a[gm]) : 0.0f;
+            // split-K landing zone in the FINISHING CTA's ring: [warp 0..7][chunk slot][16-byte vector 0..3][lane] (2 KB per chunk)
+            const int ew = warp_idx - kEpilogueWarp0;
+            const uint32_t zone_warp = ptx::smem_u32(ring) + static_cast<uint32_t>(ew * c_split) * 2048u + lane * 16u;
+
+            if (sender) {
+                // ---- split-K sending pair: ship this CTA's int32 partial sums to the CTA of the finishing pair that holds the
+                // same rows (cluster rank - 2), a chunk (32 lanes x 16 columns) at a time
+                ptx::mbar_wait(tmem_full_bar, lt & 1);
+                ptx::tc_fence_after_sync();
+                ptx::mbar_wait(ring_free_bar, lt & 1);          // the finishing pair's tensor cores have read their whole ring
+                if (et == 0) trace_stamp(lt == 0 ? 6 : 8);
+                const uint32_t peer = crank - 2u;
+                const uint32_t r_zone = ptx::mapa_shared(zone_warp, peer);
+                const uint32_t r_bar0 = ptx::mapa_shared(ptx::smem_u32(&part_bar[ew * kFatMaxPartPairs]), peer);
+                uint32_t va[16], vb[16];
+                auto ship = [&](const uint32_t (&v)[16], int c) {
+                    const uint32_t dst = r_zone + static_cast<uint32_t>(c - c_begin) * 2048u;
+                    const uint32_t bar = r_bar0 + static_cast<uint32_t>((c - c_begin) >> 1) * 8u;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) ptx::st_async_v4(dst + g * 512u, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], bar);
+                };
+                if (c_begin < c_end) ptx::tmem_ld_32x16(t_acc + c_begin * 16, va);
+                for (int c = c_begin; c < c_end; c += 2) {
+                    ptx::tmem_ld_wait();
+                    if (c + 1 < c_end) ptx::tmem_ld_32x16(t_acc + (c + 1) * 16, vb);
+                    ship(va, c);
+                    if (c + 1 < c_end) {
+                        ptx::tmem_ld_wait();
+                        if (c + 2 < c_end) ptx::tmem_ld_32x16(t_acc + (c + 2) * 16, va);
+                        ship(vb, c + 1);
+                    }
+                }
+                if (et == 0) trace_stamp(9);
+                arrive(tmem_empty_bar);
+                continue;
+            }
 
             if (has_outlier) {
                 // ---- outlier product: fp32 accumulators -> fp16 (the reference's rounding), two per TMEM column
@@ -272,6 +340,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
             ptx::mbar_wait(tmem_full_bar, lt & 1);
             ptx::tc_fence_after_sync();
             if (et == 0) trace_stamp(lt == 0 ? 6 : 8);
+            if (ksplit == 2 && et == 0) ptx::mbar_arrive_cluster(ring_free_bar, crank + 2u);   // the sending CTA may overwrite the ring now
             __half* out_row = Out + static_cast<size_t>(gm) * N + n0;
             // The result leaves through shared memory: row-per-thread 16-byte global stores touch 32 cache lines per instruction;
             // instead each warp writes 32-row x 32-column SWIZZLE_64B tiles (conflict free for row-per-thread writes) that go out
@@ -338,14 +407,26 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                 if (has_outlier) ptx::tmem_ld_32x8(t_out0 + c * 8, vo);
             };
             if (!gated) {
+            // split-K: the other pair's partial sums of chunk c wait in the landing zone once the chunk pair's barrier has fired
+            auto add_partial = [&](uint32_t (&vi)[16], int c) {
+                if (ksplit != 2) return;
+                const uint32_t src = zone_warp + static_cast<uint32_t>(c - c_begin) * 2048u;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint4 pv = ptx::ld_shared_u4(src + g * 512u);
+                    vi[4 * g] += pv.x; vi[4 * g + 1] += pv.y; vi[4 * g + 2] += pv.z; vi[4 * g + 3] += pv.w;
+                }
+            };
             if (c_begin < c_end) load(ia, oa, c_begin);
             for (int c = c_begin; c < c_end; c += 2) {
                 uint32_t pa[8], pb[8];
                 const bool pair = c + 1 < c_end;
                 const int pi = ((c - c_begin) >> 1) & 1;
                 const uint32_t t = tiles_addr + pi * 2048;
+                if (ksplit == 2) ptx::mbar_wait(&part_bar[ew * kFatMaxPartPairs + ((c - c_begin) >> 1)], lt & 1);
                 ptx::tmem_ld_wait();
                 if (pair) load(ib, ob, c + 1);
+                add_partial(ia, c);
                 finish(ia, oa, c, pa);
                 if (pair) {
                     // the TMA store that last used this staging tile (two pairs ago) must have finished READING it
@@ -354,6 +435,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                     store_staged(pa, t, 0u);
                     ptx::tmem_ld_wait();
                     if (c + 2 < c_end) load(ia, oa, c + 2);
+                    add_partial(ib, c + 1);
                     finish(ib, ob, c + 1, pb);
                     store_staged(pb, t, 2u);
                     ptx::fence_proxy_async_smem();
@@ -443,7 +525,6 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
     }
 
     if (threadIdx.x == kEpilogueWarp0 * 32) trace_stamp(7);
-    ptx::pdl_launch_dependents();
     ptx::tc_fence_before_sync();
     ptx::cluster_sync();
     if (warp_idx == 2) ptx::tmem_dealloc_2cta(tmem_base, 512);

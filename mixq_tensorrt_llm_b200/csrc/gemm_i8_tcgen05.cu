@@ -185,6 +185,7 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
 
     // Everything above overlaps the tail of the previous kernel (PDL); A8/sa/fp_A are produced by it.
     ptx::pdl_wait_prior_grid();
+    ptx::pdl_launch_dependents();   // dependents may be scheduled as our CTAs retire; they wait for this grid's completion themselves
 
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = (K + kBlockKBytes - 1) / kBlockKBytes;
@@ -357,7 +358,6 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
     }
 
     // teardown
-    ptx::pdl_launch_dependents();
     ptx::tc_fence_before_sync();
     if constexpr (CTA == 2) ptx::cluster_sync(); else __syncthreads();
     if (warp_idx == 2) {
@@ -465,6 +465,7 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
     const uint32_t tmem_base = *tmem_ptr_s;
 
     ptx::pdl_wait_prior_grid();
+    ptx::pdl_launch_dependents();   // dependents may be scheduled as our CTAs retire; they wait for this grid's completion themselves
 
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = (K + kBlockKBytes - 1) / kBlockKBytes;
@@ -679,7 +680,6 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
         }
     }
 
-    ptx::pdl_launch_dependents();
     ptx::tc_fence_before_sync();
     if constexpr (CTA == 2) ptx::cluster_sync(); else __syncthreads();
     if (warp_idx == 2) {
@@ -878,6 +878,7 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
 
     if (threadIdx.x == 0) trace_stamp(1);
     ptx::pdl_wait_prior_grid();
+    ptx::pdl_launch_dependents();   // dependents may be scheduled as our CTAs retire; they wait for this grid's completion themselves
 
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = (K + kBlockKBytes - 1) / kBlockKBytes;
@@ -1390,7 +1391,6 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
     }
 
     if (threadIdx.x == kEpilogueWarp0 * 32) trace_stamp(7);
-    ptx::pdl_launch_dependents();
     ptx::tc_fence_before_sync();
     if constexpr (CTA == 2) ptx::cluster_sync(); else __syncthreads();
     if (warp_idx == 2) {
@@ -1777,13 +1777,61 @@ struct FatGated {
     const void* fp_weight_up;
 };
 
+// CTA clusters of 4 with the fat kernel's shared-memory footprint that can be resident at once (split-K mode); cached per device
+int fat_max_clusters4() {
+    static std::atomic<int> cached[kMaxDevices];
+    const DeviceInfo& dev = device_info();
+    if (dev.device < 0) return 0;
+    int v = cached[dev.device].load(std::memory_order_acquire);
+    if (v != 0) return v > 0 ? v : 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(dev.num_sms / 4 * 4));
+    cfg.blockDim = dim3(kStashThreads);
+    cfg.dynamicSmemBytes = 227 * 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = cudaFuncSetAttribute(mixq_gemm_dequant_fat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, mixq_gemm_dequant_fat_kernel, &cfg);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    cached[dev.device].store(n > 0 ? n : -1, std::memory_order_release);
+    return n;
+}
+
+// Split-K plan (two CTA pairs per tile in a cluster of 4, gemm_fat.cuh): only when every tile gets its own cluster (one wave) and
+// the partial-sum landing zone fits the ring
+bool plan_fat_split(int64_t M, int64_t N, int64_t K, const LaunchOpts& opts, FatPlan* out) {
+    int clusters = fat_max_clusters4();
+    const int by_sms = usable_sms(opts) / 4;
+    if (by_sms < clusters) clusters = by_sms;
+    if (clusters < 1 || (K + kBlockKBytes - 1) / kBlockKBytes < 8) return false;
+    const FatPlan pl = plan_fat(M, N, clusters);
+    const int n_chunks = pl.Nt / 16;
+    int c_split = ((n_chunks + 1) / 2 + 1) & ~1;
+    if (c_split > n_chunks) c_split = n_chunks;
+    if (pl.waves != 1 || pl.stages < 4 || (c_split + 1) / 2 > kFatMaxPartPairs) return false;
+    if (static_cast<size_t>(8) * c_split * 2048 > static_cast<size_t>(pl.stages) * pl.stage_bytes) return false;
+    *out = pl;
+    return true;
+}
+
 int launch_fat(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A, const void* fp_weight,
                void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl, EpiArgs epi, LaunchOpts opts,
-               const FatGated* gated = nullptr) {
+               const FatGated* gated = nullptr, int ksplit = 1) {
     const DeviceInfo& dev = device_info();
     const int pairs = usable_sms(opts) / 2;
     if (pairs < 1) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: sm_limit leaves no CTA pair");
-    const FatPlan pl = plan_fat(M, gated ? 2 * N : N, pairs, gated != nullptr);
+    FatPlan pl = plan_fat(M, gated ? 2 * N : N, pairs, gated != nullptr);
+    if (ksplit == 2 && (gated || !plan_fat_split(M, N, K, opts, &pl)))
+        return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: the split-K fat-tile schedule needs one cluster of 4 per tile");
     if (pl.stages < 3) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: fat tile does not fit shared memory");
     const int N1 = gated ? pl.Nt / 2 : (pl.Nt > 256 ? 256 : pl.Nt), N2 = pl.Nt - N1;
     const void* W2 = gated ? gated->W8_up : W8;
@@ -1815,16 +1863,17 @@ int launch_fat(const void* A8, const void* W8, const void* scale_a, const void* 
         attr_set_mask.fetch_or(uint64_t(1) << dev.device, std::memory_order_release);
     }
     const int64_t tiles = static_cast<int64_t>(pl.m_tiles) * pl.n_tiles;
-    const int groups = static_cast<int>(tiles < pairs ? tiles : pairs);
+    const int workers = ksplit == 2 ? static_cast<int>(tiles) : pairs;     // split-K: exactly one cluster of 4 per tile
+    const int groups = static_cast<int>(tiles < workers ? tiles : workers);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(groups * 2);
+    cfg.gridDim = dim3(groups * 2 * ksplit);
     cfg.blockDim = dim3(kStashThreads);
     cfg.dynamicSmemBytes = 1024 + static_cast<size_t>(pl.stages) * pl.stage_bytes + kFatFixedBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.x = 2 * ksplit;
     attr[na].val.clusterDim.y = 1;
     attr[na].val.clusterDim.z = 1;
     ++na;
@@ -1838,7 +1887,7 @@ int launch_fat(const void* A8, const void* W8, const void* scale_a, const void* 
     e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w1, tm_w2, tm_fa, tm_fw1, tm_fw2, tm_out, static_cast<const __half*>(scale_a),
                            static_cast<const __half*>(scale_b), static_cast<const __half*>(gated ? gated->scale_b_up : scale_b),
                            static_cast<__half*>(Out), static_cast<int>(M), static_cast<int>(N), static_cast<int>(K), has_outlier,
-                           pl.m_tiles, pl.n_tiles, pl.Nt, pl.stages, gated ? 1 : 0, epi);
+                           pl.m_tiles, pl.n_tiles, pl.Nt, pl.stages, gated ? 1 : 0, ksplit, epi);
     if (e != cudaSuccess) return set_cuda_error(e, "launch gemm_dequant_fat");
     count_launch();
     return MIXQ_OK;
@@ -1847,6 +1896,7 @@ int launch_fat(const void* A8, const void* W8, const void* scale_a, const void* 
 // out[i] *= other[i] (fp16): the last step of the gated linear where the two projections ran as separate GEMMs (M > 1024)
 __global__ void mixq_mul_inplace_kernel(__half2* __restrict__ out, const __half2* __restrict__ other, size_t n2) {
     ptx::pdl_wait_prior_grid();
+    ptx::pdl_launch_dependents();   // dependents may be scheduled as our CTAs retire; they wait for this grid's completion themselves
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n2; i += static_cast<size_t>(gridDim.x) * blockDim.x)
         out[i] = __hmul2(out[i], other[i]);
 }
@@ -1927,11 +1977,15 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
                 best = est;
                 cfg = kCfg2CtaFat;
             }
+            // (config 14, two pairs per tile each reducing half of K inside a cluster of 4, is not a candidate: measured on the
+            // B200 the main loop runs at the same rate per MAC whatever the tile width -- the tensor pipe at these clocks, not the
+            // operand bytes, sets it -- so the split only adds its exchange: 512x4096x11008 28.7 us against 22.6 us for id 5)
         }
     }
-    if (cfg == kCfg2CtaFat) {
+    if (cfg == kCfg2CtaFat || cfg == kCfg2CtaFatSplitK) {
         if (M > kDecodeMaxM) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: the fat-tile kernel serves M <= 1024");
-        return launch_fat(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, epi, opts);
+        return launch_fat(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, epi, opts, nullptr,
+                          cfg == kCfg2CtaFatSplitK ? 2 : 1);
     }
     if (cfg == kCfg2CtaN256Decode || cfg == kCfg2CtaN256DecodeNoSplit) {
         if (!decode_ok)

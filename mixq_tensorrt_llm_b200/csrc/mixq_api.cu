@@ -308,15 +308,20 @@ HostPipe& host_pipe() {
 }
 }  // namespace
 
-extern "C" int mixq_linears_host(const mixq_tensors* const* t, int count, const void* A_host, void* const* Out_host, int64_t M,
-                                 const int64_t* N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes, unsigned flags,
-                                 void* stream) {
+namespace {
+// gated: t[0] / t[1] are the gate / up projections of one MLP, ONE output Out_host[0] [M, N[0]] (mixq_enqueue_gated per slab)
+int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_host, void* const* Out_host, int64_t M,
+                      const int64_t* N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes, unsigned flags, void* stream,
+                      bool gated) {
+    const int n_tab = gated ? 2 : count;
     if (!t || !N || !Out_host || !A_host || !dev_scratch || count <= 0 || count > 8)
         return set_error(MIXQ_ERR_BAD_ARG, "linears_host: null pointer / count not in [1, 8]");
     if (M <= 0 || K <= 0) return set_error(MIXQ_ERR_BAD_ARG, "linears_host: bad dimensions");
+    for (int i = 0; i < n_tab; ++i)
+        if (!t[i]) return set_error(MIXQ_ERR_BAD_ARG, "linears_host: null tensor table");
     for (int i = 0; i < count; ++i)
-        if (!t[i] || !Out_host[i] || N[i] <= 0) return set_error(MIXQ_ERR_BAD_ARG, "linears_host: null tensor table / output or bad N");
-    if (dev_scratch_bytes < mixq_linears_host_scratch_size(M, N, count, K))
+        if (!Out_host[i] || N[i] <= 0) return set_error(MIXQ_ERR_BAD_ARG, "linears_host: null output or bad N");
+    if (dev_scratch_bytes < (gated ? mixq_gated_host_scratch_size(M, N[0], K) : mixq_linears_host_scratch_size(M, N, count, K)))
         return set_error(MIXQ_ERR_WORKSPACE, "linears_host: scratch too small");
     if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
     HostPipe& hp = host_pipe();
@@ -330,7 +335,7 @@ extern "C" int mixq_linears_host(const mixq_tensors* const* t, int count, const 
     for (int i = 0; i < count; ++i) {
         dOut[i] = cur;
         cur += align_up(static_cast<size_t>(M) * N[i] * 2);
-        const size_t w = mixq_workspace_size(M, N[i], K);
+        const size_t w = gated ? mixq_gated_workspace_size(M, N[i], K) : mixq_workspace_size(M, N[i], K);
         ws_bytes = w > ws_bytes ? w : ws_bytes;
     }
     uint8_t* ws = cur;
@@ -358,7 +363,14 @@ extern "C" int mixq_linears_host(const mixq_tensors* const* t, int count, const 
         const int64_t r0 = c * rows, nr = (r0 + rows <= M) ? rows : M - r0;
         e = cudaStreamWaitEvent(s, hp.up[c], 0);
         if (e != cudaSuccess) return set_cuda_error(e, "linears_host: wait H2D");
-        for (int i = 0; i < count; ++i) {
+        if (gated) {
+            mixq_tensors g = *t[0], u = *t[1];
+            g.A = u.A = dA + r0 * K * 2;
+            g.Out = dOut[0] + r0 * N[0] * 2;
+            const int rc = mixq_enqueue_gated(&g, &u, nr, N[0], K, ws, ws_bytes, nullptr, flags, stream);
+            if (rc) return rc;
+        }
+        for (int i = 0; i < count && !gated; ++i) {
             mixq_tensors d = *t[i];
             d.A = dA + r0 * K * 2;
             d.Out = dOut[i] + r0 * N[i] * 2;
@@ -377,6 +389,25 @@ extern "C" int mixq_linears_host(const mixq_tensors* const* t, int count, const 
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return set_cuda_error(e, "stream synchronize");
     return MIXQ_OK;
+}
+}  // namespace
+
+extern "C" int mixq_linears_host(const mixq_tensors* const* t, int count, const void* A_host, void* const* Out_host, int64_t M,
+                                 const int64_t* N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes, unsigned flags,
+                                 void* stream) {
+    return linears_host_impl(t, count, A_host, Out_host, M, N, K, dev_scratch, dev_scratch_bytes, flags, stream, false);
+}
+
+extern "C" size_t mixq_gated_host_scratch_size(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || K <= 0 || N <= 0) return 0;
+    return align_up(static_cast<size_t>(M) * K * 2) + align_up(static_cast<size_t>(M) * N * 2) + mixq_gated_workspace_size(M, N, K) + kAlign;
+}
+
+extern "C" int mixq_gated_host(const mixq_tensors* gate, const mixq_tensors* up, const void* A_host, void* Out_host, int64_t M,
+                               int64_t N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes, unsigned flags, void* stream) {
+    const mixq_tensors* t[2] = {gate, up};
+    if (!gate || !up) return set_error(MIXQ_ERR_BAD_ARG, "gated_host: null tensor table");
+    return linears_host_impl(t, 1, A_host, &Out_host, M, &N, K, dev_scratch, dev_scratch_bytes, flags, stream, true);
 }
 
 extern "C" int mixq_linear_host(const mixq_tensors* t, const void* A_host, void* Out_host, int64_t M, int64_t N, int64_t K,

@@ -270,6 +270,14 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
         "h"(static_cast<uint16_t>(3))
         : "memory");
 }
+// The same for a CTA pair inside a larger cluster: `mask` has the two bits of the pair's cluster ranks set.
+__device__ __forceinline__ void umma_commit_2cta_mask(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+}
 __device__ __forceinline__ void umma_i8_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
     asm volatile(
@@ -300,6 +308,25 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
         "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [remote];\n\t}\n" ::"r"(smem_u32(bar)),
         "r"(cta)
         : "memory");
+}
+
+// shared::cluster address of `local_saddr` (a shared::cta address of this CTA) in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_saddr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(cta));
+    return r;
+}
+// 16-byte store into another CTA's shared memory; the 16 bytes are counted on the mbarrier `remote_bar` (an address in the
+// same remote CTA) like a TMA transfer: the consumer waits on that barrier and reads with plain ld.shared
+__device__ __forceinline__ void st_async_v4(uint32_t remote_saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_saddr),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
 }
 
 // ------------------------------------------------------------------ misc

@@ -89,6 +89,7 @@ mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const 
 
     // The activations are produced by the previous kernel in the stream.
     ptx::pdl_wait_prior_grid();
+    ptx::pdl_launch_dependents();   // dependents may be scheduled as our CTAs retire; they wait for this grid's completion themselves
 
     // kernel 2's stream-K flags live in the same workspace; clearing them here costs no extra launch
     if (blockIdx.x == 0)
@@ -225,8 +226,6 @@ mixq_quant_extract_kernel(const __half* __restrict__ A, int64_t M, int K, const 
         }
     }
     ptx::cp_async_wait<0>();
-    // Let the dependent GEMM start its prologue.
-    ptx::pdl_launch_dependents();
 }
 
 using QuantKernel = void (*)(const __half*, int64_t, int, const int*, int, int8_t*, __half*, __half*, int, uint32_t*, int,

@@ -150,3 +150,51 @@ def symmetric_quantize_half(W_t):
     scales = np.zeros(N, dtype=np.float16)
     _prelib().ref_symmetric_quantize_half(proc.ctypes.data, unproc.ctypes.data, scales.ctypes.data, W.ctypes.data, K, N)
     return unproc, scales
+
+
+# ---- MixQ/src torch-extension pieces compiled unmodified (oracle/_ref/libref_mixsrc.so, driver oracle/ref_mixsrc_driver.cu):
+# generalT5LayerNorm_extract_outliers (layernorm.cu:121-198) and GemmDequantSilu as int8FusedDequantizeSiluCUDA instantiates it
+_mixsrc = None
+
+
+def mixsrc_available() -> bool:
+    return (REF_DIR / "libref_mixsrc.so").exists()
+
+
+def _mixsrc_lib():
+    global _mixsrc
+    if _mixsrc is None:
+        import torch  # noqa: F401  (libtorch must be in the process: layernorm.cu launches on torch's current stream)
+        L = ctypes.CDLL(str(REF_DIR / "libref_mixsrc.so"))
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        L.ref_rmsnorm_extract_quant.restype = ci
+        L.ref_rmsnorm_extract_quant.argtypes = [vp, vp, vp, ctypes.c_float, ci, ci, vp, vp, ci, vp, vp]
+        L.ref_int8_fused_dequant_silu.restype = ci
+        L.ref_int8_fused_dequant_silu.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, vp]
+        _mixsrc = L
+    return _mixsrc
+
+
+def rmsnorm_extract_quant(X, gamma, eps, ind):
+    """reference generalT5LayerNorm_extract_outliers: returns (normalised rows with the outlier columns zeroed, outliers
+    [M, len(ind)], INT8 codes, per-token scales)."""
+    import torch
+    M, K = X.shape
+    out = torch.empty_like(X)
+    outl = torch.zeros(M, ind.numel(), dtype=torch.float16, device=X.device)
+    q = torch.zeros(M, K, dtype=torch.int8, device=X.device)
+    sc = torch.empty(M, dtype=torch.float16, device=X.device)
+    rc = _mixsrc_lib().ref_rmsnorm_extract_quant(_p(X), _p(gamma), _p(out), float(eps), M, K, _p(outl), _p(ind), ind.numel(), _p(q), _p(sc))
+    assert rc == 0, rc
+    return out, outl, q, sc
+
+
+def int8_fused_dequant_silu(A8, W8, scale_row, scale_col, y):
+    """reference int8FusedDequantizeSiluCUDA(A, B, scale_row [M], scale_col [N], y [M,N]) -> fp16 [M,N]."""
+    import torch
+    M, K = A8.shape
+    N = W8.shape[0]
+    D = torch.empty(M, N, dtype=torch.float16, device=A8.device)
+    rc = _mixsrc_lib().ref_int8_fused_dequant_silu(_p(A8), _p(W8), _p(scale_row), _p(scale_col), _p(y), _p(D), M, N, K, _s())
+    assert rc == 0, rc
+    return D

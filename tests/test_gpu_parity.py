@@ -174,6 +174,77 @@ def test_rmsnorm_quant_extract(B, oracle, M, K, mask):
     assert torch.equal(A8, A8b) and torch.equal(sa.view(torch.int16), sab.view(torch.int16))
 
 
+@pytest.mark.skipif(not refgpu.mixsrc_available(), reason="oracle/_ref/libref_mixsrc.so not built")
+@pytest.mark.parametrize("M,K", [(7, 1024), (64, 4096), (300, 3584), (40, 11008), (512, 4096)])   # the reference's max-reduction assumes >= 256 threads, i.e. K >= 512
+def test_rmsnorm_quant_extract_vs_reference_kernel(B, oracle, M, K):
+    """SURVEY 8f #1 pinned to the reference's own kernel: generalT5LayerNorm_extract_outliers (layernorm.cu:121-198)
+    compiled unmodified (oracle/_ref/libref_mixsrc.so) and run on the same inputs.  The kernel always zeroes the outlier
+    columns (= MIXQ_FLAG_MASK_OUTLIERS).  Its sum of squares is a different fp32 tree from ours, so a normalised value may
+    differ in the last fp16 bit; every token whose normalised row agrees must agree bit for bit in scale and INT8 codes,
+    and the oracle's restatement must sit within the same 1 ulp of the reference kernel."""
+    rng = np.random.default_rng(M * 7 + K)
+    X = (rng.standard_normal((M, K)) * 1.5).astype(np.float16)
+    X[:, rng.choice(K, 16, replace=False)] *= 30
+    gamma = (1 + 0.2 * rng.standard_normal(K)).astype(np.float16)
+    ind = np.sort(rng.choice(K, size=128, replace=False)).astype(np.int32)
+    tX, tg, ti = _t(X), _t(gamma), _t(ind)
+    r_out, r_outl, r_q, r_sc = refgpu.rmsnorm_extract_quant(tX, tg, 1e-5, ti)
+    A8 = torch.empty(M, K, dtype=torch.int8, device=DEV)
+    sa = torch.empty(M, dtype=torch.float16, device=DEV)
+    fpA = torch.empty(M, 128, dtype=torch.float16, device=DEV)
+    Y = torch.empty(M, K, dtype=torch.float16, device=DEV)
+    B.rmsnorm_quant_extract(tX, tg, 1e-5, ti, A8, sa, fpA, Y, flags=B.FLAG_MASK_OUTLIERS)
+    torch.cuda.synchronize()
+    y = Y.cpu().numpy().copy()
+    ref_y = r_out.cpu().numpy()
+    ref_full = ref_y.copy()
+    ref_full[:, ind] = r_outl.cpu().numpy()                     # the reference's normalised row before the zeroing
+    assert _ulp_diff(y, ref_full).max() <= 1.0
+    assert _ulp_diff(oracle.rmsnorm(X, gamma, 1e-5), ref_full).max() <= 1.0
+    same_row = (y.view(np.uint16) == ref_full.view(np.uint16)).all(axis=1)
+    assert same_row.mean() >= 0.5, same_row.mean()
+    assert np.array_equal(fpA.cpu().numpy().view(np.uint16)[same_row], r_outl.cpu().numpy().view(np.uint16)[same_row])
+    assert np.array_equal(sa.cpu().numpy().view(np.uint16)[same_row], r_sc.cpu().numpy().view(np.uint16)[same_row])
+    assert np.array_equal(A8.cpu().numpy()[same_row], r_q.cpu().numpy()[same_row])
+    # rows that differ by an ulp somewhere: codes within 1 of the reference's
+    assert np.abs(A8.cpu().numpy().astype(np.int32) - r_q.cpu().numpy().astype(np.int32)).max() <= 1
+
+
+@pytest.mark.skipif(not refgpu.mixsrc_available(), reason="oracle/_ref/libref_mixsrc.so not built")
+@pytest.mark.parametrize("cfg", [0, 5, 9, 13])
+@pytest.mark.parametrize("M,N,K", [(96, 512, 1024), (512, 1376, 4096), (300, 2048, 3584)])
+def test_silu_epilogue_vs_reference_kernel(B, lib, oracle, cfg, M, N, K):
+    """SURVEY 8f #4 pinned to the reference's own kernel: GemmDequantSilu instantiated as int8FusedDequantizeSiluCUDA does
+    (cult.cu:2248-2273; epilogue functor linear_combination_dequant.h:167-272), compiled unmodified with the reference's
+    --use_fast_math, on the same INT8 operands, scales and fp16 addend.  Same op sequence (one FMA, fast-math SiLU, one
+    rounding), so the outputs must agree bit for bit -- without the outlier slab (addend 0, the reference's cache.zeros path,
+    linear.py:321-323) and with it (the addend given to the reference is this library's own fp16 outlier product)."""
+    if cfg == 13 and M <= 128:
+        pytest.skip("fat tiles serve 128 < M <= 1024")
+    rng = np.random.default_rng(M + N + K)
+    q = rng.integers(-127, 128, (M, K), dtype=np.int8)
+    w = rng.integers(-127, 128, (N, K), dtype=np.int8)
+    sa = (rng.random(M) * 2e-3 + 1e-4).astype(np.float16)
+    sb = (rng.random(N) * 2e-3 + 1e-4).astype(np.float16)
+    fpA = (rng.standard_normal((M, 128)) * 2).astype(np.float16)
+    fpW = (rng.standard_normal((N, 128)) * 0.05).astype(np.float16)
+    tq, tw, tsa, tsb, tfa, tfw = _t(q), _t(w), _t(sa), _t(sb), _t(fpA), _t(fpW)
+    ws = _gemm_ws(lib, M, N)
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    zeros = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+    B.gemm_dequant(tq, tw, tsa, tsb, None, None, out, workspace=ws, activation=B.ACT_SILU, config=cfg)
+    ref = refgpu.int8_fused_dequant_silu(tq, tw, tsa, tsb, zeros)
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int16), ref.view(torch.int16)), int((out.view(torch.int16) != ref.view(torch.int16)).sum())
+    # with the outlier product: out0 = this library's fp16 product (a zero INT8 operand leaves fp16(fma(0, s, out0)) = out0)
+    out0 = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    B.gemm_dequant(torch.zeros_like(tq), tw, tsa, tsb, tfa, tfw, out0, workspace=ws, config=cfg)
+    B.gemm_dequant(tq, tw, tsa, tsb, tfa, tfw, out, workspace=ws, activation=B.ACT_SILU, config=cfg)
+    ref = refgpu.int8_fused_dequant_silu(tq, tw, tsa, tsb, out0)
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int16), ref.view(torch.int16)), int((out.view(torch.int16) != ref.view(torch.int16)).sum())
+
+
 # ----------------------------------------------------------------------------- stage 2
 GEMM_SHAPES = [(128, 128, 128), (128, 128, 256), (256, 256, 512), (1, 8, 16), (100, 136, 144), (5, 4096, 4096),
                (130, 264, 4096), (512, 1024, 4096), (300, 512, 11008), (257, 1280, 8192), (32, 12288, 4096),
@@ -272,6 +343,51 @@ def test_decode_kernel_split_schedules(B, lib, oracle, M, N, K):
     out0 = oracle.outlier_gemm(fpA, fpW)
     mag = np.abs(fpA).astype(np.float64) @ np.abs(fpW).astype(np.float64).T
     _assert_mixed_close(mixed[11].cpu().numpy(), oracle.epilogue(oracle.igemm(q, w), sa, sb, out0), out0, "decode kernel vs oracle", mag)
+
+
+SPLITK_SHAPES = [(512, 4096, 4096), (512, 4096, 11008), (1024, 4096, 4096), (300, 3584, 3584), (512, 3584, 18944), (257, 1280, 8192),
+                 (512, 8192, 1024), (512, 8192, 3584), (200, 1000, 2064), (130, 520, 1040)]
+
+
+@pytest.mark.parametrize("M,N,K", SPLITK_SHAPES)
+def test_fat_splitk_cluster(B, lib, oracle, M, N, K):
+    """Config 14: two CTA pairs of a cluster of 4 reduce half of K each and the partial sums cross shared memory
+    (gemm_fat.cuh, st.async).  int32 addition is associative, so the result must equal the oracle bit for bit without the
+    outlier slab, and the unsplit fat-tile kernel (config 13) bit for bit with it -- also with the fused bias / SiLU epilogue.
+    The row-parallel shapes of the benchmarked models (o, down) must be served, not refused."""
+    rng = np.random.default_rng(M * 3 + N + K)
+    q = rng.integers(-127, 128, (M, K), dtype=np.int8)
+    w = rng.integers(-127, 128, (N, K), dtype=np.int8)
+    sa = (rng.random(M) * 0.05 + 1e-3).astype(np.float16)
+    sb = (rng.random(N) * 0.002 + 1e-4).astype(np.float16)
+    fpA = (rng.standard_normal((M, 128)) * 4).astype(np.float16)
+    fpW = (rng.standard_normal((N, 128)) * 0.05).astype(np.float16)
+    bias = rng.standard_normal(N).astype(np.float16)
+    tq, tw, tsa, tsb, tfa, tfw = _t(q), _t(w), _t(sa), _t(sb), _t(fpA), _t(fpW)
+    o = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
+    try:
+        B.gemm_dequant(tq, tw, tsa, tsb, None, None, o, config=14)
+    except Exception as e:
+        assert "split-K" in str(e)
+        assert M > 512 or (N, K) not in ((4096, 4096), (4096, 11008), (3584, 3584), (3584, 18944)), f"split-K refused a benchmarked shape: {e}"
+        pytest.skip(f"shape not served by the split-K schedule: {e}")
+    torch.cuda.synchronize()
+    ref = oracle.epilogue(oracle.igemm(q, w), sa, sb, None)
+    bad = np.argwhere(o.cpu().numpy().view(np.uint16) != ref.view(np.uint16))
+    assert bad.size == 0, f"{len(bad)} mismatches vs oracle, first at {bad[:5].tolist()}"
+    a, b = torch.empty_like(o), torch.empty_like(o)
+    for kw in ({}, {"bias": _t(bias)}, {"activation": B.ACT_SILU}):
+        B.gemm_dequant(tq, tw, tsa, tsb, tfa, tfw, a, config=14, **kw)
+        B.gemm_dequant(tq, tw, tsa, tsb, tfa, tfw, b, config=13, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16)), f"{kw}: split-K differs from the unsplit kernel"
+    # back-to-back launches
+    for cfg in (14, 14):
+        B.gemm_dequant(tq, tw, tsa, tsb, tfa, tfw, a, config=cfg)
+    torch.cuda.synchronize()
+    B.gemm_dequant(tq, tw, tsa, tsb, tfa, tfw, b, config=13)
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.int16), b.view(torch.int16))
 
 
 # ----------------------------------------------------------------------------- whole path
