@@ -663,7 +663,8 @@ def run_ours(args, wl):
                     del got, ref
                 del rws
             elif world > 1:
-                parity["against"] = "the single-GPU mixq_enqueue of the unsharded linear (rank 0), rel-Frobenius <= 2e-3 (SURVEY.md 8e)"
+                parity["against"] = ("rank 0: column-parallel = bit-identical slices of the single-GPU call on the unsharded linear; row-parallel = "
+                                     "bit-identical to the rank-order fp32 sum of the single-GPU calls on the shards")
                 for lin in layers[0]:
                     o = run_linear(lin)
                     if lin["mode"] == "row":
@@ -683,8 +684,28 @@ def run_ours(args, wl):
                             B.enqueue(acts[lin["name"]][0], W8f, sbf, fwf, indf, ref, wsf)
                         rel = float(torch.linalg.norm((res.float() - ref.float()).double()) / torch.linalg.norm(ref.float().double()))
                         same = bool(torch.equal(res.view(torch.int16), ref.view(torch.int16)))
-                        okl = rel <= 2e-3 and (same or lin["mode"] == "row")   # column-parallel shards are bit-identical slices
-                        parity["linears"][lin["name"]] = {"rel_frobenius": rel, "bit_identical": same, "ok": okl}
+                        if lin["mode"] == "row":
+                            # Row-parallel: every rank quantises ITS K slice with its own per-token scale, so the
+                            # result is a different -- finer -- quantisation of the same product than the unsharded call and
+                            # differs from it at the level of the INT8 quantisation error (reported, not bounded).  The
+                            # checkable statement: the all-reduced result equals fp16(sum_r fp32(partial_r)) in rank order,
+                            # where partial_r is the single-GPU mixq_enqueue of shard r -- bit for bit.
+                            acc = torch.zeros(M, W8f.shape[0], dtype=torch.float32, device=dev)
+                            part = torch.empty(M, W8f.shape[0], dtype=torch.float16, device=dev)
+                            for r in range(world):
+                                w8r, sbr, fwr, indr, (lo, hi) = shard_packed(torch, W8f, sbf, fwf, indf, "row", world, r)
+                                B.enqueue(acts[lin["name"]][0][:, lo:hi].contiguous(), w8r, sbr, fwr, indr, part, wsf)
+                                acc += part.float()
+                            want = acc.half()
+                            same_sum = bool(torch.equal(res.view(torch.int16), want.view(torch.int16)))
+                            nbad = int((res.view(torch.int16) != want.view(torch.int16)).sum())
+                            parity["linears"][lin["name"]] = {"bit_identical_to_rank_order_sum_of_shard_results": same_sum, "mismatches": nbad,
+                                                              "rel_frobenius_vs_unsharded_call": rel, "ok": same_sum}
+                            okl = same_sum
+                            del acc, part, want
+                        else:
+                            okl = same and rel == 0.0          # column-parallel shards are bit-identical slices of the unsharded result
+                            parity["linears"][lin["name"]] = {"rel_frobenius": rel, "bit_identical": same, "ok": okl}
                         parity["ok"] = parity["ok"] and okl
                         del ref, wsf
                     barrier()

@@ -74,10 +74,12 @@ int mixq_device_ok(void);
 
 /* Bytes of device workspace mixq_enqueue needs for (M, N, K). Layout (each
  * block 128-byte aligned, as nextWorkspacePtr does, TsinghuaMixQPlugin.cpp:206-215):
- *   A8 int8 [M,K] | scale_a fp16 [M] | fp_A fp16 [M,128] | split-K scratch: flags + int32 partial-sum slots (31.4 MB,
- *   M-independent) + fp16 outlier product of the decode kernel's tiles (2 * min(M,1024)pad256 * Npad256 bytes);
- *   non-decreasing in M, so the size for a profile's maximum covers every smaller batch
- * Replaces the reference's max(M*K + 2M + 2*K*N, 16*M*N) (TsinghuaMixQPlugin.cpp:342-346). */
+ *   A8 int8 [M,K] | scale_a fp16 [M] | fp_A fp16 [M,128]
+ * i.e. M*K + 258*M bytes plus alignment; non-decreasing in M, so the size for a profile's maximum covers every
+ * smaller batch.  Replaces the reference's max(M*K + 2M + 2*K*N, 16*M*N) (TsinghuaMixQPlugin.cpp:342-346).
+ * The opt-in split-K tile configurations (ids 8, 11, 12: never picked automatically) need
+ * mixq_decode_workspace_size(M, N) more bytes behind it: mixq_workspace_size_opt() includes them for such a
+ * mixq_options; mixq_enqueue_opt uses that scratch when the workspace it is given is large enough. */
 size_t mixq_workspace_size(int64_t M, int64_t N, int64_t K);
 
 /* The hot path: replaces MixQPlugin::enqueueImpl's M>4 branch
@@ -214,6 +216,13 @@ typedef struct mixq_peer_group {
 } mixq_peer_group;
 size_t mixq_allreduce_staging_size(int64_t M, int64_t N, int world);
 size_t mixq_allreduce_counter_size(int64_t M, int64_t N, int world);
+/* Peer waits inside the fused kernel poll with back-off and never trap: ranks may be skewed by seconds (first call after a
+ * per-rank checkpoint load, a debugger, a long kernel ahead of the call on one rank).  Callers should still barrier once
+ * before the FIRST fused call (every rank's counter block must have been zeroed).  After MIXQ_AR_TIMEOUT_MS (environment,
+ * default 60000, 0 = wait for ever) without progress a rank gives up, finishes the launch with an invalid result and raises
+ * a sticky error word in its counter block; mixq_allreduce_check copies that word back (synchronising `stream`) and
+ * returns MIXQ_ERR_CUDA if it is set, 0 otherwise.  `clear` != 0 resets it. */
+int mixq_allreduce_check(void* counters_local, int clear, void* stream);
 /* mixq_enqueue with the reduction fused in: t->Out is ignored, the result lands in g->out[i] on every rank i. */
 int mixq_enqueue_allreduce(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace,
                            size_t workspace_bytes, const mixq_peer_group* g, unsigned flags, void* stream);
@@ -269,6 +278,7 @@ typedef struct mixq_options {
 } mixq_options;
 /* mixq_enqueue_ex / mixq_gemm_dequant_ws+_ex / mixq_enqueue_allreduce / mixq_gemm_dequant_allreduce with options.
  * Unknown config ids fail with MIXQ_ERR_BAD_ARG. */
+size_t mixq_workspace_size_opt(int64_t M, int64_t N, int64_t K, const mixq_options* opt);
 int mixq_enqueue_opt(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, void* workspace,
                      size_t workspace_bytes, const mixq_epilogue* epi, const mixq_options* opt,
                      unsigned flags, void* stream);
@@ -284,8 +294,8 @@ int mixq_gemm_dequant_allreduce_opt(const void* A8, const void* W8, const void* 
                                     int64_t M, int64_t N, int64_t K, const mixq_peer_group* g,
                                     const mixq_options* opt, void* stream);
 /* Scratch stage 2 needs to run the decode-batch kernel (M <= 1024: split-K partial sums + the fp16 outlier product
- * of every tile): mixq_gemm_workspace_size() plus an (M, N)-dependent part.  mixq_workspace_size()
- * already includes it; a mixq_gemm_dequant_ws/_opt call with less scratch uses the whole-tile kernels. */
+ * of every tile): mixq_gemm_workspace_size() plus an (M, N)-dependent part (31.4 MB + 2 * Mpad256 * Npad256
+ * bytes).  Only the opt-in configurations 8 / 11 / 12 read it. */
 size_t mixq_decode_workspace_size(int64_t M, int64_t N);
 
 /* ---- TensorRT plugin surface through C handles (for ctypes / C callers) ----

@@ -18,11 +18,11 @@ FLAG_FORCE_MIXED = 2
 
 # every symbol include/mixq_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_enqueue", "mixq_enqueue_ex",
+    "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_workspace_size_opt", "mixq_enqueue", "mixq_enqueue_ex",
     "mixq_gemm_dequant_ex", "mixq_gated_workspace_size", "mixq_enqueue_gated", "mixq_gemm_dequant_gated",
     "mixq_quant_extract", "mixq_rmsnorm_quant_extract", "mixq_gemv_w8a16", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
     "mixq_host_scratch_size", "mixq_linear_host", "mixq_linears_host_scratch_size", "mixq_linears_host", "mixq_gated_host_scratch_size", "mixq_gated_host",
-    "mixq_allreduce_staging_size", "mixq_allreduce_counter_size", "mixq_enqueue_allreduce", "mixq_gemm_dequant_allreduce",
+    "mixq_allreduce_staging_size", "mixq_allreduce_counter_size", "mixq_allreduce_check", "mixq_enqueue_allreduce", "mixq_gemm_dequant_allreduce",
     "mixq_enqueue_opt", "mixq_gemm_dequant_opt", "mixq_enqueue_allreduce_opt", "mixq_gemm_dequant_allreduce_opt",
     "mixq_decode_workspace_size",
     "mixq_launch_count", "mixq_debug_set_trace", "initOpenAiTritonPlugins", "mixq_plugin_create",
@@ -85,6 +85,8 @@ def load() -> ctypes.CDLL:
     L.mixq_device_ok.restype = ci
     L.mixq_workspace_size.restype = sz
     L.mixq_workspace_size.argtypes = [i64, i64, i64]
+    L.mixq_workspace_size_opt.restype = sz
+    L.mixq_workspace_size_opt.argtypes = [i64, i64, i64, ctypes.POINTER(Options)]
     L.mixq_enqueue.restype = ci
     L.mixq_enqueue.argtypes = [ctypes.POINTER(Tensors), i64, i64, i64, vp, sz, u32, vp]
     L.mixq_enqueue_ex.restype = ci
@@ -122,6 +124,8 @@ def load() -> ctypes.CDLL:
     L.mixq_gated_host_scratch_size.argtypes = [i64, i64, i64]
     L.mixq_gated_host.restype = ci
     L.mixq_gated_host.argtypes = [ctypes.POINTER(Tensors), ctypes.POINTER(Tensors), vp, vp, i64, i64, i64, vp, sz, u32, vp]
+    L.mixq_allreduce_check.restype = ci
+    L.mixq_allreduce_check.argtypes = [vp, ci, vp]
     L.mixq_allreduce_staging_size.restype = sz
     L.mixq_allreduce_staging_size.argtypes = [i64, i64, ci]
     L.mixq_allreduce_counter_size.restype = sz
@@ -195,7 +199,9 @@ def _stream(stream=None):
     return ctypes.c_void_p(s.cuda_stream)
 
 
-def workspace_size(M: int, N: int, K: int) -> int:
+def workspace_size(M: int, N: int, K: int, config: int = 0) -> int:
+    if config:
+        return int(load().mixq_workspace_size_opt(M, N, K, ctypes.byref(Options(int(config), 0))))
     return int(load().mixq_workspace_size(M, N, K))
 
 

@@ -764,6 +764,29 @@ __device__ __forceinline__ void signal_add_relaxed_sys(uint32_t* p, uint32_t v) 
     asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+// Wait until a counter that peers on other GPUs bump reaches `expect`.  Ranks may be skewed by seconds (first call after a
+// per-rank checkpoint load, a debugger, a long kernel ahead of this one on one rank), so this never traps: it polls, backs
+// off with nanosleep, and only after `timeout_ns` (0 = wait for ever) gives up, raising the error word of this rank's counter
+// block -- the launch then completes with an invalid result that mixq_allreduce_check() reports to the host, instead of a
+// sticky context error.
+__device__ __forceinline__ bool wait_counter_sys(const uint32_t* p, uint32_t expect, unsigned long long timeout_ns, uint32_t* err_word) {
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
+    while (ld_acquire_sys(p) < expect) {
+        if (++spins < 2048u) continue;
+        __nanosleep(spins < (1u << 16) ? 64 : 1000);
+        if ((spins & 0x3FFu) == 0u && timeout_ns != 0ull) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0ull) t0 = now;
+            else if (now - t0 > timeout_ns) {
+                atomicExch(err_word, 1u);
+                return false;
+            }
+        }
+    }
+    return true;
+}
 // 16-byte store to an NVSwitch multicast address: the switch replicates it into every rank's copy of the buffer
 __device__ __forceinline__ void multimem_st_v4(void* mc_ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_ptr), "r"(a), "r"(b), "r"(c), "r"(d)
@@ -789,8 +812,8 @@ __device__ __forceinline__ void multimem_st_v4(void* mc_ptr, uint32_t a, uint32_
 //                             i.e. when this rank's Out is complete.  It re-arms `done` and the `pushed` word of this
 //                             launch and advances the launch epoch; consecutive launches alternate between two
 //                             `pushed` words so a fast peer's next launch can never race with the re-arming.
-// Counter block of a rank (uint32 words): 0 = done, 1 = launch epoch, 2..3 = pushed[epoch & 1].
-constexpr int kArWordDone = 0, kArWordEpoch = 1, kArWordPushed = 2;
+// Counter block of a rank (uint32 words): 0 = done, 1 = launch epoch, 2..3 = pushed[epoch & 1], 4 = error flag.
+constexpr int kArWordDone = 0, kArWordEpoch = 1, kArWordPushed = 2, kArWordError = 4;   // 4: a peer wait timed out (sticky until cleared by the host)
 constexpr size_t kArCounterBytes = 128;
 struct alignas(64) ArParams {
     CUtensorMap tm_out[MIXQ_MAX_RANKS];     // every rank's Out [M, N], box 32 rows x BLOCK_N columns, no swizzle
@@ -801,6 +824,7 @@ struct alignas(64) ArParams {
     const __half* stage_local;              // this rank's whole staging area: [world][slots][256][BLOCK_N] fp16
     __half* out_mc;                         // NVSwitch multicast mapping of Out (a store lands in every rank's Out), or null
     int world, rank, slots;
+    unsigned long long timeout_ns;          // give up waiting for a peer after this long (0 = never), see wait_counter_sys
 };
 struct ArNone {
     int unused;
@@ -1242,12 +1266,9 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                 // ---- broadcast through the switch: each warp reduces whole 512-byte rows (lane = chunk * 4 + 16-byte slot of the
                 // chunk-major staging image) and issues ONE multicast store per row; the egress of this phase drops from
                 // (world - 1) copies to one.
-                if (et == 0) {
-                    const uint32_t expect = static_cast<uint32_t>(world) * gridDim.x;
-                    uint32_t spins = 0;
-                    while (ld_acquire_sys(my_cnt + kArWordPushed + parity) < expect) {
-                        if (++spins > (1u << 24)) __trap();
-                    }
+                if (et == 0 && static_cast<int>(blockIdx.x) < units) {   // a CTA without units must not poll a word CTA 0 may already have re-armed
+                    wait_counter_sys(my_cnt + kArWordPushed + parity, static_cast<uint32_t>(world) * gridDim.x, ar.timeout_ns,
+                                     my_cnt + kArWordError);
                     trace_stamp(13);
                 }
                 ptx::named_bar_sync(2, kStashEpiThreads);
@@ -1304,11 +1325,8 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                     ptx::tma_store_wait_read<kNumSlabs - 1>();   // the store that last used this slab has read it
                     if (k == 0) {
                         // every CTA of every rank has pushed (and fenced) its partial tiles
-                        const uint32_t expect = static_cast<uint32_t>(world) * gridDim.x;
-                        uint32_t spins = 0;
-                        while (ld_acquire_sys(my_cnt + kArWordPushed + parity) < expect) {
-                            if (++spins > (1u << 24)) __trap();
-                        }
+                        wait_counter_sys(my_cnt + kArWordPushed + parity, static_cast<uint32_t>(world) * gridDim.x, ar.timeout_ns,
+                                         my_cnt + kArWordError);
                         trace_stamp(13);
                     }
                 }
@@ -1374,11 +1392,12 @@ mixq_gemm_dequant_streamk_kernel(const __grid_constant__ CUtensorMap tm_a8, cons
                 }
                 if (blockIdx.x == 0) {
                     // this rank's Out is complete when every row group of every tile has been delivered
-                    const uint32_t expect = static_cast<uint32_t>(num_tiles) * 8u;
-                    uint32_t spins = 0;
-                    while (ld_acquire_sys(my_cnt + kArWordDone) < expect) {
-                        if (++spins > (1u << 24)) __trap();
-                    }
+                    wait_counter_sys(my_cnt + kArWordDone, static_cast<uint32_t>(num_tiles) * 8u, ar.timeout_ns, my_cnt + kArWordError);
+                    // A rank that owns no tile (fewer tiles than ranks) never waited for `pushed` itself: make sure every
+                    // peer's bump of this launch has landed before the word is re-armed, or a late one would leak into the
+                    // launch after next.
+                    wait_counter_sys(my_cnt + kArWordPushed + parity, static_cast<uint32_t>(world) * gridDim.x, ar.timeout_ns,
+                                     my_cnt + kArWordError);
                     // every CTA of this rank that had row groups to reduce is past its `pushed` wait (its groups are
                     // counted in `done`): re-arm for the launch after next and flip the epoch
                     my_cnt[kArWordDone] = 0u;
@@ -1610,6 +1629,13 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
                 ar.stage_push[i] = static_cast<uint8_t*>(pg->staging[i]) + region * pg->rank;
                 if ((rc = make_tmap(&ar.tm_out[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, pg->out[i], M, N, 32, T::kBlockN * 2)))
                     return rc;
+            }
+            {   // peer-wait timeout: MIXQ_AR_TIMEOUT_MS (default 60 s, 0 = wait for ever)
+                static const long long timeout_ms = [] {
+                    const char* e = std::getenv("MIXQ_AR_TIMEOUT_MS");
+                    return e ? std::atoll(e) : 60000ll;
+                }();
+                ar.timeout_ns = timeout_ms > 0 ? static_cast<unsigned long long>(timeout_ms) * 1000000ull : 0ull;
             }
             ar.stage_local = static_cast<const __half*>(pg->staging[pg->rank]);
             ar.out_mc = static_cast<__half*>(pg->out_multicast);

@@ -27,7 +27,8 @@ inline Carve carve(int64_t M, int64_t N, int64_t K) {
     c.off_sa = align_up(static_cast<size_t>(M) * static_cast<size_t>(K));
     c.off_fpa = c.off_sa + align_up(static_cast<size_t>(M) * 2);
     c.off_sk = c.off_fpa + align_up(static_cast<size_t>(M) * MIXQ_NUM_OUTLIERS * 2);
-    c.total = c.off_sk + align_up(decode_workspace_bytes(M, N));  // split-K flags + partial-sum slots + decode out0 area
+    c.total = c.off_sk;   // what the default path needs; the opt-in split-K configurations want decode_workspace_bytes() more
+    (void)N;
     return c;
 }
 }  // namespace
@@ -90,6 +91,13 @@ size_t mixq_workspace_size(int64_t M, int64_t N, int64_t K) {
     return carve(M, N < 0 ? 0 : N, K).total + kAlign;  // + slack to align the base like nextWorkspacePtr does
 }
 size_t mixq_decode_workspace_size(int64_t M, int64_t N) { return decode_workspace_bytes(M, N); }
+size_t mixq_workspace_size_opt(int64_t M, int64_t N, int64_t K, const mixq_options* opt) {
+    const size_t base = mixq_workspace_size(M, N, K);
+    if (!base || !opt) return base;
+    const int c = opt->gemm_config;
+    const bool scratch = c == kCfg2CtaN256StreamK || c == kCfg2CtaN256Decode || c == kCfg2CtaN256DecodeNoSplit;
+    return base + (scratch ? align_up(decode_workspace_bytes(M, N < 0 ? 0 : N)) : 0);
+}
 
 int mixq_quant_extract(const void* A, int64_t M, int64_t K, const void* ind, int n_ind, void* A8, void* scale_a,
                        void* fp_A, unsigned flags, void* stream) {
@@ -182,12 +190,15 @@ int mixq_enqueue_opt(const mixq_tensors* t, int64_t M, int64_t N, int64_t K, voi
     void* sa = ws + c.off_sa;
     void* fpA = ws + c.off_fpa;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    void* sk = ws + c.off_sk;
-    int rc = launch_quant_extract(t->A, M, K, t->ind, MIXQ_NUM_OUTLIERS, A8, sa, fpA, flags, s, /*pdl=*/true, sk, 1024, nullptr,
+    // split-K scratch of the opt-in configurations 8 / 11 / 12: present only when the caller sized the workspace with
+    // mixq_workspace_size_opt; the quantise kernel then also clears its flags
+    const size_t sk_bytes = decode_workspace_bytes(M, N);
+    void* sk = workspace_bytes >= (aligned - base) + c.total + sk_bytes ? ws + c.off_sk : nullptr;
+    int rc = launch_quant_extract(t->A, M, K, t->ind, MIXQ_NUM_OUTLIERS, A8, sa, fpA, flags, s, /*pdl=*/true, sk, sk ? 1024 : 0, nullptr,
                                   0.0f, nullptr, lo);
     if (rc) return rc;
     return launch_gemm_dequant(A8, t->W8, sa, t->scale_b, fpA, t->fp_weight, t->Out, M, N, K, s, /*pdl=*/true, sk,
-                               decode_workspace_bytes(M, N), /*sk_flags_clean=*/true, bias, act, lo);
+                               sk ? sk_bytes : 0, /*sk_flags_clean=*/sk != nullptr, bias, act, lo);
 }
 
 size_t mixq_gated_workspace_size(int64_t M, int64_t N, int64_t K) {
@@ -231,6 +242,18 @@ int mixq_enqueue_gated(const mixq_tensors* gate, const mixq_tensors* up, int64_t
 
 size_t mixq_allreduce_staging_size(int64_t M, int64_t N, int world) { return allreduce_staging_bytes(M, N, world); }
 size_t mixq_allreduce_counter_size(int64_t M, int64_t N, int world) { return allreduce_counter_bytes(M, N, world); }
+
+int mixq_allreduce_check(void* counters_local, int clear, void* stream) {
+    if (!counters_local) return set_error(MIXQ_ERR_BAD_ARG, "allreduce_check: null counter block");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint32_t word = 0;
+    uint32_t* dev_word = static_cast<uint32_t*>(counters_local) + 4;   // kArWordError
+    cudaError_t e = cudaMemcpyAsync(&word, dev_word, sizeof(word), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess && word && clear) e = cudaMemsetAsync(dev_word, 0, sizeof(word), s);
+    if (e != cudaSuccess) return set_cuda_error(e, "allreduce_check");
+    return word ? set_error(MIXQ_ERR_CUDA, "fused all-reduce: a peer did not arrive within MIXQ_AR_TIMEOUT_MS; the result of that call is invalid") : MIXQ_OK;
+}
 
 int mixq_gemm_dequant_allreduce(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                                 const void* fp_weight, int64_t M, int64_t N, int64_t K, const mixq_peer_group* g, void* stream) {

@@ -48,6 +48,13 @@ class PeerBuffers:
         """The local Out [M, N] view the fused call fills."""
         return self.buf[: M * N * 2].view(torch.float16).view(M, N)
 
+    def check(self, clear: bool = False) -> None:
+        """Raise if a fused call on this rank gave up waiting for a peer (mixq_allreduce_check; synchronises the stream)."""
+        cnt = self.bases[self.rank] + self.out_bytes + self.staging_bytes
+        import ctypes
+        binding.check(binding.load().mixq_allreduce_check(ctypes.c_void_p(cnt), int(clear),
+                                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "mixq_allreduce_check")
+
     def peer_group(self, M: int, N: int) -> binding.PeerGroup:
         if M * N * 2 > self.out_bytes:
             raise binding.MixQError("PeerBuffers: shape exceeds the allocation")

@@ -68,14 +68,20 @@ class _PluginHandle:
 
 
 _workspaces: dict = {}
+_retired: list = []
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Grow-only per-device scratch, playing the role of the workspace TensorRT hands to enqueue."""
-    ws = _workspaces.get(device)
+    """Scratch playing the role of the workspace TensorRT hands to enqueue: one buffer per (device, stream), so linears
+    running on different streams never share A8 / scale_a / fp_A, grow-only, and a buffer that has been outgrown is kept
+    alive (a captured CUDA graph may still hold its address) instead of being freed."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _retired.append(ws)
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[device] = ws
+        _workspaces[key] = ws
     return ws
 
 
@@ -172,8 +178,8 @@ class MixQLinear(torch.nn.Module):
 
     def forward(self, A: torch.Tensor, activation: Optional[str] = None, fuse_bias: bool = False) -> torch.Tensor:
         """``activation="silu"`` and/or ``fuse_bias=True`` run the fused epilogue (mixq_enqueue_ex: SiLU in fp32 before the
-        output rounding, bias added to the fp16 result) instead of separate elementwise passes; not for tensor-parallel
-        shards, whose partial results must be reduced first."""
+        output rounding, bias added to the fp16 result) instead of separate elementwise passes; not for row-parallel
+        shards, whose partial results must be reduced first (column-parallel shards are gathered afterwards)."""
         if activation is not None or fuse_bias:
             if activation not in (None, "silu"):
                 raise ValueError("activation must be None or 'silu'")
@@ -193,7 +199,7 @@ class MixQLinear(torch.nn.Module):
             x = out.view(*A.shape[:-1], self.out_features)
             if self.bias is not None and not fuse_bias:
                 x = x + self.bias.to(x.dtype)
-            return x
+            return self._gather_columns(x)      # the bias shard was added to its own columns before the gather
         if self._peer is not None and self.tp_size > 1:
             binding.require_device()
             M = A.numel() // A.shape[-1]
@@ -211,14 +217,21 @@ class MixQLinear(torch.nn.Module):
         x = mixgemm(A.shape[0], self.out_features, self.in_features,
                     [A, self.weight, self.weights_scaling_factor, self.fp_weight, self.fp_ind, self.qweight,
                      self.weights_scaling_factor], plugin=self._plugin)
-        if self.tp_size > 1 and self.tp_group is not None:
+        if self.tp_size > 1 and self.tp_group is not None and self.parallel_mode == "row":
             import torch.distributed as dist
-            if self.parallel_mode == "row":
-                dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.tp_group)  # the one exchange step of the path
-            elif self.gather_output:
-                parts = [torch.empty_like(x) for _ in range(self.tp_size)]
-                dist.all_gather(parts, x, group=self.tp_group)
-                x = torch.cat(parts, dim=-1)
+            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.tp_group)  # the one exchange step of the path
         if self.bias is not None:
-            x = x + self.bias.to(x.dtype)  # outside the plugin, as plugin.py:158-160
-        return x
+            # outside the plugin, as plugin.py:158-160.  Column-parallel: the bias buffer is this rank's [N / tp] shard and
+            # belongs to this rank's output columns, so it is added BEFORE the gather (TensorRT-LLM's ColumnLinear order);
+            # row-parallel: the full [N] bias is added once, after the reduction.
+            x = x + self.bias.to(x.dtype)
+        return self._gather_columns(x)
+
+    def _gather_columns(self, x: torch.Tensor) -> torch.Tensor:
+        """column-parallel with gather_output: concatenate the ranks' output-channel shards"""
+        if self.parallel_mode != "column" or self.tp_size <= 1 or self.tp_group is None or not self.gather_output:
+            return x
+        import torch.distributed as dist
+        parts = [torch.empty_like(x) for _ in range(self.tp_size)]
+        dist.all_gather(parts, x.contiguous(), group=self.tp_group)
+        return torch.cat(parts, dim=-1)

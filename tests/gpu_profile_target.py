@@ -19,7 +19,7 @@ sb = (torch.rand(N, device=dev) * 0.002 + 1e-4).half()
 fw = (torch.randn(N, 128, device=dev) * 0.02).half()
 ind = torch.randperm(K, device=dev)[:128].int()
 out = torch.empty(M, N, dtype=torch.float16, device=dev)
-ws = torch.empty(B.workspace_size(M, N, K), dtype=torch.uint8, device=dev)
+ws = torch.empty(B.workspace_size(M, N, K, config=cfg), dtype=torch.uint8, device=dev)
 for _ in range(iters):
     B.enqueue(A, W8, sb, fw, ind, out, ws, config=cfg)
 torch.cuda.synchronize()

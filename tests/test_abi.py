@@ -96,7 +96,12 @@ def test_workspace_size(lib):
     raw = M * K + 2 * M + 256 * M                                  # A8 | scale_a | fp_A  (:406-421)
     sk = lib.mixq_decode_workspace_size(M, N)                      # + split-K scratch: fixed part + fp16 out0 of the decode tiles
     assert lib.mixq_gemm_workspace_size() < sk <= lib.mixq_gemm_workspace_size() + 2 * 512 * 12288 and sk < 48 * 2**20
-    assert raw + sk <= need <= raw + sk + 6 * 128
+    assert raw <= need <= raw + 6 * 128                            # the plugin asks TensorRT for exactly what the default path uses
+    from mixq_tensorrt_llm_b200 import binding
+    lib.mixq_workspace_size_opt.restype = ctypes.c_size_t
+    for cfg, extra in ((0, 0), (5, 0), (13, 0), (8, sk), (11, sk), (12, sk)):   # only the opt-in split-K configurations add scratch
+        got = lib.mixq_workspace_size_opt(M, N, K, ctypes.byref(binding.Options(cfg, 0)))
+        assert need + extra <= got <= need + extra + 128, (cfg, got)
     # non-decreasing in M: the size for a profile's maximum covers every smaller batch
     sizes = [lib.mixq_workspace_size(m, N, K) for m in (1, 32, 512, 1024, 1025, 4096, 65536)]
     assert sizes == sorted(sizes)

@@ -431,6 +431,88 @@ def test_enqueue_matches_oracle_and_reference_plugin(B, oracle, name, M, N, K):
         _assert_mixed_close(got, ref.cpu().numpy(), r["out0"], "enqueue vs reference kernels", mag)
 
 
+BENCH_SHAPES = [  # (act-scale fixture, M, N, K, bias): the shapes bench.py times (BASELINE.json configs[1..4]), full size
+    ("Llama-2-7b/self_attn.q_proj", 65536, 12288, 4096, False),        # configs[1]: bs 32 x seq 2048, fused qkv (1.6 GB of output)
+    ("Llama-2-7b/self_attn.q_proj", 512, 12288, 4096, False),          # configs[2]: decode bs 512
+    ("Llama-2-7b/self_attn.o_proj", 512, 4096, 4096, False),
+    ("Llama-2-7b/mlp.gate_proj", 512, 11008, 4096, False),
+    ("Llama-2-7b/mlp.down_proj", 512, 4096, 11008, False),
+    ("qwen2-7b-instruct/self_attn.q_proj", 65536, 4608, 3584, True),   # configs[3]: Qwen2 qkv carries a bias
+    ("qwen2-7b-instruct/mlp.gate_proj", 8192, 18944, 3584, False),
+    ("qwen2-7b-instruct/mlp.down_proj", 8192, 3584, 18944, False),
+    ("Llama-2-70b/self_attn.q_proj", 512, 1280, 8192, False),          # configs[4]: 70B, TP 8 shards (column: N / 8)
+    ("Llama-2-70b/self_attn.o_proj", 512, 8192, 1024, False),          #   row: K / 8
+    ("Llama-2-70b/mlp.gate_proj", 512, 3584, 8192, False),
+    ("Llama-2-70b/mlp.down_proj", 512, 8192, 3584, False),
+]
+
+
+@pytest.mark.parametrize("name,M,N,K,with_bias", BENCH_SHAPES)
+def test_benchmarked_shapes_through_enqueue(B, oracle, name, M, N, K, with_bias):
+    """mixq_enqueue at the FULL benchmarked shapes (TsinghuaMixQPlugin.cpp:518-532): quantise / extract bit-exact against the
+    reference kernels over the whole batch (byte offsets beyond 2^31 at M = 65536), the whole output against the
+    reference kernels on the GPU, and rows sampled from the first, a middle and the last 128-row block against the CPU
+    oracle -- each within the mixed-path tolerance.  Weights are packed on the device by bench.py's packer (checked against
+    the product's host packer in test_bench_host.py)."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    z = np.load(GOLD / "act_scales_l0.npz")
+    sc = z[name].astype(np.float32) if name in z.files and z[name].shape[0] == K else oracle.synth_act_scale(K, seed=7)
+    if sc.shape[0] != K:      # a TP row shard reads a K slice of the activation
+        sc = sc[:K]
+    g = torch.Generator(device=DEV).manual_seed(1234 + N + K)
+    sct = torch.from_numpy(sc).to(DEV)
+    W = (torch.randn(N, K, device=DEV, generator=g) * 0.02).half()
+    W8, sb, fw, ind = bench.pack_gpu(torch, W, sct)
+    del W
+    A = (torch.randn(M, K, device=DEV, generator=g) * (sct[None, :] / 3.0)).half()
+    bias = (torch.randn(N, device=DEV, generator=g)).half() if with_bias else None
+    out = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
+    ws = torch.empty(B.workspace_size(M, N, K), dtype=torch.uint8, device=DEV)
+    B.enqueue(A, W8, sb, fw, ind, out, ws, bias=bias)
+    torch.cuda.synchronize()
+    # stage 1 against the reference kernels, whole batch
+    if refgpu.available():
+        A8 = torch.empty(M, K, dtype=torch.int8, device=DEV)
+        sa = torch.empty(M, dtype=torch.float16, device=DEV)
+        fpA = torch.empty(M, 128, dtype=torch.float16, device=DEV)
+        B.quant_extract(A, ind, A8, sa, fpA)
+        rq, rsa = refgpu.int8quant(A)
+        assert torch.equal(rq, A8) and torch.equal(rsa.view(torch.int16), sa.view(torch.int16))
+        assert torch.equal(refgpu.extract(A, ind).view(torch.int16), fpA.view(torch.int16))
+        del rq, A8
+        ref = refgpu.enqueue(A, W8, sb, fw, ind)
+        if bias is not None:
+            ref = (ref.float() + bias.float()[None, :]).half()      # plugin.py:158-160: bias added after the plugin
+        for lo in range(0, M, 8192):                                # the bound needs M x N floats: walk row bands
+            hi = min(M, lo + 8192)
+            if bias is None:
+                ok, worst, rel = bench.mixed_close(torch, out[lo:hi], ref[lo:hi], A[lo:hi], fw, ind)
+                assert ok, (lo, worst, rel)
+            else:   # the bias add rounds once more: compare the biased outputs within one more ulp
+                d = (out[lo:hi].float() - ref[lo:hi].float()).abs()
+                ulp = torch.exp2(torch.floor(torch.log2(ref[lo:hi].float().abs().clamp_min(2.0 ** -14))) - 10)
+                fa = A[lo:hi][:, ind.long()].float()
+                o0 = (fa @ fw.float().t()).half().float().abs().clamp_min(2.0 ** -14)
+                bound = 2 * ulp + torch.exp2(torch.floor(torch.log2(o0)) - 10) + (fa.abs() @ fw.float().abs().t()) * 2.0 ** -20
+                assert bool((d <= bound).all()), float((d / bound).max())
+        del ref
+    # sampled rows against the CPU oracle
+    rows = np.unique(np.concatenate([np.arange(0, 8), np.arange(M // 2 // 128 * 128, M // 2 // 128 * 128 + 8) % M, np.arange(M - 8, M)]))
+    rt = torch.from_numpy(rows).to(DEV)
+    A_s = A[rt].cpu().numpy()
+    r = oracle.forward(A_s, W8.cpu().numpy(), sb.cpu().numpy(), fw.cpu().numpy(), ind.cpu().numpy(), return_parts=True)
+    want = r["out"] if bias is None else oracle.epilogue_ex(r["acc"], r["sa"], sb.cpu().numpy(), r["out0"], bias=bias.cpu().numpy())
+    got = out[rt].cpu().numpy()
+    if bias is None:
+        mag = np.abs(r["fp_A"]).astype(np.float64) @ np.abs(fw.cpu().numpy()).astype(np.float64).T
+        _assert_mixed_close(got, want, r["out0"], f"{name} {M}x{N}x{K} sampled rows vs oracle", mag)
+    else:
+        ulp = lambda x: np.spacing(np.abs(x).astype(np.float16)).astype(np.float32)
+        bound = 2 * ulp(want.astype(np.float32)) + ulp(r["out0"].astype(np.float32)) + ulp(r["out"].astype(np.float32))
+        assert (np.abs(got.astype(np.float32) - want.astype(np.float32)) <= bound).all()
+
+
 def test_enqueue_workspace_and_errors(B, lib, oracle):
     lin = _packed(oracle, "synthetic", 64, 256)
     A = oracle.synth_activations(16, lin["act_scale"])

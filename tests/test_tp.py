@@ -148,3 +148,43 @@ def test_qweight_shards_equal_processing_the_sharded_codes():
              for r, (k0, k1) in enumerate([(0, K // 2), (K // 2, K)])]
     ref = A.astype(np.float64) @ (codes.astype(np.float64) * scales.astype(np.float64)[None, :])
     assert np.abs(parts[0] + parts[1] - ref).max() <= 4e-3 * np.abs(ref).max() + 2e-3
+
+
+def _bias_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mixq_tensorrt_llm_b200.plugin import MixQLinear
+        N, K, M = 64, 128, 5
+        g = torch.Generator().manual_seed(7)
+        y_full = torch.randn(M, N, generator=g).half()           # stands for the plugin's column-parallel outputs
+        bias_full = torch.randn(N, generator=g).half()
+        mod = MixQLinear(K, N, bias=True, tp_group=dist.group.WORLD, tp_size=world, parallel_mode="column")
+        lo, hi = rank * (N // world), (rank + 1) * (N // world)
+        mod.bias.copy_(bias_full[lo:hi])                          # the bias buffer is this rank's [N / tp] shard
+        assert mod.bias.shape == (N // world,)
+        x = y_full[:, lo:hi] + mod.bias                           # what forward() does before the gather
+        out = mod._gather_columns(x)
+        mod.gather_output = False
+        assert mod._gather_columns(x) is x
+        if rank == 0:
+            q.put((out, (y_full + bias_full[None, :])))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_column_parallel_bias_is_added_before_the_gather():
+    """tp > 1 with bias (Qwen2 qkv): each rank adds ITS bias shard to its own output columns, then the shards are
+    gathered -- the gathered [.., N] tensor equals the unsharded linear's output + the full bias."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bias_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out, want = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out.shape == want.shape and torch.equal(out, want)
