@@ -235,3 +235,73 @@ class MixQLinear(torch.nn.Module):
         parts = [torch.empty_like(x) for _ in range(self.tp_size)]
         dist.all_gather(parts, x.contiguous(), group=self.tp_group)
         return torch.cat(parts, dim=-1)
+
+
+class MixQSrcLinear(torch.nn.Module):
+    """The reference's torch-side module, MixLinear_GEMM (MixQ/src/mixquant/modules/linear.py), 8-bit branch with
+    ``unfused=True``: weights quantised WITHOUT outlier handling at construction (:110-118, ``ind`` empty :42) and outlier
+    columns discovered at run time -- while ``add_outliers`` holds, a batch whose per-token scale exceeds sigma / 127 adds
+    the columns holding a value above sigma (:197-223).  Known outlier columns are zeroed in the activations before the
+    per-token quantisation (MIXQ_FLAG_MASK_OUTLIERS = cult.cu:1588) and their weights are the DEQUANTISED codes.
+    The device work is this library's two kernels; the growth logic is host code, as it is in the reference.
+    The kernels hold 128 outlier columns (the plugin's num_ind), so growth beyond that raises."""
+
+    def __init__(self, weight: torch.Tensor, sigma: float = 6.0, stop: int = 2, bias: Optional[torch.Tensor] = None):
+        super().__init__()
+        W = weight.detach().to(torch.float16)
+        scale = (W.abs().amax(dim=1, keepdim=True) / 127).to(torch.float16)
+        self.register_buffer("scale_col", scale.reshape(-1).contiguous())
+        self.register_buffer("q_weight", (W / scale).round().nan_to_num(0).to(torch.int8).contiguous())
+        self.register_buffer("ind", torch.zeros(0, dtype=torch.int32, device=W.device))
+        self.register_buffer("weight_cache", torch.zeros(W.shape[0], 0, dtype=torch.float16, device=W.device))
+        self.bias = bias
+        self.sigma = torch.tensor(sigma, dtype=torch.float16, device=W.device)
+        self.stop, self.cnt, self.add_outliers = stop, 0, True
+        self.out_features, self.in_features = W.shape
+
+    def _padded(self):
+        """(ind [128] int32, fp_weight [N,128]) for the kernels: unused slots repeat the first outlier column with zero weights"""
+        n = self.ind.numel()
+        ind = torch.cat([self.ind, self.ind[:1].expand(NUM_OUTLIERS - n)]).contiguous()
+        fw = torch.zeros(self.out_features, NUM_OUTLIERS, dtype=torch.float16, device=self.q_weight.device)
+        fw[:, :n] = self.weight_cache
+        return ind, fw
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        binding.require_device()
+        M = x.numel() // x.shape[-1]
+        x2 = x.reshape(M, self.in_features).to(torch.float16).contiguous()
+        dev = x2.device
+        A8 = torch.empty(M, self.in_features, dtype=torch.int8, device=dev)
+        sa = torch.empty(M, dtype=torch.float16, device=dev)
+        fpA = torch.empty(M, NUM_OUTLIERS, dtype=torch.float16, device=dev)
+
+        def stage1():
+            if self.ind.numel():
+                binding.quant_extract(x2, self._padded()[0], A8, sa, fpA, flags=binding.FLAG_MASK_OUTLIERS)
+            else:
+                binding.quant_extract(x2, None, A8, sa, None)
+        stage1()
+        if self.add_outliers:
+            if bool(sa.max() > self.sigma / 127):                       # linear.py:198
+                xm = x2.clone()
+                if self.ind.numel():
+                    xm[:, self.ind.long()] = 0
+                new = torch.unique(torch.where(xm.abs() > self.sigma)[1]).to(torch.int32)      # FindOutliers, :154-159
+                if self.ind.numel() + new.numel() > NUM_OUTLIERS:
+                    raise binding.MixQError(f"MixQSrcLinear: {self.ind.numel() + new.numel()} outlier columns; the kernels hold {NUM_OUTLIERS}")
+                w_new = (self.q_weight[:, new.long()].to(torch.float16) * self.scale_col[:, None]).to(torch.float16)   # :203-204
+                self.weight_cache = torch.cat([self.weight_cache, w_new], dim=1)
+                self.ind = torch.cat([self.ind, new])
+                stage1()                                                 # re-quantise with the new columns zeroed, :219
+            self.cnt += 1
+            if self.cnt >= self.stop or self.ind.numel() > 256:
+                self.add_outliers = False
+        out = torch.empty(M, self.out_features, dtype=torch.float16, device=dev)
+        if self.ind.numel():
+            binding.gemm_dequant(A8, self.q_weight, sa, self.scale_col, fpA, self._padded()[1], out)
+        else:
+            binding.gemm_dequant(A8, self.q_weight, sa, self.scale_col, None, None, out)
+        y = out.view(*x.shape[:-1], self.out_features)
+        return y + self.bias.to(y.dtype) if self.bias is not None else y

@@ -242,6 +242,56 @@ def gated_mlp_half(A, gate: dict, up: dict, mask: bool = False, use_table: bool 
     return (gs.astype(np.float32) * u["out"].astype(np.float32)).astype(np.float16)
 
 
+# ---- MixQ/src torch path (BASELINE.json configs[0]: "via MixQ/src torch reference"), 8-bit branch ---------------------
+def mixsrc_init(W: np.ndarray) -> dict:
+    """MixLinear_GEMM.from_linear, bit == 8 (MixQ/src/mixquant/modules/linear.py:110-118): per-output-channel scale
+    max|W| / 127 in fp16, codes round(W / scale) -- the division in fp16 like the torch call, NO outlier columns at init
+    (`ind` empty, :42) and none removed from the codes."""
+    W = np.ascontiguousarray(W, dtype=np.float16)
+    scale_col = (np.abs(W).astype(np.float32).max(axis=1) / np.float32(127)).astype(np.float16)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = np.rint((W / scale_col[:, None]).astype(np.float16).astype(np.float32))
+    q = np.nan_to_num(q, nan=0.0).astype(np.int8)
+    return dict(q_weight=q, scale_col=scale_col, ind=np.zeros((0,), dtype=np.int32), weight_cache=np.zeros((W.shape[0], 0), dtype=np.float16),
+                add_outliers=True, cnt=0)
+
+
+def mixsrc_forward(st: dict, x: np.ndarray, sigma: float = 6.0, stop: int = 2, use_table: bool = True) -> np.ndarray:
+    """MixLinear_GEMM.forward(x, cache, unfused=True), 8-bit, non-Hopper branch (linear.py:163-286), on a [M, K] fp16 batch.
+    `st` is the layer state of mixsrc_init and is UPDATED like the module (ind / weight_cache grow while add_outliers):
+      1. known outlier columns are extracted and ZEROED in the activations (ExtractOutliersAndSetToZeros, cult.cu:1588),
+      2. per-token scale max|x| / 127 and INT8 codes (FindRowScale),
+      3. while add_outliers: if any token scale exceeds sigma / 127, the columns holding a value above sigma become outliers
+         (FindOutliers, :154-159: torch.unique -> ascending), are extracted and zeroed too, their weight columns are
+         DEQUANTISED from the codes (q_weight[:, ind] * scale_col, fp16, :203-204) and the batch is re-quantised (:219);
+         growth stops after `stop` calls or beyond 256 columns (:222-224),
+      4. outlier product in fp16 with fp32 accumulation (torch.mm) and the fused dequant epilogue (int8FusedDequantize:
+         the plugin's epilogue, linear_combination_dequant.h:152-157)."""
+    x = np.array(x, dtype=np.float16, copy=True)
+    M, K = x.shape
+    acts = np.zeros((M, 0), dtype=np.float16)
+    if st["ind"].size:
+        acts = x[:, st["ind"]].copy()
+        x[:, st["ind"]] = 0
+    q, sa = quant(x, use_table=use_table)
+    if st["add_outliers"]:
+        if np.float16(sa.astype(np.float32).max()) > np.float16(np.float16(sigma) / np.float16(127)):
+            new = np.unique(np.where(np.abs(x) > np.float16(sigma))[1]).astype(np.int32)
+            a_new = x[:, new].copy()
+            x[:, new] = 0
+            w_new = (st["q_weight"][:, new].astype(np.float16) * st["scale_col"][:, None]).astype(np.float16)
+            acts = np.hstack([acts, a_new])
+            st["weight_cache"] = np.hstack([st["weight_cache"], w_new])
+            st["ind"] = np.concatenate([st["ind"], new]).astype(np.int32)
+            q, sa = quant(x, use_table=use_table)
+        st["cnt"] += 1
+        if st["cnt"] >= stop or st["ind"].size > 256:
+            st["add_outliers"] = False
+    acc = igemm(q, st["q_weight"])
+    out0 = outlier_gemm(acts, st["weight_cache"]) if st["ind"].size else None
+    return epilogue(acc, sa, st["scale_col"], out0)
+
+
 def forward_f64(A, W8, sb, fp_weight, ind, q, sa):
     """Higher-precision 'truth' for error reporting: same quantised operands, float64 math, no
     intermediate fp16 rounding of the outlier product."""

@@ -896,3 +896,39 @@ def test_module_fused_bias_equals_unfused(B, oracle):
     a, b = mod(A), mod(A, fuse_bias=True)
     torch.cuda.synchronize()
     assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+
+# ------------------------------------------------------------------ configs[0]: the MixQ/src torch path (dynamic outliers)
+@pytest.mark.parametrize("M", [1, 32])
+def test_config0_mixsrc_forward(B, oracle, M):
+    """BASELINE.json configs[0]: one 4096 x 4096 Llama-7B linear at bs = 1 "via MixQ/src torch reference": weights quantised
+    WITHOUT outlier handling (linear.py:110-118), outlier columns found at run time above sigma = 6 (:197-223), masked in the
+    activations (MIXQ_FLAG_MASK_OUTLIERS) and multiplied with the dequantised codes.  MixQSrcLinear (the product's mirror of
+    MixLinear_GEMM) against the oracle's restatement over three calls: before, while and after the outlier set grows."""
+    from mixq_tensorrt_llm_b200.plugin import MixQSrcLinear
+    N = K = 4096
+    rng = np.random.default_rng(40 + M)
+    W = (rng.standard_normal((N, K)) * 0.02).astype(np.float16)
+    sc = oracle.load_act_scales("Llama-2-7b/self_attn.q_proj")
+    st = oracle.mixsrc_init(W)
+    mod = MixQSrcLinear(_t(W))
+    assert np.array_equal(mod.q_weight.cpu().numpy(), st["q_weight"]) and np.array_equal(mod.scale_col.cpu().numpy().view(np.uint16), st["scale_col"].view(np.uint16))
+    calm = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)                     # nothing above sigma
+    # layer-0 channel statistics, scaled so that a dozen (bs 1) to a few dozen (bs 32) columns hold values above sigma = 6
+    hot = (oracle.synth_activations(M, sc, seed=77 + M).astype(np.float32) * 6).astype(np.float16)
+    hot2 = (oracle.synth_activations(M, sc, seed=99 + M).astype(np.float32) * 6).astype(np.float16)
+    for step, x in enumerate((calm, hot, hot2)):
+        want = oracle.mixsrc_forward(st, x)
+        got = mod(_t(x)).cpu().numpy()
+        assert mod.ind.cpu().numpy().tolist() == st["ind"].tolist(), step
+        assert mod.add_outliers == st["add_outliers"]
+        n = st["ind"].size
+        if n == 0:
+            assert np.array_equal(got.view(np.uint16), want.view(np.uint16)), step     # INT8 part only: bit-exact
+        else:
+            assert 0 < n <= 128
+            acts = x[:, st["ind"]]
+            out0 = oracle.outlier_gemm(acts, st["weight_cache"])
+            mag = np.abs(acts).astype(np.float64) @ np.abs(st["weight_cache"]).astype(np.float64).T
+            _assert_mixed_close(got, want, out0, f"MixQ/src forward, call {step}", mag)
+    assert st["ind"].size > 0 and not st["add_outliers"]

@@ -310,3 +310,33 @@ def test_emulated_hfma_is_the_exactly_rounded_fma(oracle):
             assert got & 0x7FFF == 0
             continue
         assert got == want, (hex(a), hex(b), hex(c), hex(got), hex(want))
+
+
+def test_mixsrc_forward_dynamic_outliers(oracle):
+    """configs[0] as BASELINE.json words it ("via MixQ/src torch reference"): weights quantised without outlier handling,
+    outlier columns discovered at run time.  Checked against an independent numpy restatement of linear.py:163-286 that
+    uses float64 for the products (the INT8 part is exact; the outlier product differs by accumulation order only)."""
+    rng = np.random.default_rng(5)
+    N, K = 64, 256
+    W = (rng.standard_normal((N, K)) * 0.02).astype(np.float16)
+    st = oracle.mixsrc_init(W)
+    assert st["ind"].size == 0 and st["q_weight"].dtype == np.int8 and np.abs(st["q_weight"]).max() <= 127
+    assert np.array_equal(st["scale_col"], (np.abs(W).astype(np.float32).max(1) / 127).astype(np.float16))
+    x1 = rng.standard_normal((3, K)).astype(np.float16)                # nothing above sigma = 6: no outliers yet
+    y1 = oracle.mixsrc_forward(st, x1)
+    assert st["ind"].size == 0 and st["cnt"] == 1 and st["add_outliers"]
+    q, sa = oracle.quant(x1)
+    assert np.array_equal(y1.view(np.uint16), oracle.epilogue(oracle.igemm(q, st["q_weight"]), sa, st["scale_col"], None).view(np.uint16))
+    x2 = rng.standard_normal((3, K)).astype(np.float16)
+    x2[0, 7], x2[2, 100], x2[1, 7] = 40.0, -25.0, 9.0                  # columns 7 and 100 exceed sigma
+    y2 = oracle.mixsrc_forward(st, x2)
+    assert st["ind"].tolist() == [7, 100] and st["weight_cache"].shape == (N, 2) and not st["add_outliers"]   # stop = 2 calls
+    assert np.array_equal(st["weight_cache"], (st["q_weight"][:, [7, 100]].astype(np.float16) * st["scale_col"][:, None]))
+    xm = x2.copy(); xm[:, [7, 100]] = 0
+    q, sa = oracle.quant(xm)
+    want = (q.astype(np.float64) @ st["q_weight"].astype(np.float64).T) * (sa.astype(np.float64)[:, None] * st["scale_col"].astype(np.float64)[None, :]) \
+        + x2[:, [7, 100]].astype(np.float64) @ st["weight_cache"].astype(np.float64).T
+    assert np.abs(y2.astype(np.float64) - want).max() <= 2e-3 * np.abs(want).max() + 1e-3
+    x3 = x2.copy(); x3[1, 33] = 50.0                                    # growth has stopped: column 33 stays in the INT8 part
+    y3 = oracle.mixsrc_forward(st, x3)
+    assert st["ind"].tolist() == [7, 100] and np.isfinite(y3.astype(np.float32)).all()
