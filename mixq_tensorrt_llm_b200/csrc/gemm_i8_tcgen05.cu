@@ -58,17 +58,23 @@ constexpr int kStashThreads = kEpilogueWarp0 * 32 + kStashEpiThreads;      // 38
 //           each CTA stages its own 128 rows of A and HALF of the W rows, the leader issues the MMAs
 //           for both, each CTA's TMEM holds its 128 accumulator rows.  Halves the shared-memory
 //           and L2 operand traffic per MAC.
-template <int CTA, int BLOCK_N, int ACC_STAGES, int STAGES>
+// A_ROWS: rows of the A box staged per K-block: 128, or 32 / 64 for a batch that small.  The tensor core still reads 128 rows
+//           (whatever follows the A box in shared memory) into accumulator rows nobody stores; the smaller stage buys a deeper
+//           ring, and a decode-sized call is bound by the weight bytes a CTA has in flight (HBM latency x bandwidth).
+template <int CTA, int BLOCK_N, int ACC_STAGES, int STAGES, int A_ROWS = 128>
 struct GemmTraits {
     static constexpr int kCta = CTA;
+    static constexpr int kARows = A_ROWS;
     static constexpr int kBlockN = BLOCK_N;            // UMMA N = output columns per tile
     static constexpr int kLoadN = BLOCK_N / CTA;       // W rows each CTA stages per K-block
     static constexpr int kTileM = kBlockM * CTA;       // output rows per tile
     static constexpr int kAccStages = ACC_STAGES;
     static constexpr int kStages = STAGES;
-    static constexpr int kABytes = kBlockM * kBlockKBytes;
+    static constexpr int kABytes = A_ROWS * kBlockKBytes;
     static constexpr int kBBytes = kLoadN * kBlockKBytes;
     static constexpr int kStageBytes = kABytes + kBBytes;
+    static_assert(A_ROWS == 128 || (CTA == 1 && (A_ROWS == 32 || A_ROWS == 64)), "short A boxes: one-CTA tiles only");
+    static_assert(kABytes % 1024 == 0, "A box must be whole 8-row swizzle groups");
     static constexpr int kAccCols = 2 * BLOCK_N;  // int32 accumulator | fp32 outlier accumulator
     static constexpr int kTmemColsRaw = kAccCols * ACC_STAGES;
     static constexpr int kTmemCols = kTmemColsRaw <= 32 ? 32 : kTmemColsRaw <= 64 ? 64 : kTmemColsRaw <= 128 ? 128
@@ -79,8 +85,10 @@ struct GemmTraits {
     static_assert(kLoadN % 8 == 0 && kBBytes % 1024 == 0, "W tile must be whole 8-row swizzle groups");
     // dynamic smem: ring | sb and bias staging (2 x 2 x BLOCK_N floats) | barriers | tmem ptr  (+1024 alignment slack)
     static constexpr int kNumBarriers = 2 * STAGES + 2 * ACC_STAGES;
+    // (+ the bytes the tensor core over-reads behind the last stage's short A box)
     static constexpr size_t kSmemBytes =
-        1024 + static_cast<size_t>(STAGES) * kStageBytes + 4 * BLOCK_N * sizeof(float) + kNumBarriers * 8 + 16;
+        1024 + static_cast<size_t>(STAGES) * kStageBytes + 4 * BLOCK_N * sizeof(float) + kNumBarriers * 8 + 16 +
+        (A_ROWS < 128 ? (128 - A_ROWS) * kBlockKBytes : 0);
     static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
@@ -1538,6 +1546,10 @@ struct KernelOf<StreamKTraits<CTA, STAGES, BLOCK_N>> {
     static auto get_ar() { return mixq_gemm_dequant_streamk_kernel<StashTraits<CTA, STAGES, BLOCK_N>, true>; }
 };
 template <class T>
+struct ARowsOf : std::integral_constant<int, kBlockM> {};
+template <int CTA, int BLOCK_N, int ACC, int STAGES, int A_ROWS>
+struct ARowsOf<GemmTraits<CTA, BLOCK_N, ACC, STAGES, A_ROWS>> : std::integral_constant<int, A_ROWS> {};
+template <class T>
 struct IsStreamK : std::false_type {};
 template <int CTA, int STAGES, int BLOCK_N>
 struct IsStreamK<StreamKTraits<CTA, STAGES, BLOCK_N>> : std::true_type {};
@@ -1550,11 +1562,12 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     const DeviceInfo& dev = device_info();
     CUtensorMap tm_a8, tm_w8, tm_fa, tm_fw;
     int rc;
-    if ((rc = make_tmap(&tm_a8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, A8, M, K, kBlockM))) return rc;
+    constexpr int a_rows = ARowsOf<T>::value;
+    if ((rc = make_tmap(&tm_a8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, A8, M, K, a_rows))) return rc;
     if ((rc = make_tmap(&tm_w8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, W8, N, K, T::kLoadN))) return rc;
     const int has_outlier = (fp_A && fp_weight) ? 1 : 0;
     if (has_outlier) {
-        if ((rc = make_tmap(&tm_fa, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_A, M, MIXQ_NUM_OUTLIERS, kBlockM))) return rc;
+        if ((rc = make_tmap(&tm_fa, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_A, M, MIXQ_NUM_OUTLIERS, a_rows))) return rc;
         if ((rc = make_tmap(&tm_fw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, fp_weight, N, MIXQ_NUM_OUTLIERS, T::kLoadN)))
             return rc;
     } else {
@@ -1975,7 +1988,13 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
             int id, tile_m, tile_n, cta;
             int64_t kb_cycles, tail_cycles;
         };
-        const Cand cands[] = {{kCfgN128x2, 128, 128, 1, 512, 3000},
+        // one row-block of tokens (M <= 128): a CTA is bound by the bytes that land in its shared memory per K-block -- the A box
+        // (32 / 64 / 128 rows, see launch_cfg) plus its W rows -- at ~48 B/clk; the 64-wide tile halves the W part and doubles the
+        // CTAs that stream weights, which pays when N / 128 tiles leave SMs idle
+        const int64_t a_rows = M <= 32 ? 32 : M <= 64 ? 64 : 128;
+        const Cand cands[] = {{kCfgN128x2, 128, 128, 1, M <= 128 ? (a_rows + 128) * 128 / 48 : 512, 3000},
+                              {kCfgN64x2, 128, 64, 1, M <= 128 ? (a_rows + 64) * 128 / 48 : 100000, 3000},
+                              {kCfgN32x2, 128, 32, 1, M <= 128 ? (a_rows + 32) * 128 / 48 : 100000, 3000},
                               {kCfg2CtaN128x2, 256, 128, 2, M <= kDecodeMaxM ? 500 : 384, 3000},
                               {kCfg2CtaN192Tma, 256, 192, 2, 436, 4500},
                               {kCfg2CtaN256Tma, 256, 256, 2, 556, 6000}};
@@ -2037,11 +2056,19 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
     }
     switch (cfg) {
         case kCfgN128x2:
+            if (M <= 32) return launch_cfg<GemmTraits<1, 128, 2, 10, 32>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
+            if (M <= 64) return launch_cfg<GemmTraits<1, 128, 2, 8, 64>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
             return launch_cfg<GemmTraits<1, 128, 2, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         case kCfgN256x1:
             return launch_cfg<GemmTraits<1, 256, 1, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         case kCfgN64x2:
+            if (M <= 32) return launch_cfg<GemmTraits<1, 64, 2, 16, 32>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
+            if (M <= 64) return launch_cfg<GemmTraits<1, 64, 2, 12, 64>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
             return launch_cfg<GemmTraits<1, 64, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
+        case kCfgN32x2:   // 128 x 32 tiles: four times the CTAs of id 1 stream weights (few output channels, one row-block of tokens)
+            if (M <= 32) return launch_cfg<GemmTraits<1, 32, 2, 24, 32>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
+            if (M <= 64) return launch_cfg<GemmTraits<1, 32, 2, 16, 64>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
+            return launch_cfg<GemmTraits<1, 32, 2, 10>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         case kCfg2CtaN256x1:
             return launch_cfg<GemmTraits<2, 256, 1, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         case kCfg2CtaN128x2:

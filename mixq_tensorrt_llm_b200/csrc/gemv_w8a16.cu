@@ -32,14 +32,20 @@ __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
     return v;
 }
 
-// four biased codes (bytes [e0, e2, e1, e3]) -> (e0 - 128, e1 - 128), (e2 - 128, e3 - 128) as fp16, exactly:
-// 0x6400 | byte is the fp16 value 1024 + byte; subtracting 1152 leaves byte - 128.
-__device__ __forceinline__ void cvt4(uint32_t w, __half2& lo, __half2& hi) {
-    const uint32_t a = __byte_perm(w, 0x64646464u, 0x5250);
-    const uint32_t b = __byte_perm(w, 0x64646464u, 0x5351);
+// Biased codes -> fp16, exactly: 0x6400 | byte is the fp16 value 1024 + byte; subtracting 1152 leaves byte - 128.
+// A stored word holds four codes of ONE channel as bytes [e0, e2, e1, e3]; the FMA chains want, for each k, the pair
+// (channel 0, channel 1) in one half2 register (one HFMA2 then advances both channels' chains).  The interleave is done on
+// the BYTES, before the conversion: two PRMTs gather (a.e0, b.e0, a.e1, b.e1) and (a.e2, b.e2, a.e3, b.e3) from the two
+// channels' words, four more widen them -- half the permutes of converting per channel and transposing the half2 values
+// afterwards, and none inside the per-token loop.  The values, and so every rounding, are unchanged.
+__device__ __forceinline__ void cvt8(uint32_t a, uint32_t b, __half2 (&out)[4]) {   // out[j] = (a.e_j - 128, b.e_j - 128)
+    const uint32_t g0 = __byte_perm(a, b, 0x6240);    // a.e0 b.e0 a.e1 b.e1
+    const uint32_t g1 = __byte_perm(a, b, 0x7351);    // a.e2 b.e2 a.e3 b.e3
+    const uint32_t h[4] = {__byte_perm(g0, 0x64646464u, 0x5140), __byte_perm(g0, 0x64646464u, 0x5342),
+                           __byte_perm(g1, 0x64646464u, 0x5140), __byte_perm(g1, 0x64646464u, 0x5342)};
     const __half2 bias = __halves2half2(__ushort_as_half(0x6480), __ushort_as_half(0x6480));
-    lo = __hsub2(*reinterpret_cast<const __half2*>(&a), bias);
-    hi = __hsub2(*reinterpret_cast<const __half2*>(&b), bias);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = __hsub2(*reinterpret_cast<const __half2*>(&h[j]), bias);
 }
 
 template <int M>
@@ -76,8 +82,7 @@ mixq_gemv_w8a16_kernel(const __half* __restrict__ in, const uint8_t* __restrict_
     int par = 0;
     for (; g < groups; g += gridDim.x, par ^= 1) {
         const int n0 = g * 4;
-        const __half2 s0 = __half2half2(scales[n0 + r]);         // channel n0 + 2*idx + r, idx = 0, 1
-        const __half2 s1 = __half2half2(scales[n0 + 2 + r]);
+        const __half2 s01 = __halves2half2(scales[n0 + r], scales[n0 + 2 + r]);   // channel n0 + 2*idx + r, idx = 0, 1
         __half2 acc[M];                                          // (.x, .y) = (idx 0, idx 1)
 #pragma unroll
         for (int m = 0; m < M; ++m) acc[m] = zero;
@@ -95,19 +100,19 @@ mixq_gemv_w8a16_kernel(const __half* __restrict__ in, const uint8_t* __restrict_
                 const int lk = (st * 2 + p) * 4096 + t * 16;
                 if (lk < total) {
                     const int kb = (lk >> 7) * 64 + (lk & 63);   // first k of this slot's 16 codes
-                    // dequantise: pair pp = i + 2 j of the stored order is k-pair 4 i + j (undoes permute_B_rows)
-                    __half2 w0[8], w1[8];
+                    // dequantise: stored word wd of a channel holds k = kb + 2 wd, + 1 (codes e0, e1) and k = kb + 8 + 2 wd, + 1
+                    // (codes e2, e3) -- this undoes permute_B_rows; wk[j] = (channel 0, channel 1) weights of k = kb + j
+                    __half2 wk[16];
                     const uint32_t a[4] = {qc[p][0].x, qc[p][0].y, qc[p][0].z, qc[p][0].w};
                     const uint32_t b[4] = {qc[p][1].x, qc[p][1].y, qc[p][1].z, qc[p][1].w};
 #pragma unroll
                     for (int wd = 0; wd < 4; ++wd) {
-                        __half2 lo, hi;
-                        cvt4(a[wd], lo, hi);                      // stored pairs 2 wd, 2 wd + 1
-                        w0[wd] = __hfma2(lo, s0, zero);           // pp = 2 wd     -> k-pair wd
-                        w0[4 + wd] = __hfma2(hi, s0, zero);       // pp = 2 wd + 1 -> k-pair 4 + wd
-                        cvt4(b[wd], lo, hi);
-                        w1[wd] = __hfma2(lo, s1, zero);
-                        w1[4 + wd] = __hfma2(hi, s1, zero);
+                        __half2 c[4];
+                        cvt8(a[wd], b[wd], c);
+                        wk[2 * wd] = __hfma2(c[0], s01, zero);
+                        wk[2 * wd + 1] = __hfma2(c[1], s01, zero);
+                        wk[8 + 2 * wd] = __hfma2(c[2], s01, zero);
+                        wk[8 + 2 * wd + 1] = __hfma2(c[3], s01, zero);
                     }
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
@@ -117,8 +122,8 @@ mixq_gemv_w8a16_kernel(const __half* __restrict__ in, const uint8_t* __restrict_
 #pragma unroll
                         for (int yy = 0; yy < 8; ++yy) {
                             const __half2 x = *reinterpret_cast<const __half2*>(&xs[yy]);
-                            acc[m] = __hfma2(__lows2half2(w0[yy], w1[yy]), __low2half2(x), acc[m]);     // k = kb + 2 yy
-                            acc[m] = __hfma2(__highs2half2(w0[yy], w1[yy]), __high2half2(x), acc[m]);   // k = kb + 2 yy + 1
+                            acc[m] = __hfma2(wk[2 * yy], __low2half2(x), acc[m]);          // k = kb + 2 yy
+                            acc[m] = __hfma2(wk[2 * yy + 1], __high2half2(x), acc[m]);     // k = kb + 2 yy + 1
                         }
                     }
                 }

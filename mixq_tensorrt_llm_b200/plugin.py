@@ -305,3 +305,35 @@ class MixQSrcLinear(torch.nn.Module):
             binding.gemm_dequant(A8, self.q_weight, sa, self.scale_col, None, None, out)
         y = out.view(*x.shape[:-1], self.out_features)
         return y + self.bias.to(y.dtype) if self.bias is not None else y
+
+
+class MixQLlamaMLP(torch.nn.Module):
+    """reference MixQ/src/mixquant/modules/fused/mlp.py:36-70 (MixLlamaMLP), over three MixQLinear modules:
+        y = down_proj( silu(gate_proj(x)) * up_proj(x) )
+    gate and up read the same activations with the same outlier columns; they run as ONE mixq_enqueue_gated call (one
+    quantise launch, one GEMM launch whose epilogue applies the SiLU and the product), then the down projection."""
+
+    def __init__(self, gate_proj: MixQLinear, down_proj: MixQLinear, up_proj: MixQLinear):
+        super().__init__()
+        if (gate_proj.in_features, gate_proj.out_features) != (up_proj.in_features, up_proj.out_features):
+            raise ValueError("gate_proj and up_proj must have the same shape")
+        if gate_proj.bias is not None or up_proj.bias is not None:
+            raise ValueError("the gated call carries no bias (Llama / Qwen2 MLPs have none)")
+        self.gate_proj_, self.down_proj_, self.up_proj_ = gate_proj, down_proj, up_proj
+        self.out_features = down_proj.out_features
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        binding.require_device()
+        g, u = self.gate_proj_, self.up_proj_
+        if not torch.equal(g.fp_ind, u.fp_ind):
+            raise binding.MixQError("MixQLlamaMLP: gate_proj and up_proj must share their outlier columns (same activation statistics)")
+        M = x.numel() // x.shape[-1]
+        x2 = x.reshape(M, g.in_features).contiguous()
+        h = torch.empty(M, g.out_features, dtype=torch.float16, device=x.device)
+        ws = _workspace(x.device, binding.gated_workspace_size(max(M, 1), g.out_features, g.in_features))
+
+        def triple(m):
+            return (m.weight.view(torch.int8).view(m.out_features, m.in_features), m.weights_scaling_factor, m.fp_weight)
+        binding.enqueue_gated(x2, triple(g), triple(u), g.fp_ind.view(torch.int32), h, ws)
+        return self.down_proj_(h.view(*x.shape[:-1], g.out_features))

@@ -4,13 +4,15 @@
 torch SDPA (library), rotary embedding is skipped, the KV window has a fixed length so that the step is one CUDA graph.
 What it does measure is the linears in context, with everything the library offers around the plugin path:
 
-  ours       RMSNorm -> outlier extract -> INT8 quantise in ONE pass (mixq_rmsnorm_quant_extract), the quantised
-             activations shared by gate and up, SiLU fused into the gate GEMM's epilogue (mixq_gemm_dequant_ex);
+  ours       RMSNorm -> outlier extract -> INT8 quantise in ONE pass (mixq_rmsnorm_quant_extract), gate and up projections
+             with SiLU and their product in ONE GEMM launch (mixq_gemm_dequant_gated);
   plugin     the same stack through the plugin contract only: torch RMSNorm, then one mixq_enqueue per linear;
   reference  torch RMSNorm, then the reference's own kernels per linear (oracle/_ref: gather, cuBLAS fp16, int8quant,
              CUTLASS GemmDequant -- 4 launches), when oracle/_ref is on the box.
 
     python tests/gpu_layer_stack.py [bs] [kv] [layers]      -> one JSON line (tokens/s = bs / median step time)
+kv defaults to 2048 (SURVEY.md 8d ii) where the KV cache fits: 2 x 32 layers x 4096 x kv x bs fp16 values are 34 GB at bs 32
+but 1.1 TB at bs 512, so larger batches get the longest window that keeps the cache under ~70 GB (256 positions at bs 512).
 """
 import json
 import sys
@@ -40,8 +42,9 @@ def make_linear(N, K, g, dev):
 
 def main():
     bs = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-    kv = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     n_layers = int(sys.argv[3]) if len(sys.argv) > 3 else 32
+    kv_fit = int(70e9 / (2 * n_layers * H * bs * 2))
+    kv = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else min(2048, max(64, 1 << (kv_fit.bit_length() - 1)))
     dev = "cuda"
     B.require_device()
     lib = B.load()
@@ -96,11 +99,9 @@ def main():
                 lin_plugin(L["o"], attention(L, pos), o)
                 x = x + o
                 B.rmsnorm_quant_extract(x, L["g2"], EPS, L["gate"]["ind"], a8, sa, fpA)
-                p = L["gate"]
-                B.gemm_dequant(a8, p["W8"], sa, p["sb"], fpA, p["fw"], gate, activation=B.ACT_SILU)
-                p = L["up"]
-                B.gemm_dequant(a8, p["W8"], sa, p["sb"], fpA, p["fw"], up)
-                lin_plugin(L["down"], gate * up, down)
+                pg, pu = L["gate"], L["up"]
+                B.gemm_dequant_gated(a8, sa, fpA, (pg["W8"], pg["sb"], pg["fw"]), (pu["W8"], pu["sb"], pu["fw"]), gate)   # silu(gate) * up
+                lin_plugin(L["down"], gate, down)
                 x = x + down
             else:
                 lin = lin_plugin if mode == "plugin" else lin_ref

@@ -251,7 +251,7 @@ GEMM_SHAPES = [(128, 128, 128), (128, 128, 256), (256, 256, 512), (1, 8, 16), (1
                (512, 256, 28672)]
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     """No outlier slab: int32 accumulation is exact, the epilogue is one fma + one rounding, so
@@ -270,7 +270,7 @@ def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     assert bad.size == 0, f"{len(bad)} mismatches, first at {bad[:5].tolist()}: got {got[tuple(bad[0])]} want {ref[tuple(bad[0])]}"
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (100, 136, 144), (300, 520, 1040), (64, 512, 4096), (512, 1024, 4096)])
 def test_gemm_dequant_with_outlier_slab(B, lib, oracle, cfg, M, N, K):
     rng = np.random.default_rng(M + N + K)
@@ -932,3 +932,21 @@ def test_config0_mixsrc_forward(B, oracle, M):
             mag = np.abs(acts).astype(np.float64) @ np.abs(st["weight_cache"]).astype(np.float64).T
             _assert_mixed_close(got, want, out0, f"MixQ/src forward, call {step}", mag)
     assert st["ind"].size > 0 and not st["add_outliers"]
+
+
+def test_llama_mlp_module(B, oracle):
+    """MixQLlamaMLP (reference fused/mlp.py:36-70) == down(silu(gate(x)) * up(x)) built from the three MixQLinear modules'
+    own forward calls, bit for bit."""
+    from mixq_tensorrt_llm_b200.plugin import MixQLinear, MixQLlamaMLP
+    H, F, M = 1024, 2752, 200
+    sc_h, sc_f = oracle.synth_act_scale(H, seed=1), oracle.synth_act_scale(F, seed=2)
+    mods = {}
+    for name, (n, k, sc, seed) in dict(gate=(F, H, sc_h, 3), up=(F, H, sc_h, 4), down=(H, F, sc_f, 5)).items():
+        lin = oracle.synth_linear(n, k, sc, seed=seed)
+        mods[name] = MixQLinear(k, n, device=DEV).load_packed(*(_t(lin[x]) for x in ("W8", "scale_b", "fp_weight", "ind")))
+    mlp = MixQLlamaMLP(mods["gate"], mods["down"], mods["up"])
+    x = _t(oracle.synth_activations(M, sc_h, seed=9)).view(2, M // 2, H)
+    y = mlp(x)
+    want = mods["down"](mods["gate"](x, activation="silu") * mods["up"](x))
+    torch.cuda.synchronize()
+    assert y.shape == (2, M // 2, H) and torch.equal(y.view(torch.int16), want.view(torch.int16))

@@ -1,8 +1,10 @@
-mkdir -p gpurun_out/prof2
-NCU="ncu --set full --clock-control none --import-source on"
-$NCU -k regex:fat -s 2 -c 1 -f -o gpurun_out/prof2/r2_fat_512x12288x4096 python tests/gpu_profile_target.py 0 512 12288 4096 4 > gpurun_out/prof2/p1.log 2>&1
-$NCU -k regex:fat -s 2 -c 1 -f -o gpurun_out/prof2/r2_gated_512x11008x4096 python tests/gpu_profile_gated.py 512 11008 4096 4 > gpurun_out/prof2/p2.log 2>&1
-$NCU -k regex:gemm_dequant -s 2 -c 1 -f -o gpurun_out/prof2/r2_cfg5_512x4096x11008 python tests/gpu_profile_target.py 0 512 4096 11008 4 > gpurun_out/prof2/p3.log 2>&1
-$NCU -k regex:quant_extract -s 2 -c 1 -f -o gpurun_out/prof2/r2_quant_512x4096 python tests/gpu_profile_target.py 0 512 12288 4096 4 > gpurun_out/prof2/p4.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 400 --csv --log-file gpurun_out/prof2/r2_bench_launches.csv python bench.py --layers 4 --steps 3 --warmup 1 --no-e2e --no-cpu --no-ref-gpu --no-parity --graph off > gpurun_out/prof2/bench_under_ncu.log 2>&1
-tail -2 gpurun_out/prof2/p*.log; ls -la gpurun_out/prof2
+mkdir -p gpurun_out/r2
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "gemm_dequant or enqueue_matches or benchmarked" 2>&1 | tail -4 > gpurun_out/r2/t13.log; cat gpurun_out/r2/t13.log
+for shp in "32 4096 4096" "32 4096 11008" "32 12288 4096" "64 4096 4096" "128 4096 11008" "32 8192 1024"; do python tests/gpu_ab.py "1,3,15,0" $shp 2>&1 | tail -5; done
+python bench.py --workload llama2-7b-linears-decode-bs32 --no-e2e --no-cpu > gpurun_out/r2/bench_bs32c.json 2> gpurun_out/r2/bench_bs32c.err; tail -2 gpurun_out/r2/bench_bs32c.err
+python -c "
+import json
+d=json.load(open('gpurun_out/r2/bench_bs32c.json'))
+print(d['value'], d['ms_per_layer'], d['tokens_per_s'], d['roofline']['frac'], d['roofline']['bound'], d['parity_checked'], d['ref_gpu']['speedup_ours'])
+for k,v in d['roofline']['per_linear'].items(): print(k, v['gemm_us'], v['quant_us'], v['floor_us'])
+"
