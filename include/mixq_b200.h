@@ -273,7 +273,8 @@ int mixq_debug_set_trace(void* dev_buf);
  * call.  Nothing in mixq_options changes a result bit.  opt == NULL (and every entry point without an `opt`
  * argument) means {0, 0}. */
 typedef struct mixq_options {
-    int gemm_config; /* 0 = pick by shape; ids are listed in DESIGN.md (tests pin every id against the oracle) */
+    int gemm_config; /* 0 = pick by shape; tile ids are listed in DESIGN.md (tests pin every id against the oracle);
+                        + 100 x s (s = 2, 4, 8) on the one-CTA ids 1 / 3 / 15 and M <= 128 splits K over a cluster of s CTAs */
     int sm_limit;    /* SMs the persistent kernels may occupy, 0 = all of the current device                    */
 } mixq_options;
 /* mixq_enqueue_ex / mixq_gemm_dequant_ws+_ex / mixq_enqueue_allreduce / mixq_gemm_dequant_allreduce with options.

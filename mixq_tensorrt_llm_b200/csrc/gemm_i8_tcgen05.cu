@@ -84,7 +84,8 @@ struct GemmTraits {
     static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
     static_assert(kLoadN % 8 == 0 && kBBytes % 1024 == 0, "W tile must be whole 8-row swizzle groups");
     // dynamic smem: ring | sb and bias staging (2 x 2 x BLOCK_N floats) | barriers | tmem ptr  (+1024 alignment slack)
-    static constexpr int kNumBarriers = 2 * STAGES + 2 * ACC_STAGES;
+    static constexpr int kMaxKSplit = 8;                                       // CTAs of a cluster that share one tile along K (CTA == 1)
+    static constexpr int kNumBarriers = 2 * STAGES + 2 * ACC_STAGES + 1 + (kMaxKSplit - 1) * 4;   // + ring_free, partial sums landed
     // (+ the bytes the tensor core over-reads behind the last stage's short A box)
     static constexpr size_t kSmemBytes =
         1024 + static_cast<size_t>(STAGES) * kStageBytes + 4 * BLOCK_N * sizeof(float) + kNumBarriers * 8 + 16 +
@@ -135,7 +136,12 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
                          const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fw,
                          const __half* __restrict__ scale_a, const __half* __restrict__ scale_b,
                          __half* __restrict__ Out, int M, int N, int K, int has_outlier, int m_tiles, int n_tiles,
-                         int group_m, EpiArgs epi) {
+                         int group_m, int ksplit, EpiArgs epi) {
+    // ksplit > 1 (one-CTA tiles, one row-block of tokens): a cluster of `ksplit` CTAs shares ONE tile, each reducing a slice of K.
+    // A decode-sized call with few tokens is bound by the number of tcgen05.mma it issues along K (~93 clk each below N = 128,
+    // whatever the tile), so the K loop is what has to be parallelised.  Rank 0 also does the outlier K-blocks and finishes the
+    // tile; the others ship the int32 partial sums of the rows that exist (32 per epilogue warp) into rank 0's idle ring with
+    // st.async, counted on mbarriers there.  Integer sums: the result is bit-identical to the unsplit kernel.
     constexpr int BLOCK_N = T::kBlockN;
     constexpr int CTA = T::kCta;
     extern __shared__ uint8_t smem_raw[];
@@ -148,15 +154,21 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
     uint64_t* empty_bar = full_bar + T::kStages;
     uint64_t* tmem_full_bar = empty_bar + T::kStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + T::kAccStages;
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty_bar + T::kAccStages);
+    uint64_t* ring_free_bar = tmem_empty_bar + T::kAccStages;   // K-split, in a sending CTA: rank 0's ring may be overwritten
+    uint64_t* part_bar = ring_free_bar + 1;                     // K-split, in rank 0: [sender 1..7][epilogue warp] partial sums landed
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(part_bar + (T::kMaxKSplit - 1) * 4);
 
     const int warp_idx = threadIdx.x >> 5;  // warp-uniform
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = (CTA == 2) ? ptx::cluster_ctarank() : 0u;
     const bool is_leader = cta_rank == 0;
-    // tiles are distributed over CTA groups (a single CTA, or a pair working on one 256-row tile)
-    const int group_id = blockIdx.x / CTA;
-    const int num_groups = gridDim.x / CTA;
+    const int ks = (CTA == 1 && ksplit > 1) ? ksplit : 1;
+    const uint32_t krank = ks > 1 ? ptx::cluster_ctarank() : 0u;   // which K slice this CTA reduces
+    if (krank) has_outlier = 0;
+    const int row_warps = min(4, (M + 31) >> 5);                  // epilogue warps that hold real token rows (K-split: one row-block)
+    // tiles are distributed over CTA groups (a single CTA, a pair working on one 256-row tile, or a K-split cluster)
+    const int group_id = blockIdx.x / (CTA * ks);
+    const int num_groups = gridDim.x / (CTA * ks);
 
     if (warp_idx == 0 && ptx::elect_one()) {
         ptx::prefetch_tensormap(&tm_a8);
@@ -175,6 +187,11 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
             ptx::mbar_init(&tmem_full_bar[i], 1);
             ptx::mbar_init(&tmem_empty_bar[i], CTA * kNumEpilogueThreads / 32);  // every epilogue warp of the group
         }
+        ptx::mbar_init(ring_free_bar, 1);
+        for (int i = 0; i < (T::kMaxKSplit - 1) * 4; ++i) ptx::mbar_init(&part_bar[i], 1);
+        if (ks > 1 && krank == 0)   // arm the landing barriers: sender sd, warp q brings 32 lanes x BLOCK_N columns x 4 bytes
+            for (int sd = 0; sd < ks - 1; ++sd)
+                for (int q = 0; q < row_warps; ++q) ptx::mbar_arrive_expect_tx(&part_bar[sd * 4 + q], 32u * BLOCK_N * 4u);
         ptx::fence_barrier_init();
     }
     if (warp_idx == 2) {
@@ -187,7 +204,7 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
         }
     }
     ptx::tc_fence_before_sync();
-    if constexpr (CTA == 2) ptx::cluster_sync(); else __syncthreads();
+    if (CTA == 2 || ks > 1) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr_s;
 
@@ -196,7 +213,13 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
     ptx::pdl_launch_dependents();   // dependents may be scheduled as our CTAs retire; they wait for this grid's completion themselves
 
     const int num_tiles = m_tiles * n_tiles;
-    const int num_kb = (K + kBlockKBytes - 1) / kBlockKBytes;
+    const int num_kb_all = (K + kBlockKBytes - 1) / kBlockKBytes;
+    // K-split: rank 0 (outlier K-blocks, finishing epilogue) gets about two K-blocks less than the others
+    const int kb_cut0 = ks > 1 ? max(1, min(num_kb_all - (ks - 1), num_kb_all / ks - 2)) : num_kb_all;
+    const int kb_first = krank == 0 ? 0 : kb_cut0 + static_cast<int>((static_cast<long long>(krank - 1) * (num_kb_all - kb_cut0)) / (ks - 1));
+    const int kb_last = krank == 0 ? kb_cut0
+                                   : kb_cut0 + static_cast<int>((static_cast<long long>(krank) * (num_kb_all - kb_cut0)) / (ks - 1));
+    const int num_kb = kb_last - kb_first;      // K-blocks of THIS CTA
     const int n_f = has_outlier ? kOutlierKBlocks : 0;
     const int num_items = n_f + num_kb;
 
@@ -216,7 +239,7 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
                     uint8_t* sB = sA + T::kABytes;
                     const CUtensorMap* ma = it < n_f ? &tm_fa : &tm_a8;
                     const CUtensorMap* mb = it < n_f ? &tm_fw : &tm_w8;
-                    const int k0 = it < n_f ? it * (kBlockKBytes / 2) : (it - n_f) * kBlockKBytes;
+                    const int k0 = it < n_f ? it * (kBlockKBytes / 2) : (kb_first + it - n_f) * kBlockKBytes;
                     if constexpr (CTA == 2) {
                         ptx::tma_load_2d_2cta(sA, ma, &full_bar[stage], k0, m0, ptx::kEvictNormal);
                         ptx::tma_load_2d_2cta(sB, mb, &full_bar[stage], k0, n0, ptx::kEvictNormal);
@@ -318,6 +341,37 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
             ptx::tc_fence_after_sync();
             const uint32_t t_i = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_stage * T::kAccCols;
             __half* out_row = Out + static_cast<size_t>(gm) * N + n0;
+            // K-split landing zone in rank 0's ring: [sender][row warp][chunk of 32 columns][16-byte vector 0..7][lane] (4 KB a chunk)
+            const uint32_t zone_q = ptx::smem_u32(ring) + static_cast<uint32_t>(quarter) * (BLOCK_N * 128u) + lane * 16u;
+            if (ks > 1 && krank != 0) {
+                // ---- sending CTA: ship the int32 partial sums of the rows that exist to rank 0
+                ptx::mbar_wait(ring_free_bar, 0);                 // rank 0's tensor core has read its whole ring
+                if (quarter < row_warps) {
+                    const uint32_t r_zone = ptx::mapa_shared(zone_q + (krank - 1u) * static_cast<uint32_t>(row_warps) * (BLOCK_N * 128u), 0u);
+                    const uint32_t r_bar = ptx::mapa_shared(ptx::smem_u32(&part_bar[(krank - 1u) * 4u + quarter]), 0u);
+#pragma unroll 1
+                    for (int c = 0; c < BLOCK_N / 32; ++c) {
+                        uint32_t vi[32];
+                        ptx::tmem_ld_32x32(t_i + c * 32, vi);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            ptx::st_async_v4(r_zone + c * 4096u + g * 512u, vi[4 * g], vi[4 * g + 1], vi[4 * g + 2], vi[4 * g + 3], r_bar);
+                    }
+                }
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc_stage]);
+                if (++acc_stage == T::kAccStages) {
+                    acc_stage = 0;
+                    acc_phase ^= 1;
+                }
+                continue;
+            }
+            if (ks > 1 && et == 0)
+                for (int r = 1; r < ks; ++r) ptx::mbar_arrive_cluster(ring_free_bar, static_cast<uint32_t>(r));   // senders may overwrite our ring
+            if (ks > 1 && quarter < row_warps)
+                for (int sd = 0; sd < ks - 1; ++sd) ptx::mbar_wait(&part_bar[sd * 4 + quarter], 0);
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 uint32_t vi[32], vf[32];
@@ -329,6 +383,16 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
                     for (int j = 0; j < 32; ++j) vf[j] = 0u;
                 }
                 ptx::tmem_ld_wait();
+                if (ks > 1 && quarter < row_warps) {
+                    for (int sd = 0; sd < ks - 1; ++sd) {
+                        const uint32_t src = zone_q + static_cast<uint32_t>(sd * row_warps) * (BLOCK_N * 128u) + c * 4096u;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            const uint4 pv = ptx::ld_shared_u4(src + g * 512u);
+                            vi[4 * g] += pv.x; vi[4 * g + 1] += pv.y; vi[4 * g + 2] += pv.z; vi[4 * g + 3] += pv.w;
+                        }
+                    }
+                }
                 uint32_t packed[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
@@ -367,7 +431,7 @@ mixq_gemm_dequant_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid
 
     // teardown
     ptx::tc_fence_before_sync();
-    if constexpr (CTA == 2) ptx::cluster_sync(); else __syncthreads();
+    if (CTA == 2 || ks > 1) ptx::cluster_sync(); else __syncthreads();
     if (warp_idx == 2) {
         if constexpr (CTA == 2) ptx::tmem_dealloc_2cta(tmem_base, T::kTmemCols);
         else ptx::tmem_dealloc(tmem_base, T::kTmemCols);
@@ -413,7 +477,7 @@ mixq_gemm_dequant_stash_kernel(const __grid_constant__ CUtensorMap tm_a8, const 
                                const __grid_constant__ CUtensorMap tm_fa, const __grid_constant__ CUtensorMap tm_fw,
                                const __half* __restrict__ scale_a, const __half* __restrict__ scale_b,
                                __half* __restrict__ Out, int M, int N, int K, int has_outlier, int m_tiles,
-                               int n_tiles, int group_m, EpiArgs epi) {
+                               int n_tiles, int group_m, int /*ksplit: plain one-CTA tiles only*/, EpiArgs epi) {
     constexpr int BLOCK_N = T::kBlockN;
     constexpr int CTA = T::kCta;
     extern __shared__ uint8_t smem_raw[];
@@ -1546,9 +1610,13 @@ struct KernelOf<StreamKTraits<CTA, STAGES, BLOCK_N>> {
     static auto get_ar() { return mixq_gemm_dequant_streamk_kernel<StashTraits<CTA, STAGES, BLOCK_N>, true>; }
 };
 template <class T>
-struct ARowsOf : std::integral_constant<int, kBlockM> {};
+struct ARowsOf : std::integral_constant<int, kBlockM> {
+    static constexpr bool plain = false;
+};
 template <int CTA, int BLOCK_N, int ACC, int STAGES, int A_ROWS>
-struct ARowsOf<GemmTraits<CTA, BLOCK_N, ACC, STAGES, A_ROWS>> : std::integral_constant<int, A_ROWS> {};
+struct ARowsOf<GemmTraits<CTA, BLOCK_N, ACC, STAGES, A_ROWS>> : std::integral_constant<int, A_ROWS> {
+    static constexpr bool plain = true;   // mixq_gemm_dequant_kernel
+};
 template <class T>
 struct IsStreamK : std::false_type {};
 template <int CTA, int STAGES, int BLOCK_N>
@@ -1558,7 +1626,7 @@ template <class T>
 int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                const void* fp_weight, void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl,
                void* sk_ws = nullptr, int stream_k = 0, const mixq_peer_group* pg = nullptr, EpiArgs epi = EpiArgs{nullptr, 0},
-               LaunchOpts opts = LaunchOpts{}) {
+               LaunchOpts opts = LaunchOpts{}, int ksplit = 1) {
     const DeviceInfo& dev = device_info();
     CUtensorMap tm_a8, tm_w8, tm_fa, tm_fw;
     int rc;
@@ -1589,6 +1657,16 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     if (num_tiles > (1ll << 30)) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: too many tiles");
     const int64_t max_groups = usable_sms(opts) / T::kCta;
     int grid = static_cast<int>(num_tiles < max_groups ? num_tiles : max_groups) * T::kCta;
+    if (ksplit > 1) {
+        // K-split (plain one-CTA tiles, one row-block of tokens): a cluster of `ksplit` CTAs per tile, every tile its own cluster
+        constexpr bool kPlain = !IsStreamK<T>::value && ARowsOf<T>::plain && T::kCta == 1;
+        const int64_t row_warps = (M + 31) / 32 < 4 ? (M + 31) / 32 : 4;
+        if (!kPlain || m_tiles != 1 || ksplit > 8 || (ksplit & (ksplit - 1)) ||
+            static_cast<int64_t>(ksplit - 1) * row_warps * T::kBlockN * 128 > static_cast<int64_t>(T::kStages) * T::kStageBytes ||
+            (K + kBlockKBytes - 1) / kBlockKBytes < 2 * ksplit)
+            return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: K-split needs a one-CTA tile configuration (ids 1, 3, 15), M <= 128, a power-of-two split <= 8 and enough K");
+        grid = static_cast<int>(num_tiles) * ksplit;
+    }
     if (IsStreamK<T>::value && sk_ws && stream_k) {
         // one equal span of (tile, K-block) units per CTA group; never more groups than units
         const int64_t units = num_tiles * ((K + kBlockKBytes - 1) / kBlockKBytes);
@@ -1609,9 +1687,9 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    if (T::kCta == 2) {
+    if (T::kCta == 2 || ksplit > 1) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.x = T::kCta == 2 ? 2 : ksplit;
         attr[na].val.clusterDim.y = 1;
         attr[na].val.clusterDim.z = 1;
         ++na;
@@ -1680,7 +1758,7 @@ int launch_cfg(const void* A8, const void* W8, const void* scale_a, const void* 
     } else {
         e = cudaLaunchKernelEx(&cfg, kern, tm_a8, tm_w8, tm_fa, tm_fw, static_cast<const __half*>(scale_a),
                                static_cast<const __half*>(scale_b), static_cast<__half*>(Out), static_cast<int>(M),
-                               static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m, epi);
+                               static_cast<int>(N), static_cast<int>(K), has_outlier, m_tiles, n_tiles, group_m, ksplit, epi);
     }
     if (e != cudaSuccess) return set_cuda_error(e, "launch gemm_dequant");
     count_launch();
@@ -1957,7 +2035,12 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
                         bool pdl, void* sk_ws, size_t sk_ws_bytes, bool sk_flags_clean, const void* bias, int act,
                         LaunchOpts opts) {
     if (M == 0 || N == 0) return MIXQ_OK;
+    // gemm_config = tile id + 100 x K-split (one-CTA tiles 1 / 3 / 15 with M <= 128: 2, 4 or 8 CTAs of a cluster share a tile along K)
+    int ksplit = opts.cfg >= 200 ? opts.cfg / 100 : 1;
+    if (opts.cfg >= 200) opts.cfg %= 100;
     if (opts.cfg < 0 || opts.cfg >= kCfgCount) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: unknown config id");
+    if (ksplit > 1 && opts.cfg != kCfgN128x2 && opts.cfg != kCfgN64x2 && opts.cfg != kCfgN32x2)
+        return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: K-split goes with the one-CTA tile ids 1, 3, 15");
     if (opts.sm_limit < 0) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: negative sm_limit");
     if (act != MIXQ_ACT_NONE && act != MIXQ_ACT_SILU) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: unknown activation");
     const EpiArgs epi{static_cast<const __half*>(bias), act};
@@ -1999,8 +2082,32 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
                               {kCfg2CtaN192Tma, 256, 192, 2, 436, 4500},
                               {kCfg2CtaN256Tma, 256, 256, 2, 556, 6000}};
         int64_t best = INT64_MAX;
+        if (M <= 128) {
+            // One row-block of tokens.  Measured: the K loop costs ~370 clk per K-block whatever the tile width (an MMA below N = 128
+            // takes a fixed ~93 clk) unless the landed bytes cost more, so the levers are CTAs and K-blocks per CTA: every
+            // (tile width, K-split) pair is priced as waves x K-blocks per CTA x cycles + tail (+ the exchange of a split).
+            const int64_t rw = (M + 31) / 32;
+            struct Small { int id, tile_n, stages; };
+            const Small smalls[] = {{kCfgN128x2, 128, M <= 32 ? 10 : M <= 64 ? 8 : 6}, {kCfgN64x2, 64, M <= 32 ? 16 : M <= 64 ? 12 : 8},
+                                    {kCfgN32x2, 32, M <= 32 ? 24 : M <= 64 ? 16 : 10}};
+            for (const Small& c : smalls)
+                for (int sp = 1; sp <= 4; sp *= 2) {      // clusters of 8 schedule badly (measured 3x slower): opt-in only
+                    const int64_t stage_bytes = (a_rows + c.tile_n) * 128;
+                    // a split pays its cluster launch and exchange (~3 us) only on a long K loop (measured: K = 11008 -3 us, K = 4096 +3 us)
+                    if (sp > 1 && ((sp - 1) * rw * c.tile_n * 128 > c.stages * stage_bytes || (nkb - kOutlierKBlocks) < 64)) continue;
+                    const int64_t ctas = ((N + c.tile_n - 1) / c.tile_n) * sp;
+                    const int64_t waves = (ctas + usable_sms(opts) - 1) / usable_sms(opts);
+                    const int64_t kb_cyc = std::max<int64_t>(370, stage_bytes / 48);
+                    const int64_t est = waves * ((nkb - kOutlierKBlocks + sp - 1) / sp + kOutlierKBlocks) * kb_cyc + 3000 + (sp > 1 ? 6000 : 0);
+                    if (est < best) {
+                        best = est;
+                        cfg = c.id;
+                        ksplit = sp;
+                    }
+                }
+        }
         for (const Cand& c : cands) {
-            if (M <= 128 && c.cta == 2) continue;
+            if (M <= 128) break;
             // decode batches (weights streamed from HBM once): every configuration is bound by the rate at which TMA lands
             // operand bytes in an SM (85-100 GB/s per SM = ~48 B/clk at the 1.97 GHz these short kernels run at,
             // tools/microbench_ingest.cu), so cycles per K-block are bytes per K-block and CTA / 48; the wide TMA-store tiles'
@@ -2056,19 +2163,19 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
     }
     switch (cfg) {
         case kCfgN128x2:
-            if (M <= 32) return launch_cfg<GemmTraits<1, 128, 2, 10, 32>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
-            if (M <= 64) return launch_cfg<GemmTraits<1, 128, 2, 8, 64>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
-            return launch_cfg<GemmTraits<1, 128, 2, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
+            if (M <= 32) return launch_cfg<GemmTraits<1, 128, 2, 10, 32>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts, ksplit);
+            if (M <= 64) return launch_cfg<GemmTraits<1, 128, 2, 8, 64>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts, ksplit);
+            return launch_cfg<GemmTraits<1, 128, 2, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts, ksplit);
         case kCfgN256x1:
             return launch_cfg<GemmTraits<1, 256, 1, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         case kCfgN64x2:
-            if (M <= 32) return launch_cfg<GemmTraits<1, 64, 2, 16, 32>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
-            if (M <= 64) return launch_cfg<GemmTraits<1, 64, 2, 12, 64>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
-            return launch_cfg<GemmTraits<1, 64, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
+            if (M <= 32) return launch_cfg<GemmTraits<1, 64, 2, 16, 32>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts, ksplit);
+            if (M <= 64) return launch_cfg<GemmTraits<1, 64, 2, 12, 64>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts, ksplit);
+            return launch_cfg<GemmTraits<1, 64, 2, 8>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts, ksplit);
         case kCfgN32x2:   // 128 x 32 tiles: four times the CTAs of id 1 stream weights (few output channels, one row-block of tokens)
-            if (M <= 32) return launch_cfg<GemmTraits<1, 32, 2, 24, 32>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
-            if (M <= 64) return launch_cfg<GemmTraits<1, 32, 2, 16, 64>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
-            return launch_cfg<GemmTraits<1, 32, 2, 10>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
+            if (M <= 32) return launch_cfg<GemmTraits<1, 32, 2, 24, 32>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts, ksplit);
+            if (M <= 64) return launch_cfg<GemmTraits<1, 32, 2, 16, 64>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts, ksplit);
+            return launch_cfg<GemmTraits<1, 32, 2, 10>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts, ksplit);
         case kCfg2CtaN256x1:
             return launch_cfg<GemmTraits<2, 256, 1, 6>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, nullptr, 0, nullptr, epi, opts);
         case kCfg2CtaN128x2:

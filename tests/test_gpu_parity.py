@@ -950,3 +950,53 @@ def test_llama_mlp_module(B, oracle):
     want = mods["down"](mods["gate"](x, activation="silu") * mods["up"](x))
     torch.cuda.synchronize()
     assert y.shape == (2, M // 2, H) and torch.equal(y.view(torch.int16), want.view(torch.int16))
+
+
+# ------------------------------------------------------------------ K-split of one-CTA tiles (one row-block of tokens)
+@pytest.mark.parametrize("M,N,K", [(32, 4096, 4096), (32, 4096, 11008), (17, 1280, 8192), (64, 8192, 1024), (100, 3584, 3584),
+                                   (128, 4096, 4096), (1, 4096, 4096), (32, 12288, 4096), (5, 264, 1040)])
+def test_small_batch_ksplit(B, lib, oracle, M, N, K):
+    """gemm_config = tile id + 100 x split: 2 / 4 / 8 CTAs of a cluster share one 128 x {128, 64, 32} tile along K and the partial
+    sums of the rows that exist cross shared memory (st.async).  int32 sums are associative: without the outlier slab the
+    output equals the oracle bit for bit, with it (and with the fused bias / SiLU epilogue) the unsplit kernel's; auto (0)
+    must agree too whatever it picks."""
+    rng = np.random.default_rng(M + N + K)
+    q = rng.integers(-127, 128, (M, K), dtype=np.int8)
+    w = rng.integers(-127, 128, (N, K), dtype=np.int8)
+    sa = (rng.random(M) * 0.05 + 1e-3).astype(np.float16)
+    sb = (rng.random(N) * 0.002 + 1e-4).astype(np.float16)
+    fpA = (rng.standard_normal((M, 128)) * 4).astype(np.float16)
+    fpW = (rng.standard_normal((N, 128)) * 0.05).astype(np.float16)
+    bias = rng.standard_normal(N).astype(np.float16)
+    tq, tw, tsa, tsb, tfa, tfw, tb = _t(q), _t(w), _t(sa), _t(sb), _t(fpA), _t(fpW), _t(bias)
+    ref = oracle.epilogue(oracle.igemm(q, w), sa, sb, None)
+    base = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    B.gemm_dequant(tq, tw, tsa, tsb, tfa, tfw, base, config=1)
+    base_b = torch.empty_like(base)
+    B.gemm_dequant(tq, tw, tsa, tsb, tfa, tfw, base_b, config=1, bias=tb, activation=B.ACT_SILU)
+    served = 0
+    for tile in (1, 3, 15):
+        for split in (2, 4, 8):
+            cfg = split * 100 + tile
+            o = torch.full((M, N), float("nan"), dtype=torch.float16, device=DEV)
+            try:
+                B.gemm_dequant(tq, tw, tsa, tsb, None, None, o, config=cfg)
+            except Exception as e:
+                assert "K-split" in str(e), e
+                continue
+            served += 1
+            torch.cuda.synchronize()
+            bad = np.argwhere(o.cpu().numpy().view(np.uint16) != ref.view(np.uint16))
+            assert bad.size == 0, f"cfg {cfg}: {len(bad)} mismatches vs oracle, first at {bad[:5].tolist()}"
+            for _ in range(2):       # back to back: barriers are single-use per launch
+                B.gemm_dequant(tq, tw, tsa, tsb, tfa, tfw, o, config=cfg)
+            torch.cuda.synchronize()
+            assert torch.equal(o.view(torch.int16), base.view(torch.int16)), f"cfg {cfg}: mixed output differs from the unsplit kernel"
+            B.gemm_dequant(tq, tw, tsa, tsb, tfa, tfw, o, config=cfg, bias=tb, activation=B.ACT_SILU)
+            torch.cuda.synchronize()
+            assert torch.equal(o.view(torch.int16), base_b.view(torch.int16)), f"cfg {cfg}: fused epilogue differs"
+    assert served >= 3, served
+    o = torch.empty_like(base)
+    B.gemm_dequant(tq, tw, tsa, tsb, tfa, tfw, o)      # auto
+    torch.cuda.synchronize()
+    assert torch.equal(o.view(torch.int16), base.view(torch.int16))
