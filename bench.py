@@ -520,9 +520,11 @@ def run_ours(args, wl):
         qu = time_kernel(lambda i: B.quant_extract(a, layers[i][idx]["ind"], a8, sa, fpA), reps)
         B.quant_extract(a, lin["ind"], a8, sa, fpA)
         if "up" in lin:
+            gscratch = torch.empty(M * Ns * 2, dtype=torch.uint8, device=dev) if M > 1024 else None   # two GEMMs + multiply above 1024 tokens
+
             def gemm(i):
                 L, U = layers[i][idx], layers[i][idx]["up"]
-                B.gemm_dequant_gated(a8, sa, fpA, (L["W8"], L["sb"], L["fw"]), (U["W8"], U["sb"], U["fw"]), o)
+                B.gemm_dequant_gated(a8, sa, fpA, (L["W8"], L["sb"], L["fw"]), (U["W8"], U["sb"], U["fw"]), o, scratch=gscratch)
         else:
             def gemm(i):
                 L = layers[i][idx]
@@ -908,14 +910,17 @@ def main():
                     help="row-parallel linears: all-reduce fused into the GEMM kernel (default) or NCCL after it")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto: decode-sized M)")
-    ap.add_argument("--mlp", default="fused", choices=["fused", "split"],
-                    help="gate and up projections: one mixq_enqueue_gated call (default) or two mixq_enqueue calls")
+    ap.add_argument("--mlp", default="auto", choices=["auto", "fused", "split"],
+                    help="gate and up projections: one mixq_enqueue_gated call (auto: decode batches, M <= 1024, where it is one GEMM "
+                         "launch) or two mixq_enqueue calls (auto: larger M, where the gated call is two GEMMs plus an elementwise pass)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
+    if args.mlp == "auto":
+        args.mlp = "fused" if wl["M"] <= 1024 else "split"
     if args.layers > 0:
         wl["layers"] = args.layers
     if args.impl == "reference":
