@@ -350,13 +350,14 @@ def make_peer_group(world: int, rank: int, out_ptrs, staging_ptrs, counter_ptrs,
 
 
 def enqueue_allreduce(A, W8, scale_b, fp_weight, ind, workspace, group: PeerGroup, flags: int = 0, stream=None,
-                      sm_limit: int = 0) -> None:
-    """mixq_enqueue_allreduce: the reduced [M,N] result lands in group.out[i] on every rank i."""
+                      sm_limit: int = 0, config: int = 0) -> None:
+    """mixq_enqueue_allreduce: the result lands in every rank's Out buffer of ``group``.  ``config=9`` keeps the one-kernel
+    path where the pull path (decode-sized result, 2 ranks) would be taken."""
     M, K = A.shape
     N = W8.shape[0]
     t = make_tensors(A, W8, scale_b, fp_weight, ind, None)
     check(load().mixq_enqueue_allreduce_opt(ctypes.byref(t), M, N, K, _ptr(workspace), workspace.numel() * workspace.element_size(),
-                                            ctypes.byref(group), _opts(0, sm_limit), flags, _stream(stream)), "mixq_enqueue_allreduce")
+                                            ctypes.byref(group), _opts(config, sm_limit), flags, _stream(stream)), "mixq_enqueue_allreduce")
 
 
 def gemm_dequant_allreduce(A8, W8, scale_a, scale_b, fp_A, fp_weight, group: PeerGroup, stream=None, sm_limit: int = 0) -> None:

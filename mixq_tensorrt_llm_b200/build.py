@@ -19,7 +19,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libmixq_b200.so"
-SOURCES = ["quant_extract.cu", "gemm_i8_tcgen05.cu", "gemv_w8a16.cu", "mixq_api.cu", "mixq_plugin.cpp", "mixq_registry.cpp"]
+SOURCES = ["quant_extract.cu", "gemm_i8_tcgen05.cu", "gemv_w8a16.cu", "allreduce_pull.cu", "mixq_api.cu", "mixq_plugin.cpp", "mixq_registry.cpp"]
 HEADERS = ["ptx.cuh", "mixq_internal.h", "mixq_plugin.h", "../../include/mixq_b200.h", "../../include/mixq/trt_shim.h"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

@@ -3,6 +3,7 @@
 // workspace carving (reference TsinghuaMixQPlugin.cpp:406-421), the two launches.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -259,9 +260,35 @@ int mixq_gemm_dequant_allreduce(const void* A8, const void* W8, const void* scal
                                 const void* fp_weight, int64_t M, int64_t N, int64_t K, const mixq_peer_group* g, void* stream) {
     return mixq_gemm_dequant_allreduce_opt(A8, W8, scale_a, scale_b, fp_A, fp_weight, M, N, K, g, nullptr, stream);
 }
+namespace {
+// Decode-sized result on few ranks: the GEMM (any tile configuration) writes this rank's partial into its staging area and a
+// small kernel pulls every rank's partial and reduces in rank order (allreduce_pull.cu) -- same arithmetic as the one-kernel
+// path, bit-identical results, ~10 us less at 2 ranks.  MIXQ_PULL_MAX_WORLD (default 2) / gemm_config 9 select the other path.
+bool use_pull(const mixq_peer_group* g, int64_t M, int64_t N, const LaunchOpts& lo) {
+    static const int max_world = [] {
+        const char* e = std::getenv("MIXQ_PULL_MAX_WORLD");
+        return e ? std::atoi(e) : 2;
+    }();
+    return g && g->world > 1 && g->world <= max_world && g->world <= MIXQ_MAX_RANKS && g->rank >= 0 && g->rank < g->world &&
+           M * N * 2 <= (8ll << 20) && static_cast<size_t>(M * N * 2) <= g->staging_bytes && lo.cfg != kCfg2CtaN256Tma;
+}
+int pull_reduce(const mixq_peer_group* g, int64_t M, int64_t N, cudaStream_t s, const LaunchOpts& lo) {
+    for (int i = 0; i < g->world; ++i)
+        if (!g->out[i] || !g->staging[i] || !g->counters[i]) return set_error(MIXQ_ERR_BAD_ARG, "enqueue_allreduce: null peer pointer");
+    return launch_allreduce_pull(g->staging, g->counters, g->out[g->rank], g->world, g->rank, static_cast<size_t>(M) * N, s, /*pdl=*/true, lo);
+}
+}  // namespace
+
 int mixq_gemm_dequant_allreduce_opt(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A,
                                     const void* fp_weight, int64_t M, int64_t N, int64_t K, const mixq_peer_group* g,
                                     const mixq_options* opt, void* stream) {
+    const LaunchOpts lo0 = make_opts(opt);
+    if (M > 0 && N > 0 && use_pull(g, M, N, lo0)) {
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const int rc = launch_gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, g->staging[g->rank], M, N, K, s, /*pdl=*/false, nullptr,
+                                           0, false, nullptr, 0, lo0);
+        return rc ? rc : pull_reduce(g, M, N, s, lo0);
+    }
     return launch_gemm_dequant_allreduce(A8, W8, scale_a, scale_b, fp_A, fp_weight, M, N, K, g,
                                          static_cast<cudaStream_t>(stream), /*pdl=*/false, make_opts(opt));
 }
@@ -288,6 +315,11 @@ int mixq_enqueue_allreduce_opt(const mixq_tensors* t, int64_t M, int64_t N, int6
     int rc = launch_quant_extract(t->A, M, K, t->ind, MIXQ_NUM_OUTLIERS, ws + c.off_a8, ws + c.off_sa, ws + c.off_fpa, flags, s,
                                   /*pdl=*/true, nullptr, 0, nullptr, 0.0f, nullptr, lo);
     if (rc) return rc;
+    if (use_pull(g, M, N, lo)) {
+        rc = launch_gemm_dequant(ws + c.off_a8, t->W8, ws + c.off_sa, t->scale_b, ws + c.off_fpa, t->fp_weight, g->staging[g->rank], M, N, K, s,
+                                 /*pdl=*/true, nullptr, 0, false, nullptr, 0, lo);
+        return rc ? rc : pull_reduce(g, M, N, s, lo);
+    }
     return launch_gemm_dequant_allreduce(ws + c.off_a8, t->W8, ws + c.off_sa, t->scale_b, ws + c.off_fpa, t->fp_weight, M, N, K, g,
                                          s, /*pdl=*/true, lo);
 }
