@@ -203,11 +203,11 @@ int mixq_gemm_dequant_ws(const void* A8, const void* W8, const void* scale_a, co
  * uses to map peer memory); index `rank` is the local buffer.  `counters` must be zeroed once after allocation and is
  * re-armed by the kernel itself.  Buffers are M/N dependent only through the two size functions.
  *
- * Decode-sized results (M*N*2 <= 8 MB) on 2 ranks take a two-launch variant of the same exchange: the GEMM (whatever tile
- * configuration `auto` picks) writes the partial into staging[rank] and a small kernel lets every rank pull all partials
- * with peer loads and reduce them in rank order (csrc/allreduce_pull.cu): the same arithmetic, bit-identical results, one
- * NVLink hop instead of two.  mixq_options.gemm_config = 9 keeps the one-kernel path; the environment variable
- * MIXQ_PULL_MAX_WORLD (default 2) moves the rank limit. */
+ * Decode-sized results take a two-launch variant of the same exchange while the bytes a rank must receive,
+ * (world-1) * M*N*2, stay within 4 MB (8 MB at 2 ranks): the GEMM (whatever tile configuration `auto` picks) writes the
+ * partial into staging[rank] and a small kernel lets every rank pull all partials with peer loads and reduce them in rank
+ * order (csrc/allreduce_pull.cu): the same arithmetic, bit-identical results, one NVLink hop instead of two.
+ * mixq_options.gemm_config = 9 keeps the one-kernel path; MIXQ_PULL_MAX_INGRESS_MB (environment) moves the limit. */
 #define MIXQ_MAX_RANKS 8
 typedef struct mixq_peer_group {
     int world, rank;

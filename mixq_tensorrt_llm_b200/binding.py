@@ -352,7 +352,7 @@ def make_peer_group(world: int, rank: int, out_ptrs, staging_ptrs, counter_ptrs,
 def enqueue_allreduce(A, W8, scale_b, fp_weight, ind, workspace, group: PeerGroup, flags: int = 0, stream=None,
                       sm_limit: int = 0, config: int = 0) -> None:
     """mixq_enqueue_allreduce: the result lands in every rank's Out buffer of ``group``.  ``config=9`` keeps the one-kernel
-    path where the pull path (decode-sized result, 2 ranks) would be taken."""
+    path where the pull path (small decode-sized results) would be taken."""
     M, K = A.shape
     N = W8.shape[0]
     t = make_tensors(A, W8, scale_b, fp_weight, ind, None)
@@ -360,11 +360,12 @@ def enqueue_allreduce(A, W8, scale_b, fp_weight, ind, workspace, group: PeerGrou
                                             ctypes.byref(group), _opts(config, sm_limit), flags, _stream(stream)), "mixq_enqueue_allreduce")
 
 
-def gemm_dequant_allreduce(A8, W8, scale_a, scale_b, fp_A, fp_weight, group: PeerGroup, stream=None, sm_limit: int = 0) -> None:
+def gemm_dequant_allreduce(A8, W8, scale_a, scale_b, fp_A, fp_weight, group: PeerGroup, stream=None, sm_limit: int = 0,
+                           config: int = 0) -> None:
     M, K = A8.shape
     N = W8.shape[0]
     check(load().mixq_gemm_dequant_allreduce_opt(_ptr(A8), _ptr(W8), _ptr(scale_a), _ptr(scale_b), _ptr(fp_A), _ptr(fp_weight),
-                                                 M, N, K, ctypes.byref(group), _opts(0, sm_limit), _stream(stream)),
+                                                 M, N, K, ctypes.byref(group), _opts(config, sm_limit), _stream(stream)),
           "mixq_gemm_dequant_allreduce")
 
 

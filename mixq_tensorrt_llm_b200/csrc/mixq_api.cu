@@ -261,16 +261,20 @@ int mixq_gemm_dequant_allreduce(const void* A8, const void* W8, const void* scal
     return mixq_gemm_dequant_allreduce_opt(A8, W8, scale_a, scale_b, fp_A, fp_weight, M, N, K, g, nullptr, stream);
 }
 namespace {
-// Decode-sized result on few ranks: the GEMM (any tile configuration) writes this rank's partial into its staging area and a
-// small kernel pulls every rank's partial and reduces in rank order (allreduce_pull.cu) -- same arithmetic as the one-kernel
-// path, bit-identical results, ~10 us less at 2 ranks.  MIXQ_PULL_MAX_WORLD (default 2) / gemm_config 9 select the other path.
+// Decode-sized result: the GEMM (any tile configuration) writes this rank's partial into its staging area and a small kernel
+// pulls every rank's partial and reduces in rank order (allreduce_pull.cu) -- same arithmetic as the one-kernel path,
+// bit-identical results.  Every rank then RECEIVES (world - 1) partials, so it pays while that ingress is small: up to 4 MB
+// (measured: 2 ranks 4 MB 1.3x faster in the graph-replayed decode step, 4 ranks 12 MB 1.2x slower, 4 ranks 0.75 MB faster),
+// 8 MB at 2 ranks (equal).  gemm_config 9 keeps the one-kernel path; MIXQ_PULL_MAX_INGRESS_MB overrides the limit.
 bool use_pull(const mixq_peer_group* g, int64_t M, int64_t N, const LaunchOpts& lo) {
-    static const int max_world = [] {
-        const char* e = std::getenv("MIXQ_PULL_MAX_WORLD");
-        return e ? std::atoi(e) : 2;
+    static const long long max_ingress = [] {
+        const char* e = std::getenv("MIXQ_PULL_MAX_INGRESS_MB");
+        return (e ? std::atoll(e) : 4ll) << 20;
     }();
-    return g && g->world > 1 && g->world <= max_world && g->world <= MIXQ_MAX_RANKS && g->rank >= 0 && g->rank < g->world &&
-           M * N * 2 <= (8ll << 20) && static_cast<size_t>(M * N * 2) <= g->staging_bytes && lo.cfg != kCfg2CtaN256Tma;
+    if (!g || g->world < 2 || g->world > MIXQ_MAX_RANKS || g->rank < 0 || g->rank >= g->world || lo.cfg == kCfg2CtaN256Tma) return false;
+    const long long bytes = static_cast<long long>(M) * N * 2;
+    if (static_cast<size_t>(bytes) > g->staging_bytes) return false;
+    return bytes * (g->world - 1) <= max_ingress || (g->world == 2 && bytes <= 2 * max_ingress);
 }
 int pull_reduce(const mixq_peer_group* g, int64_t M, int64_t N, cudaStream_t s, const LaunchOpts& lo) {
     for (int i = 0; i < g->world; ++i)

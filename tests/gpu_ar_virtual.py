@@ -33,6 +33,7 @@ def main():
     streams = [torch.cuda.Stream() for _ in range(world)]
     g = torch.Generator(device=dev).manual_seed(7)
     lim = (nsm // world) // 2 * 2
+    bulk_launches = [0]
     for it, (M, N, K) in enumerate(shapes * 2):
         Kr = K // world
         parts, args = [], []
@@ -53,23 +54,33 @@ def main():
         for r in range(1, world):
             ref = ref + parts[r].float()
         ref = ref.half()
-        for r in range(world):
-            grp = B.make_peer_group(world, r, [o.data_ptr() for o in outs], [s.data_ptr() for s in stag],
-                                    [c.data_ptr() for c in cnts], st_bytes, ct_bytes)
-            with torch.cuda.stream(streams[r]):
-                B.gemm_dequant_allreduce(*args[r], grp, stream=streams[r], sm_limit=lim)
-        torch.cuda.synchronize()
-        for r in range(world):
-            got = outs[r][: M * N].view(M, N)
-            same = torch.equal(got.view(torch.int16), ref.view(torch.int16))
-            if not same:
-                bad = (got.view(torch.int16) != ref.view(torch.int16))
-                nz = bad.nonzero()
-                print(f"MISMATCH it={it} shape={M}x{N}x{K} rank={r}: {int(bad.sum())} of {M*N}; first {nz[:4].tolist()} "
-                      f"got {got[bad][:4].tolist()} want {ref[bad][:4].tolist()}")
-                sys.exit(1)
-        for c in cnts:   # words: 0 done, 1 launch epoch, 2..3 pushed[parity]
-            assert int(c[0]) == 0 and int(c[2]) == 0 and int(c[3]) == 0 and int(c[1]) == (it + 1) % 2, "counters not re-armed"
+        # config 9 = the one-kernel path (counters re-armed by the kernel); 0 = what the library picks: small results go GEMM ->
+        # pull-reduce kernel (allreduce_pull.cu, epoch-scaled counters) -- the same rank-order fp32 sum either way
+        for cfg in (9, 0, 0):
+            for r in range(world):
+                outs[r].fill_(float("nan"))
+            torch.cuda.synchronize()
+            for r in range(world):
+                grp = B.make_peer_group(world, r, [o.data_ptr() for o in outs], [s.data_ptr() for s in stag],
+                                        [c.data_ptr() for c in cnts], st_bytes, ct_bytes)
+                with torch.cuda.stream(streams[r]):
+                    B.gemm_dequant_allreduce(*args[r], grp, stream=streams[r], sm_limit=lim, config=cfg)
+            torch.cuda.synchronize()
+            for r in range(world):
+                got = outs[r][: M * N].view(M, N)
+                same = torch.equal(got.view(torch.int16), ref.view(torch.int16))
+                if not same:
+                    bad = (got.view(torch.int16) != ref.view(torch.int16))
+                    nz = bad.nonzero()
+                    print(f"MISMATCH it={it} cfg={cfg} shape={M}x{N}x{K} rank={r}: {int(bad.sum())} of {M*N}; first {nz[:4].tolist()} "
+                          f"got {got[bad][:4].tolist()} want {ref[bad][:4].tolist()}")
+                    sys.exit(1)
+            if cfg == 9:
+                bulk_launches[0] += 1
+                for c in cnts:   # words: 0 done, 1 launch epoch, 2..3 pushed[parity]
+                    assert int(c[0]) == 0 and int(c[2]) == 0 and int(c[3]) == 0 and int(c[1]) == bulk_launches[0] % 2, "counters not re-armed"
+            for c in cnts:
+                assert int(c[4]) == 0, "a peer wait timed out"
         print(f"ok it={it} world={world} shape={M}x{N}x{K} sm_limit={lim}")
     print("PASS")
 

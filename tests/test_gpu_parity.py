@@ -655,6 +655,22 @@ def test_fused_allreduce_virtual_ranks(world):
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NVLink peer memory)")
+def test_row_parallel_allreduce_on_real_gpus():
+    """The same check over real peer memory when the box has more than one GPU (reference site: plugin.py:155-156): both
+    exchange paths against fp16(sum_r fp32(partial_r)) bit for bit on min(4, #GPUs) ranks, the MixQLinear row-parallel module
+    against plugin + NCCL, and a CUDA-graph replay (tests/gpu_tp_fused.py prints PASS)."""
+    import subprocess
+    import sys as _sys
+    n = min(4, torch.cuda.device_count())
+    n = 2 if n == 3 else n
+    r = subprocess.run([_sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(ROOT / "tests" / "gpu_tp_fused.py"), "512x4096x4096", "32x4096x4096", "2048x4096x2048"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 # ------------------------------------------------------------------ M <= 4 branch: weight-only GEMV
 def _gemv_cases():
     import sys
