@@ -266,20 +266,29 @@ namespace {
 // bit-identical results.  Every rank then RECEIVES (world - 1) partials, so it pays while that ingress is small: up to 4 MB
 // (measured: 2 ranks 4 MB 1.3x faster in the graph-replayed decode step, 4 ranks 12 MB 1.2x slower, 4 ranks 0.75 MB faster),
 // 8 MB at 2 ranks (equal).  gemm_config 9 keeps the one-kernel path; MIXQ_PULL_MAX_INGRESS_MB overrides the limit.
-bool use_pull(const mixq_peer_group* g, int64_t M, int64_t N, const LaunchOpts& lo) {
+// returns 0 = one-kernel path, 1 = one-shot pull, 2 = two-shot pull
+int use_pull(const mixq_peer_group* g, int64_t M, int64_t N, const LaunchOpts& lo) {
     static const long long max_ingress = [] {
         const char* e = std::getenv("MIXQ_PULL_MAX_INGRESS_MB");
         return (e ? std::atoll(e) : 4ll) << 20;
     }();
-    if (!g || g->world < 2 || g->world > MIXQ_MAX_RANKS || g->rank < 0 || g->rank >= g->world || lo.cfg == kCfg2CtaN256Tma) return false;
+    // two-shot pull (each rank reduces its slice, then copies the others'): bit-exact and tested, but measured slower than the
+    // one-kernel path in the graph-replayed decode step on 4 ranks (1457 vs 1873 TFLOPS), so it is opt-in: results up to
+    // MIXQ_PULL_TWO_SHOT_MAX_MB megabytes take it
+    static const long long max_two_shot = [] {
+        const char* e = std::getenv("MIXQ_PULL_TWO_SHOT_MAX_MB");
+        return (e ? std::atoll(e) : 0ll) << 20;
+    }();
+    if (!g || g->world < 2 || g->world > MIXQ_MAX_RANKS || g->rank < 0 || g->rank >= g->world || lo.cfg == kCfg2CtaN256Tma) return 0;
     const long long bytes = static_cast<long long>(M) * N * 2;
-    if (static_cast<size_t>(bytes) > g->staging_bytes) return false;
-    return bytes * (g->world - 1) <= max_ingress || (g->world == 2 && bytes <= 2 * max_ingress);
+    if (static_cast<size_t>(bytes) > g->staging_bytes) return 0;
+    if (bytes * (g->world - 1) <= max_ingress || (g->world == 2 && bytes <= 2 * max_ingress)) return 1;
+    return bytes <= max_two_shot ? 2 : 0;
 }
-int pull_reduce(const mixq_peer_group* g, int64_t M, int64_t N, cudaStream_t s, const LaunchOpts& lo) {
+int pull_reduce(const mixq_peer_group* g, int64_t M, int64_t N, int mode, cudaStream_t s, const LaunchOpts& lo) {
     for (int i = 0; i < g->world; ++i)
         if (!g->out[i] || !g->staging[i] || !g->counters[i]) return set_error(MIXQ_ERR_BAD_ARG, "enqueue_allreduce: null peer pointer");
-    return launch_allreduce_pull(g->staging, g->counters, g->out[g->rank], g->world, g->rank, static_cast<size_t>(M) * N, s, /*pdl=*/true, lo);
+    return launch_allreduce_pull(g->staging, g->counters, g->out, g->world, g->rank, static_cast<size_t>(M) * N, mode == 2, s, /*pdl=*/true, lo);
 }
 }  // namespace
 
@@ -287,11 +296,11 @@ int mixq_gemm_dequant_allreduce_opt(const void* A8, const void* W8, const void* 
                                     const void* fp_weight, int64_t M, int64_t N, int64_t K, const mixq_peer_group* g,
                                     const mixq_options* opt, void* stream) {
     const LaunchOpts lo0 = make_opts(opt);
-    if (M > 0 && N > 0 && use_pull(g, M, N, lo0)) {
+    if (const int mode = (M > 0 && N > 0) ? use_pull(g, M, N, lo0) : 0) {
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         const int rc = launch_gemm_dequant(A8, W8, scale_a, scale_b, fp_A, fp_weight, g->staging[g->rank], M, N, K, s, /*pdl=*/false, nullptr,
                                            0, false, nullptr, 0, lo0);
-        return rc ? rc : pull_reduce(g, M, N, s, lo0);
+        return rc ? rc : pull_reduce(g, M, N, mode, s, lo0);
     }
     return launch_gemm_dequant_allreduce(A8, W8, scale_a, scale_b, fp_A, fp_weight, M, N, K, g,
                                          static_cast<cudaStream_t>(stream), /*pdl=*/false, make_opts(opt));
@@ -319,10 +328,10 @@ int mixq_enqueue_allreduce_opt(const mixq_tensors* t, int64_t M, int64_t N, int6
     int rc = launch_quant_extract(t->A, M, K, t->ind, MIXQ_NUM_OUTLIERS, ws + c.off_a8, ws + c.off_sa, ws + c.off_fpa, flags, s,
                                   /*pdl=*/true, nullptr, 0, nullptr, 0.0f, nullptr, lo);
     if (rc) return rc;
-    if (use_pull(g, M, N, lo)) {
+    if (const int mode = use_pull(g, M, N, lo)) {
         rc = launch_gemm_dequant(ws + c.off_a8, t->W8, ws + c.off_sa, t->scale_b, ws + c.off_fpa, t->fp_weight, g->staging[g->rank], M, N, K, s,
                                  /*pdl=*/true, nullptr, 0, false, nullptr, 0, lo);
-        return rc ? rc : pull_reduce(g, M, N, s, lo);
+        return rc ? rc : pull_reduce(g, M, N, mode, s, lo);
     }
     return launch_gemm_dequant_allreduce(ws + c.off_a8, t->W8, ws + c.off_sa, t->scale_b, ws + c.off_fpa, t->fp_weight, M, N, K, g,
                                          s, /*pdl=*/true, lo);

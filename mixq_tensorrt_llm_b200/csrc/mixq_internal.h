@@ -63,8 +63,8 @@ int launch_gemm_dequant_allreduce(const void* A8, const void* W8, const void* sc
                                   const void* fp_A, const void* fp_weight, int64_t M, int64_t N, int64_t K,
                                   const mixq_peer_group* pg, cudaStream_t stream, bool pdl, LaunchOpts opts = LaunchOpts{});
 // decode-sized results on few ranks: every rank pulls all partials over peer loads and reduces in rank order (allreduce_pull.cu)
-int launch_allreduce_pull(void* const* partials, void* const* counters, void* out_local, int world, int rank, size_t n_elems,
-                          cudaStream_t stream, bool pdl, LaunchOpts opts = LaunchOpts{});
+int launch_allreduce_pull(void* const* partials, void* const* counters, void* const* outs, int world, int rank, size_t n_elems,
+                          bool two_shot, cudaStream_t stream, bool pdl, LaunchOpts opts = LaunchOpts{});
 size_t allreduce_staging_bytes(int64_t M, int64_t N, int world);
 size_t allreduce_counter_bytes(int64_t M, int64_t N, int world);
 int set_trace_buffer(void* dev_buf);

@@ -649,10 +649,12 @@ def test_fused_allreduce_virtual_ranks(world):
     and shapes with M/N edges.  Runs in a subprocess: a protocol bug traps that context instead of hanging pytest."""
     import subprocess
     import sys as _sys
-    r = subprocess.run([_sys.executable, str(ROOT / "tests" / "gpu_ar_virtual.py"), str(world),
-                        "512x4096x1024", "300x1000x512", "2048x4096x2048", "40x256x256"],
-                       capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    import os
+    for env in ({}, {"MIXQ_PULL_TWO_SHOT_MAX_MB": "32"}):        # default selection; then with the opt-in two-shot pull enabled
+        r = subprocess.run([_sys.executable, str(ROOT / "tests" / "gpu_ar_virtual.py"), str(world),
+                            "512x4096x1024", "300x1000x512", "2048x4096x2048", "40x256x256"],
+                           capture_output=True, text=True, timeout=300, env={**os.environ, **env})
+        assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 @pytest.mark.gpu
