@@ -1,4 +1,4 @@
-# usage: bash tools/_run_tp.sh N   (inside gpurun --gpus N)
+# usage: bash tools/run_tp_bench.sh N   (inside gpurun --gpus N)
 N=$1
 mkdir -p gpurun_out/r2
 run() { # workload tag extra
