@@ -2233,12 +2233,27 @@ int launch_gemm_dequant_gated(const void* A8, const void* scale_a, const void* f
     return MIXQ_OK;
 }
 
+// Tile of the one-kernel exchange: 256 x 256, or 256 x 128 for decode batches (twice the tiles: a 512 x 4096 result is 64 tiles
+// for the 74 CTA pairs instead of 32, and a tile's main loop is half as long).  MIXQ_AR_DECODE_TILE_N=256 restores the wide tile.
+using ArBulkT = StreamKTraits<2, 4>;
+using ArDecodeT = StreamKTraits<2, 7, 128>;
+bool ar_decode_tile(int64_t M) {
+    static const int wide = [] {
+        const char* e = std::getenv("MIXQ_AR_DECODE_TILE_N");
+        return (e && std::atoi(e) == 256) ? 1 : 0;
+    }();
+    return M <= kDecodeMaxM && !wide;
+}
 size_t allreduce_staging_bytes(int64_t M, int64_t N, int world) {
     if (M <= 0 || N <= 0 || world <= 0) return 0;
-    using T = StreamKTraits<2, 4>;
-    const int64_t tiles = ((M + T::kTileM - 1) / T::kTileM) * ((N + T::kBlockN - 1) / T::kBlockN);
-    const int64_t slots = (tiles + world - 1) / world;
-    return static_cast<size_t>(slots) * world * T::kTileM * T::kBlockN * 2;
+    size_t need = 0;
+    for (int bn : {ArBulkT::kBlockN, ArDecodeT::kBlockN}) {     // the larger of the two tilings: one allocation serves every batch
+        const int64_t tiles = ((M + ArBulkT::kTileM - 1) / ArBulkT::kTileM) * ((N + bn - 1) / bn);
+        const int64_t slots = (tiles + world - 1) / world;
+        const size_t b = static_cast<size_t>(slots) * world * ArBulkT::kTileM * bn * 2;
+        need = b > need ? b : need;
+    }
+    return need;
 }
 size_t allreduce_counter_bytes(int64_t M, int64_t N, int world) {
     (void)M; (void)N; (void)world;
@@ -2267,8 +2282,11 @@ int launch_gemm_dequant_allreduce(const void* A8, const void* W8, const void* sc
              reinterpret_cast<uintptr_t>(pg->counters[i])) & 15)
             return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant_allreduce: peer buffers must be 16-byte aligned");
     if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
-    return launch_cfg<StreamKTraits<2, 4>>(A8, W8, scale_a, scale_b, fp_A, fp_weight, pg->out[pg->rank], M, N, K, stream, pdl,
-                                           nullptr, 0, pg, EpiArgs{nullptr, 0}, opts);
+    if (ar_decode_tile(M))
+        return launch_cfg<ArDecodeT>(A8, W8, scale_a, scale_b, fp_A, fp_weight, pg->out[pg->rank], M, N, K, stream, pdl, nullptr, 0, pg,
+                                     EpiArgs{nullptr, 0}, opts);
+    return launch_cfg<ArBulkT>(A8, W8, scale_a, scale_b, fp_A, fp_weight, pg->out[pg->rank], M, N, K, stream, pdl, nullptr, 0, pg,
+                               EpiArgs{nullptr, 0}, opts);
 }
 
 }  // namespace mixq
