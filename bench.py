@@ -745,9 +745,13 @@ def run_ours(args, wl):
             h2d = sum(h.numel() * 2 for h in hA.values()) * n_layers * tp
             d2h = sum(h.numel() * 2 for h in hO.values()) * n_layers * tp
             if tp == 1:
-                scratch = torch.empty(max(B.gated_host_scratch_size(M, layers[0][grp[0]]["N"], layers[0][grp[0]]["K"]) if "up" in layers[0][grp[0]] else
-                                          B.linears_host_scratch_size(M, [layers[0][i]["N"] for i in grp], layers[0][grp[0]]["K"]) for grp in groups),
+                # twice the largest call's scratch (+ alignment): consecutive asynchronous calls alternate between the halves
+                scratch = torch.empty(2 * max(B.gated_host_scratch_size(M, layers[0][grp[0]]["N"], layers[0][grp[0]]["K"]) if "up" in layers[0][grp[0]] else
+                                              B.linears_host_scratch_size(M, [layers[0][i]["N"] for i in grp], layers[0][grp[0]]["K"]) for grp in groups) + 1024,
                                       dtype=torch.uint8, device=dev)
+                # decode-sized calls are queued (MIXQ_FLAG_HOST_ASYNC) and drained once per step: uploads, kernels and downloads
+                # of consecutive calls overlap; bulk calls pipeline their own row slabs and stay synchronous
+                hflags = B.FLAG_HOST_ASYNC if M <= 4096 else 0
 
                 def table(L):
                     return B.make_tensors(None, L["W8"], L["sb"], L["fw"], L["ind"], None)
@@ -756,50 +760,82 @@ def run_ours(args, wl):
                     for lay in layers:
                         for gi, grp in enumerate(groups):
                             if "up" in lay[grp[0]]:
-                                B.gated_host(table(lay[grp[0]]), table(lay[grp[0]]["up"]), hA[gi], hO[grp[0]], scratch, stream=stream)
+                                B.gated_host(table(lay[grp[0]]), table(lay[grp[0]]["up"]), hA[gi], hO[grp[0]], scratch, flags=hflags, stream=stream)
                             else:
-                                B.linears_host([table(lay[i]) for i in grp], hA[gi], [hO[i] for i in grp], scratch, stream=stream)
+                                B.linears_host([table(lay[i]) for i in grp], hA[gi], [hO[i] for i in grp], scratch, flags=hflags, stream=stream)
+                    if hflags:
+                        B.host_drain(stream=stream)
                 path = ("mixq_linears_host / mixq_gated_host (C ABI): pinned host A -> H2D once per distinct activation -> mixq_enqueue per "
-                        "linear (mixq_enqueue_gated for gate+up) -> D2H Out")
+                        "linear (mixq_enqueue_gated for gate+up) -> D2H Out" +
+                        ("; calls queued with MIXQ_FLAG_HOST_ASYNC and drained once per step (upload of call i+1 | kernels | download of "
+                         "call i overlap)" if hflags else ""))
             else:
+                # three streams: uploads | all-gather + kernels (the caller's stream) | downloads.  Device activations and
+                # outputs are double-buffered by layer parity, so the upload of the next call and the download of the previous
+                # one use both directions of this rank's PCIe link while the kernels run; a buffer is rewritten only after the
+                # event that says its last reader has finished.
+                n_slot = 2 if M <= 4096 else 1
                 dA = {}
                 for gi, grp in enumerate(groups):
                     lin0 = layers[0][grp[0]]
-                    dA[gi] = torch.empty(M, lin0["full_k"] if lin0["mode"] == "column" else lin0["K"], dtype=torch.float16, device=dev)
-                dO = {i: torch.empty(M, layers[0][i]["N"], dtype=torch.float16, device=dev) for grp in groups for i in grp}
+                    dA[gi] = [torch.empty(M, lin0["full_k"] if lin0["mode"] == "column" else lin0["K"], dtype=torch.float16, device=dev)
+                              for _ in range(n_slot)]
+                dO = {i: [torch.empty(M, layers[0][i]["N"], dtype=torch.float16, device=dev) for _ in range(n_slot)]
+                      for grp in groups for i in grp}
+                s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+                ev_read, ev_drained = {}, {}     # (group, slot) -> kernels have read dA;  result address -> download finished
 
                 def e2e_step():
-                    for lay in layers:
+                    cur = torch.cuda.current_stream()
+                    for li, lay in enumerate(layers):
+                        slot = li % n_slot
                         for gi, grp in enumerate(groups):
                             lin0 = lay[grp[0]]
+                            a = dA[gi][slot]
+                            rows = M // tp
+                            with torch.cuda.stream(s_up):
+                                if (gi, slot) in ev_read:
+                                    s_up.wait_event(ev_read[(gi, slot)])
+                                if lin0["mode"] == "column":
+                                    a[rank * rows:(rank + 1) * rows].copy_(hA[gi], non_blocking=True)
+                                else:
+                                    a.copy_(hA[gi], non_blocking=True)
+                                ev_up = torch.cuda.Event()
+                                ev_up.record(s_up)
+                            cur.wait_event(ev_up)
                             if lin0["mode"] == "column":
-                                rows = M // tp
-                                dA[gi][rank * rows:(rank + 1) * rows].copy_(hA[gi], non_blocking=True)
-                                dist.all_gather_into_tensor(dA[gi], dA[gi][rank * rows:(rank + 1) * rows])
-                            else:
-                                dA[gi].copy_(hA[gi], non_blocking=True)
+                                dist.all_gather_into_tensor(a, a[rank * rows:(rank + 1) * rows])
                             for i in grp:
                                 lin = lay[i]
-                                if lin["mode"] == "row" and peer is not None:
-                                    B.enqueue_allreduce(dA[gi], lin["W8"], lin["sb"], lin["fw"], lin["ind"], ws, peer.peer_group(M, lin["N"]))
-                                    res = peer.out(M, lin["N"])
+                                fused = lin["mode"] == "row" and peer is not None
+                                res = peer.out(M, lin["N"]) if fused else dO[i][slot]
+                                key = res.data_ptr()
+                                if key in ev_drained:
+                                    cur.wait_event(ev_drained[key])
+                                if fused:
+                                    B.enqueue_allreduce(a, lin["W8"], lin["sb"], lin["fw"], lin["ind"], ws, peer.peer_group(M, lin["N"]))
                                 elif "up" in lin:
-                                    B.enqueue_gated(dA[gi], (lin["W8"], lin["sb"], lin["fw"]), (lin["up"]["W8"], lin["up"]["sb"], lin["up"]["fw"]),
-                                                    lin["ind"], dO[i], ws)
-                                    res = dO[i]
+                                    B.enqueue_gated(a, (lin["W8"], lin["sb"], lin["fw"]), (lin["up"]["W8"], lin["up"]["sb"], lin["up"]["fw"]),
+                                                    lin["ind"], res, ws)
                                 else:
-                                    B.enqueue(dA[gi], lin["W8"], lin["sb"], lin["fw"], lin["ind"], dO[i], ws)
+                                    B.enqueue(a, lin["W8"], lin["sb"], lin["fw"], lin["ind"], res, ws)
                                     if lin["mode"] == "row":
-                                        dist.all_reduce(dO[i])
-                                    res = dO[i]
-                                if lin["mode"] == "row":
-                                    rows = M // tp
-                                    hO[i].copy_(res[rank * rows:(rank + 1) * rows], non_blocking=True)
-                                else:
-                                    hO[i].copy_(res, non_blocking=True)
+                                        dist.all_reduce(res)
+                                ev_done = torch.cuda.Event()
+                                ev_done.record(cur)
+                                with torch.cuda.stream(s_dn):
+                                    s_dn.wait_event(ev_done)
+                                    if lin["mode"] == "row":
+                                        hO[i].copy_(res[rank * rows:(rank + 1) * rows], non_blocking=True)
+                                    else:
+                                        hO[i].copy_(res, non_blocking=True)
+                                    ev_drained.setdefault(key, torch.cuda.Event()).record(s_dn)
+                            ev_read.setdefault((gi, slot), torch.cuda.Event()).record(cur)
+                    cur.wait_stream(s_dn)
                     torch.cuda.synchronize()
                 path = ("pinned host A -> each rank uploads 1/tp of a replicated activation, NVLink all-gather -> mixq_enqueue / "
-                        "mixq_enqueue_allreduce -> each rank downloads its shard (column) or 1/tp of the rows (row)")
+                        "mixq_enqueue_allreduce -> each rank downloads its shard (column) or 1/tp of the rows (row); uploads, kernels "
+                        "and downloads of consecutive calls overlap on three streams")
             e2e_step()
             barrier()
             t0 = time.perf_counter()

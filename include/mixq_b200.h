@@ -48,7 +48,11 @@ enum {
     MIXQ_FLAG_MASK_OUTLIERS = 1u << 0,
     /* Skip the M<=4 weight-only branch (TsinghuaMixQPlugin.cpp:472,641-647) and
      * run the mixed W8A8O16 path for every M (also what happens when q_weight is NULL). */
-    MIXQ_FLAG_FORCE_MIXED = 1u << 1
+    MIXQ_FLAG_FORCE_MIXED = 1u << 1,
+    /* Host-buffer calls only (mixq_linear_host, mixq_linears_host, mixq_gated_host): enqueue the upload, the kernels
+     * and the download and return without waiting.  A_host must stay untouched and Out_host is not valid until
+     * mixq_host_drain returns.  See mixq_host_drain. */
+    MIXQ_FLAG_HOST_ASYNC = 1u << 8
 };
 
 /* The seven plugin inputs + one output, in the order of plugin.py:142-150 /
@@ -263,6 +267,17 @@ size_t mixq_gated_host_scratch_size(int64_t M, int64_t N, int64_t K);
 int mixq_gated_host(const mixq_tensors* gate, const mixq_tensors* up, const void* A_host, void* Out_host,
                     int64_t M, int64_t N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes,
                     unsigned flags, void* stream);
+
+/* Pipelined use of the host-buffer calls.  A decode step is a chain of small linears (4 MB in, 4-12 MB out each): run one
+ * at a time, PCIe carries the upload, then idles during the kernels, then carries the download.  With
+ * MIXQ_FLAG_HOST_ASYNC the calls of one thread queue up behind one another instead: the upload of call i+1 and the download
+ * of call i use the link's two directions at once and the kernels of call i+1 start as soon as their operands are resident.
+ * If `dev_scratch` holds TWICE the size the *_scratch_size function reports, consecutive calls alternate between its halves
+ * and no call waits for the previous one's download; with the plain size call i+1's kernels wait until call i's results
+ * have left the device.  The same `dev_scratch` may be passed to every call of a sequence (calls of different shapes
+ * included: size it for the largest).  mixq_host_drain makes `stream` wait for everything those calls queued, synchronises
+ * it and closes the sequence; a call without the flag drains first by itself.  State is per calling thread. */
+int mixq_host_drain(void* stream);
 
 /* Kernel launches issued by this library since load (all threads); bench.py
  * reads it to fill `gpu_launches`. */

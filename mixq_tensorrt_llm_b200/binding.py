@@ -15,13 +15,14 @@ LIB_PATH = PKG / "libmixq_b200.so"
 NUM_OUTLIERS = 128
 FLAG_MASK_OUTLIERS = 1
 FLAG_FORCE_MIXED = 2
+FLAG_HOST_ASYNC = 1 << 8
 
 # every symbol include/mixq_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "mixq_version", "mixq_last_error", "mixq_device_ok", "mixq_workspace_size", "mixq_workspace_size_opt", "mixq_enqueue", "mixq_enqueue_ex",
     "mixq_gemm_dequant_ex", "mixq_gated_workspace_size", "mixq_enqueue_gated", "mixq_gemm_dequant_gated",
     "mixq_quant_extract", "mixq_rmsnorm_quant_extract", "mixq_gemv_w8a16", "mixq_gemm_dequant", "mixq_gemm_dequant_ws", "mixq_gemm_workspace_size",
-    "mixq_host_scratch_size", "mixq_linear_host", "mixq_linears_host_scratch_size", "mixq_linears_host", "mixq_gated_host_scratch_size", "mixq_gated_host",
+    "mixq_host_scratch_size", "mixq_linear_host", "mixq_linears_host_scratch_size", "mixq_linears_host", "mixq_gated_host_scratch_size", "mixq_gated_host", "mixq_host_drain",
     "mixq_allreduce_staging_size", "mixq_allreduce_counter_size", "mixq_allreduce_check", "mixq_enqueue_allreduce", "mixq_gemm_dequant_allreduce",
     "mixq_enqueue_opt", "mixq_gemm_dequant_opt", "mixq_enqueue_allreduce_opt", "mixq_gemm_dequant_allreduce_opt",
     "mixq_decode_workspace_size",
@@ -120,6 +121,8 @@ def load() -> ctypes.CDLL:
     L.mixq_linears_host.restype = ci
     L.mixq_linears_host.argtypes = [ctypes.POINTER(ctypes.POINTER(Tensors)), ci, vp, ctypes.POINTER(vp), i64, ctypes.POINTER(i64), i64,
                                     vp, sz, u32, vp]
+    L.mixq_host_drain.restype = ci
+    L.mixq_host_drain.argtypes = [vp]
     L.mixq_gated_host_scratch_size.restype = sz
     L.mixq_gated_host_scratch_size.argtypes = [i64, i64, i64]
     L.mixq_gated_host.restype = ci
@@ -326,6 +329,11 @@ def gated_host(gate_table, up_table, A_host, out_host, dev_scratch, flags: int =
     check(load().mixq_gated_host(ctypes.byref(gate_table), ctypes.byref(up_table), ctypes.c_void_p(A_host.data_ptr()),
                                  ctypes.c_void_p(out_host.data_ptr()), M, out_host.shape[-1], K, _ptr(dev_scratch),
                                  dev_scratch.numel() * dev_scratch.element_size(), flags, _stream(stream)), "mixq_gated_host")
+
+
+def host_drain(stream=None) -> None:
+    """mixq_host_drain: wait for every host-buffer call issued with FLAG_HOST_ASYNC by this thread."""
+    check(load().mixq_host_drain(_stream(stream)), "mixq_host_drain")
 
 
 def gated_host_scratch_size(M: int, N: int, K: int) -> int:

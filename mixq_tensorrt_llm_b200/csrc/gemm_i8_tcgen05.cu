@@ -97,14 +97,18 @@ struct TileCoord {
     int m_blk, n_blk;
 };
 // Grouped rasterisation: tiles are walked in bands of `group_m` row-blocks, M fastest inside a
-// band, so the CTAs of one wave share a few A row-blocks and a few W row-blocks in L2.
+// band, so the CTAs of one wave share a few A row-blocks and a few W row-blocks in L2.  Odd bands walk the
+// column tiles backwards: the weights a band touched last are the ones the next band starts with, so the part of W
+// that is still in L2 is re-used instead of being re-streamed from HBM (W alone does not fit beside a band's A and
+// results when N x K is tens of MB).
 __device__ __forceinline__ TileCoord tile_coord(int tile, int m_tiles, int n_tiles, int group_m) {
     const int per_group = group_m * n_tiles;
     const int g = tile / per_group;
     const int first_m = g * group_m;
     const int gsz = min(m_tiles - first_m, group_m);
     const int r = tile - g * per_group;
-    return {first_m + r % gsz, r / gsz};
+    const int n = r / gsz;
+    return {first_m + r % gsz, (g & 1) ? n_tiles - 1 - n : n};
 }
 
 // Optional fused epilogue: activation in fp32 BEFORE the output rounding, as the reference's

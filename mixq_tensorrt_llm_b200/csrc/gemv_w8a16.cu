@@ -9,11 +9,13 @@
 // The reference accumulates in fp16 per thread and in fp32 across threads, so its rounding sequence is part of
 // the result.  This kernel keeps that sequence -- which code goes through which fp16 FMA chain, the xor-16/8/2/1
 // butterfly, the warp-ordered final sum -- and is bit-identical to the reference kernel (tests/golden/
-// ref_gemv_b200.npz); everything else is laid out for an HBM-bound stream on B200: a CTA of 256 threads owns four
-// output channels at a time (= two contiguous rows of 2K bytes of the interleaved layout), CTAs are persistent
-// (3 per SM) and stride over the channel groups, the 16-byte streaming weight loads (no L1 allocation) of the next
-// step -- of the next group, at a group's end -- are in flight while the current ones go through the FMA chains,
-// activations come through the read-only path and stay in L1.
+// ref_gemv_b200.npz).  What is left to choose is how the bytes reach the SM, and on B200 the measured answer is
+// occupancy (profiles/r2_gemv_variants.txt): one CTA of 256 threads per group of four output channels (= two contiguous
+// rows of 2K bytes of the interleaved layout), 16-byte streaming loads with no L1 allocation, as few registers as the
+// chains allow (32 at M = 1: eight CTAs per SM, 64 KB of loads in flight per SM) and the hardware CTA scheduler for the
+// tail; activations come through the read-only path and stay in L1.  Persistent CTAs with a register prefetch, a
+// statically balanced grid and a shared-memory ring fed by bulk asynchronous copies were all measured slower.  The
+// dequantisation interleaves the two channels on the code BYTES (half the permutes of the reference's converter).
 // Bytes per call: N*K (weights) + 2*M*K (activations, L2-resident) + 2*M*N; HBM roofline.
 #include <cuda_fp16.h>
 
@@ -48,124 +50,79 @@ __device__ __forceinline__ void cvt8(uint32_t a, uint32_t b, __half2 (&out)[4]) 
     for (int j = 0; j < 4; ++j) out[j] = __hsub2(*reinterpret_cast<const __half2*>(&h[j]), bias);
 }
 
-template <int M>
-__global__ void __launch_bounds__(kGemvThreads, (M == 1 ? 4 : 3))
+// One group of four output channels per CTA; OCC = CTAs per SM the register budget is held to.
+template <int M, int OCC>
+__global__ void __launch_bounds__(kGemvThreads, OCC)
 mixq_gemv_w8a16_kernel(const __half* __restrict__ in, const uint8_t* __restrict__ qweight,
-                       const __half* __restrict__ scales, __half* __restrict__ out, int N, int K, int groups,
-                       const __half* __restrict__ bias, int act) {
-    // Persistent CTAs stride over the groups of four output channels.  The weights of step s+1 (two 4 KB passes over
-    // the group's two interleaved rows, possibly of the NEXT group) are in flight while step s is being multiplied.
-    __shared__ float sm[2][kGemvThreads / 32][M * 4];
+                              const __half* __restrict__ scales, __half* __restrict__ out, int N, int K,
+                              const __half* __restrict__ bias, int act) {
+    __shared__ float sm[kGemvThreads / 32][M * 4];
     const int t = threadIdx.x;
-    const int r = (t >> 2) & 1;                                  // which channel of an interleaved pair this slot reads
+    const int r = (t >> 2) & 1;
     const int total = 2 * K;
-    const int passes = (total + 4095) >> 12;
-    const int steps = (passes + 1) >> 1;
+    const int n0 = blockIdx.x * 4;
+    const uint8_t* qw = qweight + static_cast<size_t>(blockIdx.x) * 4 * K + t * 16;
     const __half2 zero = __float2half2_rn(0.0f);
-
-    auto load_step = [&](int g, int st, uint4 (&q)[2][2]) {
-        const uint8_t* qw = qweight + static_cast<size_t>(g) * 4 * K;   // (4 g / 2) rows of 2K bytes
+    const __half2 s01 = __halves2half2(scales[n0 + r], scales[n0 + 2 + r]);
+    __half2 acc[M];
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const int lk = (st * 2 + p) * 4096 + t * 16;
-            if (lk < total) {
-                q[p][0] = ld_stream_v4(qw + lk);
-                q[p][1] = ld_stream_v4(qw + total + lk);
-            }
+    for (int m = 0; m < M; ++m) acc[m] = zero;
+#pragma unroll 1
+    for (int lk = t * 16; lk < total; lk += 4096, qw += 4096) {
+        const uint4 qa = ld_stream_v4(qw), qb = ld_stream_v4(qw + total);
+        const int kb = (lk >> 7) * 64 + (lk & 63);
+        __half2 wk[16];
+        const uint32_t a[4] = {qa.x, qa.y, qa.z, qa.w};
+        const uint32_t b[4] = {qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+        for (int wd = 0; wd < 4; ++wd) {
+            __half2 c[4];
+            cvt8(a[wd], b[wd], c);
+            wk[2 * wd] = __hfma2(c[0], s01, zero);
+            wk[2 * wd + 1] = __hfma2(c[1], s01, zero);
+            wk[8 + 2 * wd] = __hfma2(c[2], s01, zero);
+            wk[8 + 2 * wd + 1] = __hfma2(c[3], s01, zero);
         }
-    };
-
-    int g = blockIdx.x;
-    if (g >= groups) return;
-    uint4 qc[2][2], qn[2][2];
-    load_step(g, 0, qc);
-    int par = 0;
-    for (; g < groups; g += gridDim.x, par ^= 1) {
-        const int n0 = g * 4;
-        const __half2 s01 = __halves2half2(scales[n0 + r], scales[n0 + 2 + r]);   // channel n0 + 2*idx + r, idx = 0, 1
-        __half2 acc[M];                                          // (.x, .y) = (idx 0, idx 1)
-#pragma unroll
-        for (int m = 0; m < M; ++m) acc[m] = zero;
-        for (int st = 0; st < steps; ++st) {
-            {
-                int ng = g, nst = st + 1;
-                if (nst == steps) {
-                    ng = g + gridDim.x;
-                    nst = 0;
-                }
-                if (ng < groups) load_step(ng, nst, qn);
-            }
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                const int lk = (st * 2 + p) * 4096 + t * 16;
-                if (lk < total) {
-                    const int kb = (lk >> 7) * 64 + (lk & 63);   // first k of this slot's 16 codes
-                    // dequantise: stored word wd of a channel holds k = kb + 2 wd, + 1 (codes e0, e1) and k = kb + 8 + 2 wd, + 1
-                    // (codes e2, e3) -- this undoes permute_B_rows; wk[j] = (channel 0, channel 1) weights of k = kb + j
-                    __half2 wk[16];
-                    const uint32_t a[4] = {qc[p][0].x, qc[p][0].y, qc[p][0].z, qc[p][0].w};
-                    const uint32_t b[4] = {qc[p][1].x, qc[p][1].y, qc[p][1].z, qc[p][1].w};
-#pragma unroll
-                    for (int wd = 0; wd < 4; ++wd) {
-                        __half2 c[4];
-                        cvt8(a[wd], b[wd], c);
-                        wk[2 * wd] = __hfma2(c[0], s01, zero);
-                        wk[2 * wd + 1] = __hfma2(c[1], s01, zero);
-                        wk[8 + 2 * wd] = __hfma2(c[2], s01, zero);
-                        wk[8 + 2 * wd + 1] = __hfma2(c[3], s01, zero);
-                    }
-#pragma unroll
-                    for (int m = 0; m < M; ++m) {
-                        const uint4* ap = reinterpret_cast<const uint4*>(in + static_cast<size_t>(m) * K + kb);
-                        const uint4 x0 = __ldg(ap), x1 = __ldg(ap + 1);
-                        const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-                        for (int yy = 0; yy < 8; ++yy) {
-                            const __half2 x = *reinterpret_cast<const __half2*>(&xs[yy]);
-                            acc[m] = __hfma2(wk[2 * yy], __low2half2(x), acc[m]);          // k = kb + 2 yy
-                            acc[m] = __hfma2(wk[2 * yy + 1], __high2half2(x), acc[m]);     // k = kb + 2 yy + 1
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {
-                qc[p][0] = qn[p][0];
-                qc[p][1] = qn[p][1];
-            }
-        }
-
-        // fp32 across slots: butterfly inside the warp (never crosses bit 2 = r), then the 8 warps in order
-        float res[M * 2];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            res[m * 2] = __low2float(acc[m]);
-            res[m * 2 + 1] = __high2float(acc[m]);
-        }
+            const uint4* ap = reinterpret_cast<const uint4*>(in + static_cast<size_t>(m) * K + kb);
+            const uint4 x0 = __ldg(ap), x1 = __ldg(ap + 1);
+            const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-        for (int i = 0; i < M * 2; ++i) {
-            res[i] += __shfl_xor_sync(0xffffffffu, res[i], 16);
-            res[i] += __shfl_xor_sync(0xffffffffu, res[i], 8);
-            res[i] += __shfl_xor_sync(0xffffffffu, res[i], 2);
-            res[i] += __shfl_xor_sync(0xffffffffu, res[i], 1);
+            for (int yy = 0; yy < 8; ++yy) {
+                const __half2 x = *reinterpret_cast<const __half2*>(&xs[yy]);
+                acc[m] = __hfma2(wk[2 * yy], __low2half2(x), acc[m]);
+                acc[m] = __hfma2(wk[2 * yy + 1], __high2half2(x), acc[m]);
+            }
         }
-        const int warp = t >> 5, lane = t & 31;
-        if (lane == 0 || lane == 4) {
+    }
+    float res[M * 2];
 #pragma unroll
-            for (int i = 0; i < M * 2; ++i) sm[par][warp][i * 2 + (lane >> 2)] = res[i];
-        }
-        __syncthreads();   // sm[par] is rewritten two groups later, after the next group's barrier
-        if (t < M * 4) {
-            float v = 0.0f;
+    for (int m = 0; m < M; ++m) {
+        res[m * 2] = __low2float(acc[m]);
+        res[m * 2 + 1] = __high2float(acc[m]);
+    }
 #pragma unroll
-            for (int j = 0; j < kGemvThreads / 32; ++j) v += sm[par][j][t];
-            // optional fused epilogue, same convention as the GEMM kernels: activation in fp32 before the rounding,
-            // bias added to the fp16 result
-            if (act == MIXQ_ACT_SILU) v = __fdividef(v, 1.0f + __expf(-v));
-            __half h = __float2half_rn(v);
-            if (bias) h = __float2half_rn(__half2float(h) + __half2float(bias[n0 + (t & 3)]));
-            out[static_cast<size_t>(t >> 2) * N + n0 + (t & 3)] = h;
-        }
+    for (int i = 0; i < M * 2; ++i) {
+        res[i] += __shfl_xor_sync(0xffffffffu, res[i], 16);
+        res[i] += __shfl_xor_sync(0xffffffffu, res[i], 8);
+        res[i] += __shfl_xor_sync(0xffffffffu, res[i], 2);
+        res[i] += __shfl_xor_sync(0xffffffffu, res[i], 1);
+    }
+    const int warp = t >> 5, lane = t & 31;
+    if (lane == 0 || lane == 4) {
+#pragma unroll
+        for (int i = 0; i < M * 2; ++i) sm[warp][i * 2 + (lane >> 2)] = res[i];
+    }
+    __syncthreads();
+    if (t < M * 4) {
+        float v = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kGemvThreads / 32; ++j) v += sm[j][t];
+        if (act == MIXQ_ACT_SILU) v = __fdividef(v, 1.0f + __expf(-v));
+        __half h = __float2half_rn(v);
+        if (bias) h = __float2half_rn(__half2float(h) + __half2float(bias[n0 + (t & 3)]));
+        out[static_cast<size_t>(t >> 2) * N + n0 + (t & 3)] = h;
     }
 }
 
@@ -183,19 +140,18 @@ int launch_gemv_w8a16(const void* A, const void* q_weight, const void* scales, v
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(q_weight)) & 15)
         return set_error(MIXQ_ERR_BAD_ARG, "gemv_w8a16: A and q_weight must be 16-byte aligned");
     if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
-    const int groups = static_cast<int>(N / 4);
-    const int max_ctas = device_info().num_sms * (M == 1 ? 4 : 3);   // persistent: 3-4 CTAs of 256 threads per SM
-    const dim3 grid(static_cast<unsigned>(groups < max_ctas ? groups : max_ctas)), block(kGemvThreads);
+    const dim3 grid(static_cast<unsigned>(N / 4)), block(kGemvThreads);
     const __half* a = static_cast<const __half*>(A);
     const uint8_t* q = static_cast<const uint8_t*>(q_weight);
     const __half* s = static_cast<const __half*>(scales);
+    const __half* b = static_cast<const __half*>(bias);
     __half* o = static_cast<__half*>(Out);
     const int n = static_cast<int>(N), k = static_cast<int>(K);
-    switch (M) {
-        case 1: mixq_gemv_w8a16_kernel<1><<<grid, block, 0, stream>>>(a, q, s, o, n, k, groups, static_cast<const __half*>(bias), act); break;
-        case 2: mixq_gemv_w8a16_kernel<2><<<grid, block, 0, stream>>>(a, q, s, o, n, k, groups, static_cast<const __half*>(bias), act); break;
-        case 3: mixq_gemv_w8a16_kernel<3><<<grid, block, 0, stream>>>(a, q, s, o, n, k, groups, static_cast<const __half*>(bias), act); break;
-        default: mixq_gemv_w8a16_kernel<4><<<grid, block, 0, stream>>>(a, q, s, o, n, k, groups, static_cast<const __half*>(bias), act); break;
+    switch (M) {   // CTAs per SM: measured best of 4 / 6 / 8 for each batch (the fp16 chains of M tokens need M-dependent registers)
+        case 1: mixq_gemv_w8a16_kernel<1, 8><<<grid, block, 0, stream>>>(a, q, s, o, n, k, b, act); break;
+        case 2: mixq_gemv_w8a16_kernel<2, 6><<<grid, block, 0, stream>>>(a, q, s, o, n, k, b, act); break;
+        case 3: mixq_gemv_w8a16_kernel<3, 6><<<grid, block, 0, stream>>>(a, q, s, o, n, k, b, act); break;
+        default: mixq_gemv_w8a16_kernel<4, 4><<<grid, block, 0, stream>>>(a, q, s, o, n, k, b, act); break;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "launch gemv_w8a16");

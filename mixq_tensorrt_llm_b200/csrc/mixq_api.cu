@@ -359,12 +359,22 @@ namespace {
 struct HostPipe {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaEvent_t entry = nullptr, up[64] = {}, done[64] = {}, drained = nullptr;
+    // MIXQ_FLAG_HOST_ASYNC: two halves of the scratch alternate between consecutive calls.  slot_read[h] = the kernels of the
+    // last call that used half h have run (its activations may be overwritten), slot_drained[h] = its results have left the
+    // device (its Out area may be overwritten).
+    cudaEvent_t slot_read[2] = {}, slot_drained[2] = {};
+    bool slot_used[2] = {false, false};
+    int next_slot = 0;
+    bool pending = false;   // asynchronous calls issued since the last mixq_host_drain
     bool ok = false;
     HostPipe() {
         ok = cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking) == cudaSuccess &&
              cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&entry, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&drained, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; ok && i < 2; ++i)
+            ok = cudaEventCreateWithFlags(&slot_read[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&slot_drained[i], cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; ok && i < 64; ++i)
             ok = cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) == cudaSuccess;
@@ -389,13 +399,23 @@ int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_hos
         if (!t[i]) return set_error(MIXQ_ERR_BAD_ARG, "linears_host: null tensor table");
     for (int i = 0; i < count; ++i)
         if (!Out_host[i] || N[i] <= 0) return set_error(MIXQ_ERR_BAD_ARG, "linears_host: null output or bad N");
-    if (dev_scratch_bytes < (gated ? mixq_gated_host_scratch_size(M, N[0], K) : mixq_linears_host_scratch_size(M, N, count, K)))
-        return set_error(MIXQ_ERR_WORKSPACE, "linears_host: scratch too small");
+    const size_t need = gated ? mixq_gated_host_scratch_size(M, N[0], K) : mixq_linears_host_scratch_size(M, N, count, K);
+    if (dev_scratch_bytes < need) return set_error(MIXQ_ERR_WORKSPACE, "linears_host: scratch too small");
     if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
     HostPipe& hp = host_pipe();
     if (!hp.ok) return set_error(MIXQ_ERR_CUDA, "linears_host: could not create the copy streams");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    uintptr_t base = (reinterpret_cast<uintptr_t>(dev_scratch) + kAlign - 1) / kAlign * kAlign;
+    // Asynchronous form: nothing is waited for here.  With a scratch of twice the size consecutive calls alternate between its
+    // halves, so the upload of call i+1 and the download of call i share the PCIe link's two directions while the kernels
+    // of call i+1 wait only for their own operands; with a single-size scratch the Out area is the one thing call i+1 waits for.
+    const bool async = (flags & MIXQ_FLAG_HOST_ASYNC) != 0;
+    flags &= ~static_cast<unsigned>(MIXQ_FLAG_HOST_ASYNC);
+    int slot = 0;
+    if (async && dev_scratch_bytes >= 2 * align_up(need)) {
+        slot = hp.next_slot;
+        hp.next_slot ^= 1;
+    }
+    uintptr_t base = (reinterpret_cast<uintptr_t>(dev_scratch) + slot * align_up(need) + kAlign - 1) / kAlign * kAlign;
     uint8_t* dA = reinterpret_cast<uint8_t*>(base);
     uint8_t* dOut[8];
     uint8_t* cur = dA + align_up(static_cast<size_t>(M) * K * 2);
@@ -415,9 +435,20 @@ int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_hos
     while ((M + rows - 1) / rows > 64) rows *= 2;
     const int n_slabs = static_cast<int>((M + rows - 1) / rows);
 
-    cudaError_t e = cudaEventRecord(hp.entry, s);  // earlier work on the caller's stream may still use the scratch
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.h2d, hp.entry, 0);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.d2h, hp.entry, 0);
+    cudaError_t e = cudaSuccess;
+    if (async && hp.slot_used[slot]) {
+        // this half's activations were last read by the kernels of an earlier asynchronous call; its Out area is guarded below
+        e = cudaStreamWaitEvent(hp.h2d, hp.slot_read[slot], 0);
+    } else {
+        if (hp.pending) {   // undrained asynchronous calls: their downloads may still read the scratch
+            e = cudaEventRecord(hp.drained, hp.d2h);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s, hp.drained, 0);
+            if (e != cudaSuccess) return set_cuda_error(e, "linears_host: join earlier downloads");
+        }
+        e = cudaEventRecord(hp.entry, s);  // earlier work on the caller's stream may still use the scratch
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.h2d, hp.entry, 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.d2h, hp.entry, 0);
+    }
     if (e != cudaSuccess) return set_cuda_error(e, "linears_host: stream setup");
     const uint8_t* hA = static_cast<const uint8_t*>(A_host);
     // the activations cross PCIe ONCE, whatever the number of linears that consume them
@@ -426,6 +457,10 @@ int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_hos
         e = cudaMemcpyAsync(dA + r0 * K * 2, hA + r0 * K * 2, static_cast<size_t>(nr) * K * 2, cudaMemcpyHostToDevice, hp.h2d);
         if (e == cudaSuccess) e = cudaEventRecord(hp.up[c], hp.h2d);
         if (e != cudaSuccess) return set_cuda_error(e, "H2D activations");
+    }
+    if (async && hp.slot_used[slot]) {
+        e = cudaStreamWaitEvent(s, hp.slot_drained[slot], 0);   // the previous results of this half have left the device
+        if (e != cudaSuccess) return set_cuda_error(e, "linears_host: wait D2H of the previous call");
     }
     for (int c = 0; c < n_slabs; ++c) {
         const int64_t r0 = c * rows, nr = (r0 + rows <= M) ? rows : M - r0;
@@ -452,6 +487,14 @@ int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_hos
                                 static_cast<size_t>(nr) * N[i] * 2, cudaMemcpyDeviceToHost, hp.d2h);
         if (e != cudaSuccess) return set_cuda_error(e, "D2H output");
     }
+    if (async) {
+        e = cudaEventRecord(hp.slot_read[slot], s);
+        if (e == cudaSuccess) e = cudaEventRecord(hp.slot_drained[slot], hp.d2h);
+        if (e != cudaSuccess) return set_cuda_error(e, "linears_host: record");
+        hp.slot_used[slot] = true;
+        hp.pending = true;
+        return MIXQ_OK;
+    }
     e = cudaEventRecord(hp.drained, hp.d2h);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(s, hp.drained, 0);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -459,6 +502,23 @@ int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_hos
     return MIXQ_OK;
 }
 }  // namespace
+
+extern "C" int mixq_host_drain(void* stream) {
+    HostPipe& hp = host_pipe();
+    if (!hp.ok) return set_error(MIXQ_ERR_CUDA, "host_drain: could not create the copy streams");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaSuccess;
+    if (hp.pending) {
+        e = cudaEventRecord(hp.drained, hp.d2h);   // the download stream is in order: everything issued so far
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, hp.drained, 0);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    hp.pending = false;
+    hp.slot_used[0] = hp.slot_used[1] = false;
+    hp.next_slot = 0;
+    if (e != cudaSuccess) return set_cuda_error(e, "host_drain");
+    return MIXQ_OK;
+}
 
 extern "C" int mixq_linears_host(const mixq_tensors* const* t, int count, const void* A_host, void* const* Out_host, int64_t M,
                                  const int64_t* N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes, unsigned flags,
