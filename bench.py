@@ -745,8 +745,8 @@ def run_ours(args, wl):
             h2d = sum(h.numel() * 2 for h in hA.values()) * n_layers * tp
             d2h = sum(h.numel() * 2 for h in hO.values()) * n_layers * tp
             if tp == 1:
-                # twice the largest call's scratch (+ alignment): consecutive asynchronous calls alternate between the halves
-                scratch = torch.empty(2 * max(B.gated_host_scratch_size(M, layers[0][grp[0]]["N"], layers[0][grp[0]]["K"]) if "up" in layers[0][grp[0]] else
+                # four times the largest call's scratch (+ alignment): consecutive asynchronous calls take the four parts in turn
+                scratch = torch.empty(4 * max(B.gated_host_scratch_size(M, layers[0][grp[0]]["N"], layers[0][grp[0]]["K"]) if "up" in layers[0][grp[0]] else
                                               B.linears_host_scratch_size(M, [layers[0][i]["N"] for i in grp], layers[0][grp[0]]["K"]) for grp in groups) + 1024,
                                       dtype=torch.uint8, device=dev)
                 # decode-sized calls are queued (MIXQ_FLAG_HOST_ASYNC) and drained once per step: uploads, kernels and downloads
@@ -849,6 +849,41 @@ def run_ours(args, wl):
             e2e = {"value": flops_step / float(tt.item()) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h, "ms_per_step": float(tt.item()) * 1e3, "steps": args.e2e_steps,
                    "tokens_per_s": M / (float(tt.item()) * wl["model_layers"] / n_layers), "path": path}
+            # the host buffers hold the LAST layer's results: recompute that layer call by call, nothing overlapped, and compare
+            # bit for bit (a buffer rewritten before its download finished, or read before its upload, would show here)
+            lay, bad = layers[-1], 0
+            for gi, grp in enumerate(groups):
+                lin0 = lay[grp[0]]
+                rows = M // tp
+                a = torch.empty(M, lin0["full_k"] if (tp > 1 and lin0["mode"] == "column") else lin0["K"], dtype=torch.float16, device=dev)
+                if tp > 1 and lin0["mode"] == "column":
+                    a[rank * rows:(rank + 1) * rows].copy_(hA[gi])
+                    dist.all_gather_into_tensor(a, a[rank * rows:(rank + 1) * rows].clone())
+                else:
+                    a.copy_(hA[gi])
+                for i in grp:
+                    lin = lay[i]
+                    chk = torch.empty(M, lin["N"], dtype=torch.float16, device=dev)
+                    if tp > 1 and lin["mode"] == "row" and peer is not None:
+                        B.enqueue_allreduce(a, lin["W8"], lin["sb"], lin["fw"], lin["ind"], ws, peer.peer_group(M, lin["N"]))
+                        chk = peer.out(M, lin["N"])
+                    elif "up" in lin:
+                        B.enqueue_gated(a, (lin["W8"], lin["sb"], lin["fw"]), (lin["up"]["W8"], lin["up"]["sb"], lin["up"]["fw"]), lin["ind"], chk, ws)
+                    else:
+                        B.enqueue(a, lin["W8"], lin["sb"], lin["fw"], lin["ind"], chk, ws)
+                        if tp > 1 and lin["mode"] == "row":
+                            dist.all_reduce(chk)
+                    torch.cuda.synchronize()
+                    if tp > 1 and lin["mode"] == "row":
+                        chk = chk[rank * rows:(rank + 1) * rows]
+                    bad += int((chk.cpu().view(torch.int16) != hO[i].view(torch.int16)).sum().item())
+            tb = torch.tensor([bad], device=dev)
+            if world > 1:
+                dist.all_reduce(tb)
+            e2e["results_checked"] = "last layer recomputed call by call: %d differing outputs" % int(tb.item())
+            if int(tb.item()) != 0:
+                e2e["value"] = None
+                e2e["error"] = "pipelined host-buffer results differ from the call-by-call results"
         except Exception as e:
             e2e = {"value": None, "unit": UNIT, "error": repr(e)[:300]}
 

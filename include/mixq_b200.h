@@ -272,10 +272,11 @@ int mixq_gated_host(const mixq_tensors* gate, const mixq_tensors* up, const void
  * at a time, PCIe carries the upload, then idles during the kernels, then carries the download.  With
  * MIXQ_FLAG_HOST_ASYNC the calls of one thread queue up behind one another instead: the upload of call i+1 and the download
  * of call i use the link's two directions at once and the kernels of call i+1 start as soon as their operands are resident.
- * If `dev_scratch` holds TWICE the size the *_scratch_size function reports, consecutive calls alternate between its halves
- * and no call waits for the previous one's download; with the plain size call i+1's kernels wait until call i's results
- * have left the device.  The same `dev_scratch` may be passed to every call of a sequence (calls of different shapes
- * included: size it for the largest).  mixq_host_drain makes `stream` wait for everything those calls queued, synchronises
+ * A `dev_scratch` of k (2 to 4) times what the *_scratch_size function reports is used as k parts that consecutive calls
+ * take in turn (pass k times the size of the largest call of the sequence): a call then waits only for the calls that
+ * used the same bytes, k calls earlier; with the plain size call i+1 starts when call i's results have left the device.
+ * The same `dev_scratch` may be passed to every call of a sequence, calls of different shapes included (the library
+ * tracks the byte ranges in flight).  mixq_host_drain makes `stream` wait for everything those calls queued, synchronises
  * it and closes the sequence; a call without the flag drains first by itself.  State is per calling thread. */
 int mixq_host_drain(void* stream);
 

@@ -359,12 +359,16 @@ namespace {
 struct HostPipe {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaEvent_t entry = nullptr, up[64] = {}, done[64] = {}, drained = nullptr;
-    // MIXQ_FLAG_HOST_ASYNC: two halves of the scratch alternate between consecutive calls.  slot_read[h] = the kernels of the
-    // last call that used half h have run (its activations may be overwritten), slot_drained[h] = its results have left the
-    // device (its Out area may be overwritten).
-    cudaEvent_t slot_read[2] = {}, slot_drained[2] = {};
-    bool slot_used[2] = {false, false};
-    int next_slot = 0;
+    // MIXQ_FLAG_HOST_ASYNC: the last kInFlight asynchronous calls, each with the byte range of the scratch it uses and two
+    // events: `read` = its kernels have run (its activations and workspace may be overwritten), `drained` = its results
+    // have left the device.  A new call waits for every recorded call whose range overlaps its own.
+    static constexpr int kInFlight = 8;
+    struct InFlight {
+        uintptr_t begin = 0, end = 0;
+        cudaEvent_t read = nullptr, drained = nullptr;
+        bool used = false;
+    } inflight[kInFlight];
+    unsigned n_async = 0;   // asynchronous calls since the last drain: picks the part of the scratch and the record
     bool pending = false;   // asynchronous calls issued since the last mixq_host_drain
     bool ok = false;
     HostPipe() {
@@ -372,9 +376,9 @@ struct HostPipe {
              cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&entry, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&drained, cudaEventDisableTiming) == cudaSuccess;
-        for (int i = 0; ok && i < 2; ++i)
-            ok = cudaEventCreateWithFlags(&slot_read[i], cudaEventDisableTiming) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&slot_drained[i], cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; ok && i < kInFlight; ++i)
+            ok = cudaEventCreateWithFlags(&inflight[i].read, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&inflight[i].drained, cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; ok && i < 64; ++i)
             ok = cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) == cudaSuccess;
@@ -405,17 +409,20 @@ int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_hos
     HostPipe& hp = host_pipe();
     if (!hp.ok) return set_error(MIXQ_ERR_CUDA, "linears_host: could not create the copy streams");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // Asynchronous form: nothing is waited for here.  With a scratch of twice the size consecutive calls alternate between its
-    // halves, so the upload of call i+1 and the download of call i share the PCIe link's two directions while the kernels
-    // of call i+1 wait only for their own operands; with a single-size scratch the Out area is the one thing call i+1 waits for.
+    // Asynchronous form: nothing is waited for here.  A scratch of k (up to 4) times the call's size is used as k parts that
+    // consecutive calls take in turn, so the upload of a call and the downloads of the calls before it share the PCIe
+    // link's two directions while its kernels wait only for their own operands.  Calls of different shapes may cut the same
+    // scratch differently: what a call waits for is decided by byte ranges, not by part numbers.
     const bool async = (flags & MIXQ_FLAG_HOST_ASYNC) != 0;
     flags &= ~static_cast<unsigned>(MIXQ_FLAG_HOST_ASYNC);
-    int slot = 0;
-    if (async && dev_scratch_bytes >= 2 * align_up(need)) {
-        slot = hp.next_slot;
-        hp.next_slot ^= 1;
+    size_t part_off = 0;
+    if (async) {
+        size_t k = dev_scratch_bytes / align_up(need);
+        k = k > 4 ? 4 : k;
+        if (k >= 2) part_off = (hp.n_async % k) * (dev_scratch_bytes / k / kAlign * kAlign);
     }
-    uintptr_t base = (reinterpret_cast<uintptr_t>(dev_scratch) + slot * align_up(need) + kAlign - 1) / kAlign * kAlign;
+    uintptr_t base = (reinterpret_cast<uintptr_t>(dev_scratch) + part_off + kAlign - 1) / kAlign * kAlign;
+    const uintptr_t range_begin = base, range_end = base + need;
     uint8_t* dA = reinterpret_cast<uint8_t*>(base);
     uint8_t* dOut[8];
     uint8_t* cur = dA + align_up(static_cast<size_t>(M) * K * 2);
@@ -436,9 +443,22 @@ int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_hos
     const int n_slabs = static_cast<int>((M + rows - 1) / rows);
 
     cudaError_t e = cudaSuccess;
-    if (async && hp.slot_used[slot]) {
-        // this half's activations were last read by the kernels of an earlier asynchronous call; its Out area is guarded below
-        e = cudaStreamWaitEvent(hp.h2d, hp.slot_read[slot], 0);
+    HostPipe::InFlight* rec = nullptr;
+    if (async) {
+        // earlier asynchronous calls whose bytes this call reuses, possibly of another shape (their Out area may lie where this
+        // call's activations go): the upload waits for their kernels AND their downloads, the kernels for their downloads.
+        // The record about to be recycled is the oldest one: waited for unconditionally.
+        rec = &hp.inflight[hp.n_async % HostPipe::kInFlight];
+        for (int i = 0; i < HostPipe::kInFlight && e == cudaSuccess; ++i) {
+            HostPipe::InFlight& f = hp.inflight[i];
+            if (!f.used || (&f != rec && (f.end <= range_begin || range_end <= f.begin))) continue;
+            e = cudaStreamWaitEvent(hp.h2d, f.read, 0);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.h2d, f.drained, 0);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s, f.drained, 0);
+        }
+    }
+    if (async && hp.pending) {
+        // nothing else to wait for: earlier work on the caller's stream was joined when the sequence began
     } else {
         if (hp.pending) {   // undrained asynchronous calls: their downloads may still read the scratch
             e = cudaEventRecord(hp.drained, hp.d2h);
@@ -457,10 +477,6 @@ int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_hos
         e = cudaMemcpyAsync(dA + r0 * K * 2, hA + r0 * K * 2, static_cast<size_t>(nr) * K * 2, cudaMemcpyHostToDevice, hp.h2d);
         if (e == cudaSuccess) e = cudaEventRecord(hp.up[c], hp.h2d);
         if (e != cudaSuccess) return set_cuda_error(e, "H2D activations");
-    }
-    if (async && hp.slot_used[slot]) {
-        e = cudaStreamWaitEvent(s, hp.slot_drained[slot], 0);   // the previous results of this half have left the device
-        if (e != cudaSuccess) return set_cuda_error(e, "linears_host: wait D2H of the previous call");
     }
     for (int c = 0; c < n_slabs; ++c) {
         const int64_t r0 = c * rows, nr = (r0 + rows <= M) ? rows : M - r0;
@@ -488,17 +504,24 @@ int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_hos
         if (e != cudaSuccess) return set_cuda_error(e, "D2H output");
     }
     if (async) {
-        e = cudaEventRecord(hp.slot_read[slot], s);
-        if (e == cudaSuccess) e = cudaEventRecord(hp.slot_drained[slot], hp.d2h);
+        e = cudaEventRecord(rec->read, s);
+        if (e == cudaSuccess) e = cudaEventRecord(rec->drained, hp.d2h);
         if (e != cudaSuccess) return set_cuda_error(e, "linears_host: record");
-        hp.slot_used[slot] = true;
+        rec->begin = range_begin;
+        rec->end = range_end;
+        rec->used = true;
         hp.pending = true;
+        ++hp.n_async;
         return MIXQ_OK;
     }
     e = cudaEventRecord(hp.drained, hp.d2h);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(s, hp.drained, 0);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return set_cuda_error(e, "stream synchronize");
+    // the download stream is in order: asynchronous calls queued before this one have finished too
+    hp.pending = false;
+    for (auto& f : hp.inflight) f.used = false;
+    hp.n_async = 0;
     return MIXQ_OK;
 }
 }  // namespace
@@ -514,8 +537,8 @@ extern "C" int mixq_host_drain(void* stream) {
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     hp.pending = false;
-    hp.slot_used[0] = hp.slot_used[1] = false;
-    hp.next_slot = 0;
+    for (auto& f : hp.inflight) f.used = false;
+    hp.n_async = 0;
     if (e != cudaSuccess) return set_cuda_error(e, "host_drain");
     return MIXQ_OK;
 }

@@ -575,25 +575,28 @@ def test_linear_host_pipeline(B, lib, oracle, M):
     assert lib.mixq_linear_host(ctypes.byref(t), hA.data_ptr(), hO.data_ptr(), M, N, K, small.data_ptr(), 1024, 0, None) == -2
 
 
-@pytest.mark.parametrize("double_scratch", [False, True])
-def test_host_calls_async_sequence(B, lib, oracle, double_scratch):
+@pytest.mark.parametrize("parts", [1, 2, 4])
+def test_host_calls_async_sequence(B, lib, oracle, parts):
     """MIXQ_FLAG_HOST_ASYNC: a chain of host-buffer calls of different shapes (plain, shared-input, gated) queued without
-    waiting, one scratch for all of them (single size: a call's kernels wait for the previous download; double size: the
-    halves alternate), mixq_host_drain at the end.  Every result must equal the synchronous call's, bit for bit; a
+    waiting, one scratch for all of them (single size: a call waits for the previous download; k times the size: the
+    calls take the k parts in turn), mixq_host_drain at the end.  Every result must equal the synchronous call's, bit for bit; a
     synchronous call issued while asynchronous ones are pending drains by itself."""
-    M = 300
-    shapes = [(264, 400), (512, 400), (136, 656)]
+    # long downloads next to short ones and activations of different widths, so that a call's upload or kernels running
+    # before the previous user of its scratch half has finished would be seen
+    M = 2048
+    shapes = [(4096, 256), (264, 1024), (2048, 512)]
+    N0, K0 = shapes[0]
     lins = [_packed(oracle, "synthetic", N, K, seed=11 + i) for i, (N, K) in enumerate(shapes)]
     dev = [tuple(_t(l[k]) for k in ("W8", "scale_b", "fp_weight", "ind")) for l in lins]
     tabs = [B.make_tensors(None, *d, None) for d in dev]
-    up = _packed(oracle, "synthetic", 264, 400, seed=29)       # second projection of the gated call: same shape as lins[0]
+    up = _packed(oracle, "synthetic", N0, K0, seed=29)       # second projection of the gated call: same shape as lins[0]
     up["ind"] = lins[0]["ind"]
     dup = tuple(_t(up[k]) for k in ("W8", "scale_b", "fp_weight")) + (dev[0][3],)
     tab_up = B.make_tensors(None, *dup, None)
     hA = [torch.from_numpy(oracle.synth_activations(M, l["act_scale"], seed=70 + i)).pin_memory() for i, l in enumerate(lins)]
-    need = max([B.linears_host_scratch_size(M, [N], K) for N, K in shapes] + [B.gated_host_scratch_size(M, 264, 400),
-                                                                             B.linears_host_scratch_size(M, [264, 264], 400)])
-    scratch = torch.empty((2 * need + 512) if double_scratch else need, dtype=torch.uint8, device=DEV)
+    need = max([B.linears_host_scratch_size(M, [N], K) for N, K in shapes] + [B.gated_host_scratch_size(M, N0, K0),
+                                                                             B.linears_host_scratch_size(M, [N0, N0], K0)])
+    scratch = torch.empty(parts * need + (512 if parts > 1 else 0), dtype=torch.uint8, device=DEV)
 
     def run(flags, reps):
         outs = []
@@ -602,10 +605,10 @@ def test_host_calls_async_sequence(B, lib, oracle, double_scratch):
                 o = torch.full((M, shapes[i][0]), float("nan"), dtype=torch.float16).pin_memory()
                 B.linears_host([tabs[i]], hA[i], [o], scratch, flags=flags)
                 outs.append(o)
-            o1 = torch.full((M, 264), float("nan"), dtype=torch.float16).pin_memory()
-            o2 = torch.full((M, 264), float("nan"), dtype=torch.float16).pin_memory()
+            o1 = torch.full((M, N0), float("nan"), dtype=torch.float16).pin_memory()
+            o2 = torch.full((M, N0), float("nan"), dtype=torch.float16).pin_memory()
             B.linears_host([tabs[0], tab_up], hA[0], [o1, o2], scratch, flags=flags)
-            og = torch.full((M, 264), float("nan"), dtype=torch.float16).pin_memory()
+            og = torch.full((M, N0), float("nan"), dtype=torch.float16).pin_memory()
             B.gated_host(tabs[0], tab_up, hA[0], og, scratch, flags=flags)
             outs += [o1, o2, og]
         return outs
