@@ -1,7 +1,7 @@
 # usage: bash tools/run_tp_e2e.sh N   (inside gpurun --gpus N): the metric's configuration at N ranks, e2e leg included
 N=$1
 mkdir -p gpurun_out/s3
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N 2> gpurun_out/s3/tp${N}_bs512.err | grep "^{" > gpurun_out/s3/tp${N}_bs512.json
+timeout -k 10 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N 2> gpurun_out/s3/tp${N}_bs512.err | grep "^{" > gpurun_out/s3/tp${N}_bs512.json
 python - <<P
 import json
 try:
