@@ -160,6 +160,13 @@ def test_no_cpu_fallback(lib):
     g.out[0] = g.staging[0] = g.counters[0] = p
     g.staging_bytes, g.counter_bytes = 1 << 20, 4096
     assert lib.mixq_gemm_dequant_allreduce(p, p, p, p, None, None, 8, 8, 64, ctypes.byref(g), None) == -3   # and the fused all-reduce
+    # host-buffer calls, synchronous and queued, and the drain
+    t = binding.Tensors()
+    n = lib.mixq_host_scratch_size(8, 8, 64)
+    assert n > 0
+    for flags in (0, binding.FLAG_HOST_ASYNC):
+        assert lib.mixq_linear_host(ctypes.byref(t), p, p, 8, 8, 64, p, n, flags, None) == -3
+    assert lib.mixq_host_drain(None) == -3
 
 
 def test_product_does_not_touch_oracle():
