@@ -33,14 +33,28 @@
 constexpr int kFatMaxN = 336;          // Nt + Nt / 2 <= 512 TMEM columns, Nt % 16 == 0
 constexpr int kFatMaxStages = 8;
 constexpr int kFatSbFloats = 352;
-constexpr int kFatOutStageBytes = 8 * 2 * 2048;   // per epilogue warp two 32-row x 32-column fp16 tiles (double-buffered TMA-store staging)
+// per epilogue warp two 32-row x 32-column fp16 tiles (double-buffered TMA-store staging)
+constexpr int fat_out_stage_bytes(int epi_warps) { return epi_warps * 2 * 2048; }
 constexpr int kFatMaxPartPairs = 6;                // split-K: chunk pairs (32 columns) per epilogue warp, (336 / 16 / 2 + 1) / 2 rounded up
-constexpr int kFatFixedBytes = 3072 + 512 + kFatOutStageBytes;   // + scale_b / bias staging (2 x 352 floats, one tile at a time), barriers, TMEM pointer
+// + scale_b / bias staging (2 x 352 floats, one tile at a time), barriers, TMEM pointer
+constexpr int fat_fixed_bytes(int epi_warps) { return 3072 + 512 + fat_out_stage_bytes(epi_warps); }
 
 __device__ __forceinline__ uint32_t fat_idesc_i8(int n) { return ptx::make_idesc_i8(256, n); }
 __device__ __forceinline__ uint32_t fat_idesc_f16(int n) { return ptx::make_idesc_f16(256, n); }
 
-__global__ void __launch_bounds__(kStashThreads, 1)
+// Chunk (16 accumulator columns) range of part p when the `parts` epilogue warps that share a TMEM lane quarter split a tile's
+// n chunks: even-sized shares, so every part starts on a 32-column boundary (the TMA-store tiles are 32 columns wide).
+__device__ __forceinline__ void fat_chunk_range(int n, int parts, int p, int& b, int& e) {
+    const int per = ((n + parts - 1) / parts + 1) & ~1;
+    b = min(n, p * per);
+    e = min(n, b + per);
+}
+
+// EW = epilogue warps per CTA (8 or 12: two or three per TMEM lane quarter).  The exposed epilogue of a one-wave tile is a
+// dependent chain per warp (tcgen05.ld -> dequantise -> staging tile -> TMA store), not a bandwidth: more warps shorten it.
+// The split-K mode (ksplit == 2) is written for EW = 8.
+template <int EW>
+__global__ void __launch_bounds__((kEpilogueWarp0 + EW) * 32, 1)
 mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __grid_constant__ CUtensorMap tm_w1,
                              const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_fa,
                              const __grid_constant__ CUtensorMap tm_fw1, const __grid_constant__ CUtensorMap tm_fw2,
@@ -56,7 +70,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
     const int stage_bytes = kBlockM * kBlockKBytes + (Nt / 2) * kBlockKBytes;
     uint8_t* ring = smem;
     uint8_t* out_stage = ring + static_cast<size_t>(stages) * stage_bytes;                       // 2 KB tiles, 1024-aligned
-    float* sb_s = reinterpret_cast<float*>(out_stage + kFatOutStageBytes);                       // [352], rewritten per tile
+    float* sb_s = reinterpret_cast<float*>(out_stage + fat_out_stage_bytes(EW));                 // [352], rewritten per tile
     float* bias_sm = sb_s + kFatSbFloats;                                                         // [352]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_sm + kFatSbFloats);
     uint64_t* empty_bar = full_bar + kFatMaxStages;
@@ -68,6 +82,8 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
     uint64_t* part_bar = ring_free_bar + 1;              // split-K, in the finishing CTA: [8 warps][kFatMaxPartPairs] partial sums landed
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(part_bar + 8 * kFatMaxPartPairs);
 
+    constexpr int kEpiThreads = EW * 32;
+    constexpr int kParts = EW / 4;
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     // Split-K (ksplit == 2): a cluster of 4 = two CTA pairs on one tile.  Pair 0 (cluster ranks 0, 1) reduces the outlier
@@ -80,14 +96,14 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
     const uint32_t leader_rank = crank & ~1u;
     const uint16_t pair_mask = static_cast<uint16_t>(3u << (kpart * 2));
     const bool is_leader = cta_rank == 0;
-    const bool sender = kpart != 0;
+    const bool sender = EW == 8 && kpart != 0;            // (split-K exists in the EW = 8 instantiation only)
     const int cluster_ctas = 2 * ksplit;
     const int group_id = blockIdx.x / cluster_ctas;
     const int num_groups = gridDim.x / cluster_ctas;
     if (sender) has_outlier = 0;                        // the outlier product belongs to the finishing pair
     // chunk (16 accumulator columns) ranges of the two epilogue warps that share a TMEM lane quarter
     const int n_chunks_all = Nt >> 4;
-    const int c_split_all = min(n_chunks_all, ((n_chunks_all + 1) / 2 + 1) & ~1);   // even: both halves start on a 32-column boundary
+    const int c_split_all = min(n_chunks_all, ((n_chunks_all + 1) / 2 + 1) & ~1);   // split-K (EW = 8): even, both halves start on a 32-column boundary
     if (threadIdx.x == 0) trace_stamp(0);
 
     if (warp_idx == 0 && ptx::elect_one()) {
@@ -108,8 +124,8 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
         }
         ptx::mbar_init(f_full_bar, 1);
         ptx::mbar_init(tmem_full_bar, 1);
-        ptx::mbar_init(f_drained_bar, 2 * kStashEpiThreads / 32);
-        ptx::mbar_init(tmem_empty_bar, 2 * kStashEpiThreads / 32);
+        ptx::mbar_init(f_drained_bar, 2 * kEpiThreads / 32);
+        ptx::mbar_init(tmem_empty_bar, 2 * kEpiThreads / 32);
         ptx::mbar_init(ring_free_bar, 1);
         for (int i = 0; i < 8 * kFatMaxPartPairs; ++i) ptx::mbar_init(&part_bar[i], 1);
         if (ksplit == 2 && !sender) {
@@ -230,17 +246,17 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
         }
         __syncwarp();
     } else if (warp_idx >= kEpilogueWarp0) {
-        // ===================== epilogue (8 warps; every CTA: its own 128 accumulator rows) =====================
-        // two warps per TMEM lane quarter split the tile's 16-column chunks between them
+        // ===================== epilogue (EW warps; every CTA: its own 128 accumulator rows) =====================
+        // the kParts warps of a TMEM lane quarter split the tile's 16-column chunks between them
         const int quarter = warp_idx & 3;
-        const int half = (warp_idx - kEpilogueWarp0) >> 2;
-        const int et = threadIdx.x - kEpilogueWarp0 * 32;   // 0..255
+        const int part = (warp_idx - kEpilogueWarp0) >> 2;
+        const int et = threadIdx.x - kEpilogueWarp0 * 32;   // 0 .. kEpiThreads - 1
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
         const int n_chunks = n_chunks_all;
         const int c_split = c_split_all;
-        const int c_begin = half == 0 ? 0 : c_split;
-        const int c_end = half == 0 ? c_split : n_chunks;
+        int c_begin, c_end;
+        fat_chunk_range(n_chunks, kParts, part, c_begin, c_end);
         const uint32_t t_acc = tmem_base + lane_base;                                   // int32 / fp32 accumulators
         const uint32_t t_out0 = tmem_base + lane_base + static_cast<uint32_t>(Nt);      // packed fp16 outlier product
         auto arrive = [&](uint64_t* bar) {
@@ -260,7 +276,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
             const int ew = warp_idx - kEpilogueWarp0;
             const uint32_t zone_warp = ptx::smem_u32(ring) + static_cast<uint32_t>(ew * c_split) * 2048u + lane * 16u;
 
-            if (sender) {
+            if (EW == 8 && sender) {
                 // ---- split-K sending pair: ship this CTA's int32 partial sums to the CTA of the finishing pair that holds the
                 // same rows (cluster rank - 2), a chunk (32 lanes x 16 columns) at a time
                 ptx::mbar_wait(tmem_full_bar, lt & 1);
@@ -324,8 +340,8 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                 if (et == 0 && lt == 0) trace_stamp(12);
             }
             // the staging vectors are single-buffered: past this barrier every thread is done with the previous tile
-            ptx::named_bar_sync(1, kStashEpiThreads);
-            for (int j = et; j < Nt; j += kStashEpiThreads) {
+            ptx::named_bar_sync(1, kEpiThreads);
+            for (int j = et; j < Nt; j += kEpiThreads) {
                 if (gated) {   // [0, Ng): gate scales, [Ng, 2 Ng): up scales of the same channels
                     const int jj = j < N1 ? j : j - N1;
                     sb_s[j] = (n0 + jj < N) ? __half2float((j < N1 ? scale_b : scale_b2)[n0 + jj]) : 0.0f;
@@ -334,13 +350,13 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                     if (epi.bias) bias_sm[j] = (n0 + j < N) ? __half2float(epi.bias[n0 + j]) : 0.0f;
                 }
             }
-            ptx::named_bar_sync(1, kStashEpiThreads);
+            ptx::named_bar_sync(1, kEpiThreads);
 
             // ---- dequantise the int32 accumulators
             ptx::mbar_wait(tmem_full_bar, lt & 1);
             ptx::tc_fence_after_sync();
             if (et == 0) trace_stamp(lt == 0 ? 6 : 8);
-            if (ksplit == 2 && et == 0) ptx::mbar_arrive_cluster(ring_free_bar, crank + 2u);   // the sending CTA may overwrite the ring now
+            if (EW == 8 && ksplit == 2 && et == 0) ptx::mbar_arrive_cluster(ring_free_bar, crank + 2u);   // the sending CTA may overwrite the ring now
             __half* out_row = Out + static_cast<size_t>(gm) * N + n0;
             // The result leaves through shared memory: row-per-thread 16-byte global stores touch 32 cache lines per instruction;
             // instead each warp writes 32-row x 32-column SWIZZLE_64B tiles (conflict free for row-per-thread writes) that go out
@@ -409,7 +425,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
             if (!gated) {
             // split-K: the other pair's partial sums of chunk c wait in the landing zone once the chunk pair's barrier has fired
             auto add_partial = [&](uint32_t (&vi)[16], int c) {
-                if (ksplit != 2) return;
+                if (EW != 8 || ksplit != 2) return;
                 const uint32_t src = zone_warp + static_cast<uint32_t>(c - c_begin) * 2048u;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -423,7 +439,7 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                 const bool pair = c + 1 < c_end;
                 const int pi = ((c - c_begin) >> 1) & 1;
                 const uint32_t t = tiles_addr + pi * 2048;
-                if (ksplit == 2) ptx::mbar_wait(&part_bar[ew * kFatMaxPartPairs + ((c - c_begin) >> 1)], lt & 1);
+                if (EW == 8 && ksplit == 2) ptx::mbar_wait(&part_bar[ew * kFatMaxPartPairs + ((c - c_begin) >> 1)], lt & 1);
                 ptx::tmem_ld_wait();
                 if (pair) load(ib, ob, c + 1);
                 add_partial(ia, c);
@@ -452,8 +468,8 @@ mixq_gemm_dequant_fat_kernel(const __grid_constant__ CUtensorMap tm_a8, const __
                 // ---- gated: out = fp16(silu(gate)) * fp16(up) over the tile's Ng channels; gate accumulators in columns [0, Ng), up
                 // in [Ng, 2 Ng), their parked outlier products in [Nt, Nt + Ng/2) and [Nt + Ng/2, Nt + Ng)
                 const int g_chunks = N1 >> 4;
-                const int g_split = min(g_chunks, ((g_chunks + 1) / 2 + 1) & ~1);
-                const int g_begin = half == 0 ? 0 : g_split, g_end = half == 0 ? g_split : g_chunks;
+                int g_begin, g_end;
+                fat_chunk_range(g_chunks, kParts, part, g_begin, g_end);
                 const uint32_t t_up = t_acc + static_cast<uint32_t>(N1), t_out0_up = t_out0 + static_cast<uint32_t>(N1 >> 1);
                 uint32_t iu[16], ou[8];
                 if (!has_outlier) {

@@ -1868,7 +1868,7 @@ int launch_decode(const void* A8, const void* W8, const void* scale_a, const voi
 struct FatPlan {
     int Nt, n_tiles, m_tiles, stages, stage_bytes, waves;
 };
-FatPlan plan_fat(int64_t M, int64_t N, int pairs, bool gated = false) {
+FatPlan plan_fat(int64_t M, int64_t N, int pairs, bool gated = false, int epi_warps = 8) {
     // N: accumulator columns of the whole problem (gated: gate + up = 2 x the output channels; a tile then holds Nt / 2
     // channels of each, so Nt is a multiple of 32)
     FatPlan p{};
@@ -1884,7 +1884,7 @@ FatPlan plan_fat(int64_t M, int64_t N, int pairs, bool gated = false) {
     p.Nt = static_cast<int>(nt);
     p.n_tiles = static_cast<int>((N + nt - 1) / nt);
     p.stage_bytes = kBlockM * kBlockKBytes + (p.Nt / 2) * kBlockKBytes;
-    int st = static_cast<int>((227 * 1024 - 1024 - kFatFixedBytes) / p.stage_bytes);
+    int st = static_cast<int>((227 * 1024 - 1024 - fat_fixed_bytes(epi_warps)) / p.stage_bytes);
     p.stages = st > kFatMaxStages ? kFatMaxStages : st;
     const int64_t tiles = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
     p.waves = static_cast<int>((tiles + pairs - 1) / pairs);
@@ -1917,8 +1917,8 @@ int fat_max_clusters4() {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int n = 0;
-    cudaError_t e = cudaFuncSetAttribute(mixq_gemm_dequant_fat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, mixq_gemm_dequant_fat_kernel, &cfg);
+    cudaError_t e = cudaFuncSetAttribute(mixq_gemm_dequant_fat_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, mixq_gemm_dequant_fat_kernel<8>, &cfg);
     if (e != cudaSuccess) {
         cudaGetLastError();
         n = 0;
@@ -1946,11 +1946,12 @@ bool plan_fat_split(int64_t M, int64_t N, int64_t K, const LaunchOpts& opts, Fat
 
 int launch_fat(const void* A8, const void* W8, const void* scale_a, const void* scale_b, const void* fp_A, const void* fp_weight,
                void* Out, int64_t M, int64_t N, int64_t K, cudaStream_t stream, bool pdl, EpiArgs epi, LaunchOpts opts,
-               const FatGated* gated = nullptr, int ksplit = 1) {
+               const FatGated* gated = nullptr, int ksplit = 1, int epi_warps = 12) {
     const DeviceInfo& dev = device_info();
     const int pairs = usable_sms(opts) / 2;
     if (pairs < 1) return set_error(MIXQ_ERR_BAD_ARG, "gemm_dequant: sm_limit leaves no CTA pair");
-    FatPlan pl = plan_fat(M, gated ? 2 * N : N, pairs, gated != nullptr);
+    if (ksplit == 2) epi_warps = 8;   // the split-K landing zone is laid out for two warps per lane quarter
+    FatPlan pl = plan_fat(M, gated ? 2 * N : N, pairs, gated != nullptr, epi_warps);
     if (ksplit == 2 && (gated || !plan_fat_split(M, N, K, opts, &pl)))
         return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: the split-K fat-tile schedule needs one cluster of 4 per tile");
     if (pl.stages < 3) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: fat tile does not fit shared memory");
@@ -1974,12 +1975,13 @@ int launch_fat(const void* A8, const void* W8, const void* scale_a, const void* 
     }
     CUtensorMap tm_out;
     if ((rc = make_tmap(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Out, M, N, 32, 64))) return rc;
-    auto kern = mixq_gemm_dequant_fat_kernel;
+    auto kern = epi_warps == 8 ? mixq_gemm_dequant_fat_kernel<8> : mixq_gemm_dequant_fat_kernel<12>;
     constexpr int kMaxSmem = 227 * 1024;
     cudaError_t e = cudaSuccess;
     static std::atomic<uint64_t> attr_set_mask{0};
     if (!(attr_set_mask.load(std::memory_order_acquire) >> dev.device & 1)) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        e = cudaFuncSetAttribute(mixq_gemm_dequant_fat_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mixq_gemm_dequant_fat_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(gemm_dequant_fat)");
         attr_set_mask.fetch_or(uint64_t(1) << dev.device, std::memory_order_release);
     }
@@ -1988,8 +1990,8 @@ int launch_fat(const void* A8, const void* W8, const void* scale_a, const void* 
     const int groups = static_cast<int>(tiles < workers ? tiles : workers);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(groups * 2 * ksplit);
-    cfg.blockDim = dim3(kStashThreads);
-    cfg.dynamicSmemBytes = 1024 + static_cast<size_t>(pl.stages) * pl.stage_bytes + kFatFixedBytes;
+    cfg.blockDim = dim3((kEpilogueWarp0 + (epi_warps == 8 ? 8 : 12)) * 32);
+    cfg.dynamicSmemBytes = 1024 + static_cast<size_t>(pl.stages) * pl.stage_bytes + fat_fixed_bytes(epi_warps == 8 ? 8 : 12);
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
@@ -2127,7 +2129,7 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
         }
         if (M > 128 && M <= kDecodeMaxM && usable_sms(opts) >= 2) {
             // one fat tile per CTA pair and wave (gemm_fat.cuh): longer exposed head (outlier product first) and tail
-            const FatPlan pl = plan_fat(M, N, usable_sms(opts) / 2);
+            const FatPlan pl = plan_fat(M, N, usable_sms(opts) / 2, false, 12);
             const int64_t est = static_cast<int64_t>(pl.waves) * (pl.stage_bytes / 48) * nkb + 7000;
             if (pl.stages >= 4 && est < best) {
                 best = est;
@@ -2138,10 +2140,10 @@ int launch_gemm_dequant(const void* A8, const void* W8, const void* scale_a, con
             // operand bytes, sets it -- so the split only adds its exchange: 512x4096x11008 28.7 us against 22.6 us for id 5)
         }
     }
-    if (cfg == kCfg2CtaFat || cfg == kCfg2CtaFatSplitK) {
+    if (cfg == kCfg2CtaFat || cfg == kCfg2CtaFatSplitK || cfg == kCfg2CtaFatEpi8) {
         if (M > kDecodeMaxM) return set_error(MIXQ_ERR_UNSUPPORTED, "gemm_dequant: the fat-tile kernel serves M <= 1024");
         return launch_fat(A8, W8, scale_a, scale_b, fp_A, fp_weight, Out, M, N, K, stream, pdl, epi, opts, nullptr,
-                          cfg == kCfg2CtaFatSplitK ? 2 : 1);
+                          cfg == kCfg2CtaFatSplitK ? 2 : 1, cfg == kCfg2CtaFatEpi8 ? 8 : 12);
     }
     if (cfg == kCfg2CtaN256Decode || cfg == kCfg2CtaN256DecodeNoSplit) {
         if (!decode_ok)
@@ -2213,7 +2215,10 @@ int launch_gemm_dequant_gated(const void* A8, const void* scale_a, const void* f
     if (!device_info().ok) return set_error(MIXQ_ERR_CUDA, "no usable sm_100 device");
     if (M <= kDecodeMaxM && usable_sms(opts) >= 2 && opts.cfg != kCfgGatedUnfused) {
         const FatGated g{W8_up, sb_up, fpw_up};
-        return launch_fat(A8, W8_gate, scale_a, sb_gate, fp_A, fpw_gate, Out, M, N, K, stream, pdl, EpiArgs{nullptr, 0}, opts, &g);
+        // 8 epilogue warps: the gated epilogue (two accumulators and a SiLU per output) is issue-bound, a third warp per lane
+        // quarter does not shorten it (45.5 vs 45.2 us at 512 x 11008 x 4096); id 13 asks for 12 all the same (A/B)
+        return launch_fat(A8, W8_gate, scale_a, sb_gate, fp_A, fpw_gate, Out, M, N, K, stream, pdl, EpiArgs{nullptr, 0}, opts, &g, 1,
+                          opts.cfg == kCfg2CtaFat ? 12 : 8);
     }
     // prefill-sized batches are tensor-bound and their tiles fill the machine: two GEMMs over the shared quantised A
     // (the gate's with the fused SiLU) and one elementwise pass, the same roundings in the same order

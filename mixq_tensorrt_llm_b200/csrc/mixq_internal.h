@@ -74,7 +74,7 @@ int launch_gemv_w8a16(const void* A, const void* q_weight, const void* scales, v
                       cudaStream_t stream, const void* bias = nullptr, int act = 0);
 
 // GEMM tile configuration ids (mixq_set_gemm_config); 0 = pick automatically.
-enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfg2CtaN256Tma = 9, kCfg2CtaN192Tma = 10, kCfg2CtaN256Decode = 11, kCfg2CtaN256DecodeNoSplit = 12, kCfg2CtaFat = 13, kCfg2CtaFatSplitK = 14, kCfgN32x2 = 15, kCfgCount,
+enum GemmConfig { kCfgAuto = 0, kCfgN128x2 = 1, kCfgN256x1 = 2, kCfgN64x2 = 3, kCfg2CtaN256x1 = 4, kCfg2CtaN128x2 = 5, kCfg2CtaN256Stash = 6, kCfgN256Stash = 7, kCfg2CtaN256StreamK = 8, kCfg2CtaN256Tma = 9, kCfg2CtaN192Tma = 10, kCfg2CtaN256Decode = 11, kCfg2CtaN256DecodeNoSplit = 12, kCfg2CtaFat = 13, kCfg2CtaFatSplitK = 14, kCfgN32x2 = 15, kCfg2CtaFatEpi8 = 16 /* the fat tile with 8 epilogue warps (13: 12) */, kCfgCount,
                   kCfgGatedUnfused = 100 /* mixq_*_gated only: the two-GEMM + multiply composition for every M (tests) */ };
 // SMs the persistent kernels may occupy on the current device (all, or the caller's per-call limit)
 int usable_sms(const LaunchOpts& opts);

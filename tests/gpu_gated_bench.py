@@ -35,6 +35,10 @@ def fused(i):
     B.enqueue_gated(A, gates[i], ups[i], ind, o1, ws)
 
 
+def fused_epi12(i):
+    B.enqueue_gated(A, gates[i], ups[i], ind, o1, ws, config=13)
+
+
 def separate(i):
     B.enqueue(A, *gates[i], ind, o1, ws, activation=B.ACT_SILU)
     B.enqueue(A, *ups[i], ind, o2, ws)
@@ -70,7 +74,7 @@ def timed(fn):
 
 
 print(f"gated MLP input half {M}x{N}x{K}, {L} weight sets, us per layer (graph replay)")
-for name, fn in (("mixq_enqueue_gated (1 quant + 1 GEMM)", fused), ("2 x mixq_enqueue (gate with SiLU, up)", separate),
+for name, fn in (("mixq_enqueue_gated (1 quant + 1 GEMM)", fused), ("the same with 12 epilogue warps (config 13)", fused_epi12), ("2 x mixq_enqueue (gate with SiLU, up)", separate),
                  ("2 x mixq_enqueue + torch.mul", separate_mul)):
     us = timed(fn)
     print(f"  {name:42s} {us:8.2f} us   {4.0 * M * N * K / us / 1e6:7.1f} TOPS")

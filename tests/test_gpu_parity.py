@@ -251,7 +251,7 @@ GEMM_SHAPES = [(128, 128, 128), (128, 128, 256), (256, 256, 512), (1, 8, 16), (1
                (512, 256, 28672)]
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     """No outlier slab: int32 accumulation is exact, the epilogue is one fma + one rounding, so
@@ -270,7 +270,7 @@ def test_gemm_dequant_int_path_bit_exact(B, lib, oracle, cfg, M, N, K):
     assert bad.size == 0, f"{len(bad)} mismatches, first at {bad[:5].tolist()}: got {got[tuple(bad[0])]} want {ref[tuple(bad[0])]}"
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (100, 136, 144), (300, 520, 1040), (64, 512, 4096), (512, 1024, 4096)])
 def test_gemm_dequant_with_outlier_slab(B, lib, oracle, cfg, M, N, K):
     rng = np.random.default_rng(M + N + K)
@@ -824,7 +824,7 @@ def test_plugin_module_takes_weight_only_branch_with_qweight(B, oracle):
 
 
 # ------------------------------------------------------------------ fused epilogue: bias / SiLU
-@pytest.mark.parametrize("cfg", [0, 1, 5, 6, 9, 10, 11, 13])
+@pytest.mark.parametrize("cfg", [0, 1, 5, 6, 9, 10, 11, 13, 16])
 def test_fused_bias_epilogue_bit_exact(B, lib, oracle, cfg):
     """mixq_gemm_dequant_ex with a bias and no outlier slab: Out == fp16(float(fp16(fma)) + bias[n]) bit for bit
     (int32 exact, one FMA, two roundings) for every kernel family."""
@@ -909,6 +909,11 @@ def test_gated_mlp_half(B, oracle, M, N, K):
     B.enqueue_gated(tA, tg, tu, ind, unf, ws, config=100)      # the two-GEMM + multiply composition inside the library
     torch.cuda.synchronize()
     assert torch.equal(out.view(torch.int16), unf.view(torch.int16))
+    if M <= 1024:                                              # the fat tile with 12 epilogue warps (default for the gated call: 8)
+        unf.fill_(float("nan"))
+        B.enqueue_gated(tA, tg, tu, ind, unf, ws, config=13)
+        torch.cuda.synchronize()
+        assert torch.equal(out.view(torch.int16), unf.view(torch.int16))
     # oracle
     rg = oracle.forward(A, gate["W8"], gate["scale_b"], gate["fp_weight"], gate["ind"], return_parts=True)
     ru = oracle.forward(A, up["W8"], up["scale_b"], up["fp_weight"], up["ind"], return_parts=True)
