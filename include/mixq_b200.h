@@ -289,6 +289,12 @@ uint64_t mixq_launch_count(void);
  * epilogue done); NULL (default) disables it. */
 int mixq_debug_set_trace(void* dev_buf);
 
+/* Debug only (host arithmetic, no device needed): the schedule the fat-tile decode kernel would use for an M x N
+ * problem on `pairs` CTA pairs (N = output channels of ONE projection; gated != 0: gate and up side by side),
+ * out5 = {tile width Nt in accumulator columns, column tiles, row tiles, ring stages, waves}.  tests/ checks its
+ * invariants (Nt + Nt/2 <= 512 TMEM columns, the tiles cover N, the ring fits shared memory) over random shapes. */
+int mixq_debug_fat_plan(int64_t M, int64_t N, int pairs, int gated, int epi_warps, int* out5);
+
 /* ---- per-call tuning ------------------------------------------------------------------------------------------
  * The library keeps no mutable process-wide state (SURVEY.md 8b "no static mutable state"): a caller that wants a
  * particular tile configuration, or wants to leave SMs free for a concurrent communication kernel, says so on the

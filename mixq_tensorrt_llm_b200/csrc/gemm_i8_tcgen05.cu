@@ -2028,6 +2028,11 @@ __global__ void mixq_mul_inplace_kernel(__half2* __restrict__ out, const __half2
 
 size_t decode_workspace_bytes(int64_t M, int64_t N) { return streamk_workspace_bytes() + decode_out0_bytes(M, N); }
 
+void fat_plan_for(int64_t M, int64_t N, int pairs, int gated, int epi_warps, int* out5) {
+    const FatPlan p = plan_fat(M, gated ? 2 * N : N, pairs, gated != 0, epi_warps);
+    out5[0] = p.Nt; out5[1] = p.n_tiles; out5[2] = p.m_tiles; out5[3] = p.stages; out5[4] = p.waves;
+}
+
 int set_trace_buffer(void* dev_buf) {
     unsigned long long* p = static_cast<unsigned long long*>(dev_buf);
     cudaError_t e = cudaMemcpyToSymbol(g_trace, &p, sizeof(p));

@@ -127,6 +127,12 @@ int mixq_gemv_w8a16(const void* A, const void* q_weight, const void* scales, voi
 }
 
 int mixq_debug_set_trace(void* dev_buf) { return set_trace_buffer(dev_buf); }
+int mixq_debug_fat_plan(int64_t M, int64_t N, int pairs, int gated, int epi_warps, int* out5) {
+    if (!out5 || M <= 0 || N <= 0 || pairs <= 0 || (epi_warps != 8 && epi_warps != 12))
+        return set_error(MIXQ_ERR_BAD_ARG, "debug_fat_plan: bad argument");
+    fat_plan_for(M, N, pairs, gated, epi_warps, out5);
+    return MIXQ_OK;
+}
 
 size_t mixq_gemm_workspace_size(void) { return streamk_workspace_bytes(); }
 

@@ -68,6 +68,8 @@ int launch_allreduce_pull(void* const* partials, void* const* counters, void* co
 size_t allreduce_staging_bytes(int64_t M, int64_t N, int world);
 size_t allreduce_counter_bytes(int64_t M, int64_t N, int world);
 int set_trace_buffer(void* dev_buf);
+// the fat-tile schedule of a decode batch (host arithmetic only): out = {Nt, n_tiles, m_tiles, stages, waves}
+void fat_plan_for(int64_t M, int64_t N, int pairs, int gated, int epi_warps, int* out5);
 
 // M <= 4 branch (gemv_w8a16.cu): weight-only GEMV over the EETQ-interleaved q_weight
 int launch_gemv_w8a16(const void* A, const void* q_weight, const void* scales, void* Out, int64_t M, int64_t N, int64_t K,

@@ -271,3 +271,33 @@ int main(void) {
     assert ws >= 512 * 4096 + 2 * 512 + 256 * 512 and st == 512 * 8192 * 2 and gw > 0
     assert [int(x) for x in ln[2:7]] == [-1, -1, 0, -1, -1]
     assert ln[7] == "1" and ln[8] == "MixQ 1 1" and ln[9] == "[has-error-text]"
+
+
+def test_fat_tile_plan_invariants(lib):
+    """mixq_debug_fat_plan (host arithmetic of the decode fat-tile schedule, csrc/gemm_i8_tcgen05.cu plan_fat) over the
+    benchmarked shapes and random ones: the tile fits TMEM (int32 accumulators + parked fp16 outlier product), the UMMA N
+    granularity holds, the column tiles cover N, the ring has at least three stages and fits 227 KB next to the epilogue
+    staging, and the wave count is what the tile count says."""
+    import random
+    rng = random.Random(5)
+    shapes = [(512, 12288, 0), (512, 11008, 1), (512, 4096, 0), (512, 18944, 1), (512, 4608, 0), (512, 1280, 0), (512, 3584, 1),
+              (1024, 28672, 1), (129, 16, 0), (300, 8, 1)]
+    shapes += [(rng.randint(129, 1024), 8 * rng.randint(1, 4096), rng.randint(0, 1)) for _ in range(300)]
+    out = (ctypes.c_int * 5)()
+    for M, N, gated in shapes:
+        for pairs in (74, 37, 20, 1):
+            for ew in (8, 12):
+                assert lib.mixq_debug_fat_plan(M, N, pairs, gated, ew, out) == 0
+                Nt, n_tiles, m_tiles, stages, waves = list(out)
+                cols = 2 * N if gated else N                      # accumulator columns of the whole problem
+                assert Nt % (32 if gated else 16) == 0 and 16 <= Nt <= 336
+                assert Nt + Nt // 2 <= 512
+                assert n_tiles * Nt >= cols and (n_tiles - 1) * Nt < cols
+                assert m_tiles == (M + 255) // 256
+                assert waves == -(-(m_tiles * n_tiles) // pairs)
+                stage_bytes = 128 * 128 + (Nt // 2) * 128
+                fixed = 3072 + 512 + ew * 2 * 2048
+                assert stages >= 3 and stages <= 8
+                assert 1024 + stages * stage_bytes + fixed <= 227 * 1024
+    assert lib.mixq_debug_fat_plan(512, 4096, 74, 0, 10, out) == -1     # 8 or 12 epilogue warps only
+    assert lib.mixq_debug_fat_plan(512, 4096, 0, 0, 8, out) == -1
