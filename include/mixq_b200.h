@@ -295,6 +295,10 @@ int mixq_debug_set_trace(void* dev_buf);
  * invariants (Nt + Nt/2 <= 512 TMEM columns, the tiles cover N, the ring fits shared memory) over random shapes. */
 int mixq_debug_fat_plan(int64_t M, int64_t N, int pairs, int gated, int epi_warps, int* out5);
 
+/* Debug only (host arithmetic): byte offset inside `dev_scratch` of the part the `call_index`-th queued host-buffer
+ * call of a sequence takes, for a call that needs `need` bytes of a scratch of `scratch_bytes`; -1 if it does not fit. */
+int64_t mixq_debug_host_part_offset(size_t need, size_t scratch_bytes, unsigned call_index);
+
 /* ---- per-call tuning ------------------------------------------------------------------------------------------
  * The library keeps no mutable process-wide state (SURVEY.md 8b "no static mutable state"): a caller that wants a
  * particular tile configuration, or wants to leave SMs free for a concurrent communication kernel, says so on the

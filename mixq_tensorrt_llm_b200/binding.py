@@ -26,7 +26,7 @@ EXPORTS = [
     "mixq_allreduce_staging_size", "mixq_allreduce_counter_size", "mixq_allreduce_check", "mixq_enqueue_allreduce", "mixq_gemm_dequant_allreduce",
     "mixq_enqueue_opt", "mixq_gemm_dequant_opt", "mixq_enqueue_allreduce_opt", "mixq_gemm_dequant_allreduce_opt",
     "mixq_decode_workspace_size",
-    "mixq_launch_count", "mixq_debug_set_trace", "mixq_debug_fat_plan", "initOpenAiTritonPlugins", "mixq_plugin_create",
+    "mixq_launch_count", "mixq_debug_set_trace", "mixq_debug_fat_plan", "mixq_debug_host_part_offset", "initOpenAiTritonPlugins", "mixq_plugin_create",
     "mixq_plugin_deserialize", "mixq_plugin_clone", "mixq_plugin_destroy", "mixq_plugin_type",
     "mixq_plugin_version", "mixq_plugin_namespace", "mixq_plugin_nb_outputs",
     "mixq_plugin_serialization_size", "mixq_plugin_serialize", "mixq_plugin_supports_format",
@@ -122,6 +122,8 @@ def load() -> ctypes.CDLL:
     L.mixq_linears_host.argtypes = [ctypes.POINTER(ctypes.POINTER(Tensors)), ci, vp, ctypes.POINTER(vp), i64, ctypes.POINTER(i64), i64,
                                     vp, sz, u32, vp]
     L.mixq_host_drain.restype = ci
+    L.mixq_debug_host_part_offset.restype = i64
+    L.mixq_debug_host_part_offset.argtypes = [sz, sz, u32]
     L.mixq_debug_fat_plan.restype = ci
     L.mixq_debug_fat_plan.argtypes = [i64, i64, ci, ci, ci, ctypes.POINTER(ci)]
     L.mixq_host_drain.argtypes = [vp]

@@ -397,6 +397,13 @@ HostPipe& host_pipe() {
 }  // namespace
 
 namespace {
+// Queued host-buffer calls: a scratch of k (2..4) times the call's size is cut into k equal parts, taken in turn
+size_t host_part_offset(size_t need, size_t scratch_bytes, unsigned call_index) {
+    size_t k = scratch_bytes / align_up(need);
+    k = k > 4 ? 4 : k;
+    return k >= 2 ? (call_index % k) * (scratch_bytes / k / kAlign * kAlign) : 0;
+}
+
 // gated: t[0] / t[1] are the gate / up projections of one MLP, ONE output Out_host[0] [M, N[0]] (mixq_enqueue_gated per slab)
 int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_host, void* const* Out_host, int64_t M,
                       const int64_t* N, int64_t K, void* dev_scratch, size_t dev_scratch_bytes, unsigned flags, void* stream,
@@ -421,14 +428,9 @@ int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_hos
     // scratch differently: what a call waits for is decided by byte ranges, not by part numbers.
     const bool async = (flags & MIXQ_FLAG_HOST_ASYNC) != 0;
     flags &= ~static_cast<unsigned>(MIXQ_FLAG_HOST_ASYNC);
-    size_t part_off = 0;
-    if (async) {
-        size_t k = dev_scratch_bytes / align_up(need);
-        k = k > 4 ? 4 : k;
-        if (k >= 2) part_off = (hp.n_async % k) * (dev_scratch_bytes / k / kAlign * kAlign);
-    }
+    const size_t part_off = async ? host_part_offset(need, dev_scratch_bytes, hp.n_async) : 0;
     uintptr_t base = (reinterpret_cast<uintptr_t>(dev_scratch) + part_off + kAlign - 1) / kAlign * kAlign;
-    const uintptr_t range_begin = base, range_end = base + need;
+    const uintptr_t range_begin = base, range_end = base + need - kAlign;   // `need` carries kAlign bytes of slack for the alignment of base
     uint8_t* dA = reinterpret_cast<uint8_t*>(base);
     uint8_t* dOut[8];
     uint8_t* cur = dA + align_up(static_cast<size_t>(M) * K * 2);
@@ -531,6 +533,11 @@ int linears_host_impl(const mixq_tensors* const* t, int count, const void* A_hos
     return MIXQ_OK;
 }
 }  // namespace
+
+extern "C" int64_t mixq_debug_host_part_offset(size_t need, size_t scratch_bytes, unsigned call_index) {
+    if (need == 0 || scratch_bytes < need) return -1;
+    return static_cast<int64_t>(host_part_offset(need, scratch_bytes, call_index));
+}
 
 extern "C" int mixq_host_drain(void* stream) {
     HostPipe& hp = host_pipe();

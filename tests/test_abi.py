@@ -301,3 +301,25 @@ def test_fat_tile_plan_invariants(lib):
                 assert 1024 + stages * stage_bytes + fixed <= 227 * 1024
     assert lib.mixq_debug_fat_plan(512, 4096, 74, 0, 10, out) == -1     # 8 or 12 epilogue warps only
     assert lib.mixq_debug_fat_plan(512, 4096, 0, 0, 8, out) == -1
+
+
+def test_host_scratch_parts(lib):
+    """Queued host-buffer calls (MIXQ_FLAG_HOST_ASYNC): the parts of the scratch that consecutive calls take never run past
+    its end, do not overlap for calls of one size, are 128-byte aligned, and there are at most four of them."""
+    import random
+    rng = random.Random(9)
+    for _ in range(400):
+        need = rng.randint(1, 1 << 26)
+        k_given = rng.choice([1.0, 1.5, 2.0, 2.7, 3.0, 4.0, 7.5])
+        total = int(need * k_given) + rng.randint(0, 4096)
+        offs = [lib.mixq_debug_host_part_offset(need, total, i) for i in range(9)]
+        aligned_need = (need + 127) // 128 * 128
+        k = min(4, total // aligned_need)
+        distinct = sorted(set(offs))
+        assert len(distinct) == (k if k >= 2 else 1)
+        assert offs[:len(distinct)] == distinct and offs[len(distinct)] == offs[0]        # taken in turn
+        for o in distinct:
+            assert o % 128 == 0 and o + 127 + need <= total + 127                        # (+ the alignment slack `need` includes)
+        for o1, o2 in zip(distinct, distinct[1:]):
+            assert o2 - o1 >= aligned_need
+    assert lib.mixq_debug_host_part_offset(100, 50, 0) == -1
