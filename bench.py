@@ -985,7 +985,7 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="decoder layers per step (0 = the workload's default)")
     ap.add_argument("--cpu-sample-tokens", type=int, default=512, help="tokens per step of the --impl reference arm")
     ap.add_argument("--cpu-baseline-tokens", type=int, default=4096, help="token sample of the cpu_baseline leg of our arm")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--peak-sustained-s", type=float, default=2.0, help="length of the sustained INT8 peak measurement")
     ap.add_argument("--tp-chunks", type=int, default=4, help="row slabs per row-parallel linear (comm/compute overlap)")
     ap.add_argument("--comm-sms", type=int, default=40, help="SMs left free for NCCL when slabs overlap (tensor parallel only)")
